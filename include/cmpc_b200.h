@@ -1,0 +1,156 @@
+/* cmpc_b200 — C-ABI of the B200-native batched convex-MPC engine.
+ *
+ * Drop-in boundary for the reference's dense solve_mpc path
+ * (be2r_cmpc_unitree/src/controllers/convexMPC).  Two groups of entry points:
+ *
+ *  1. The reference's own C interface, symbol for symbol
+ *     (convexMPC_interface.h:44-52).  A controller that links this library
+ *     instead of convexMPC_interface.cpp + SolverMPC.cpp keeps compiling and
+ *     gets one MPC instance solved on the GPU per update_problem_data* call.
+ *  2. cmpc_batch_*: the batched engine those wrappers sit on — many independent
+ *     MPC instances (robot state, gait contact schedule, disturbance estimate)
+ *     solved by one kernel launch.
+ *
+ * Plain pointers and sizes only; no CUDA or torch types.  Every function is
+ * host-callable, returns 0 on success or a negative CMPC_E_* code, and fails
+ * loudly (no CPU fallback) when no CUDA device is usable.
+ */
+#ifndef CMPC_B200_H
+#define CMPC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMPC_MAX_HORIZON 19 /* SolverMPC.cpp:113 "horizon is too long" */
+#define CMPC_ADAPT_WINDOW 400 /* SolverMPC.cpp:704 */
+
+enum {
+  CMPC_OK = 0,
+  CMPC_E_ARG = -1,     /* bad argument (horizon out of range, null pointer, count > capacity) */
+  CMPC_E_CUDA = -2,    /* CUDA runtime error; cmpc_last_error() has the text */
+  CMPC_E_NODEVICE = -3,/* no CUDA device / kernel image not loadable: there is no CPU path */
+  CMPC_E_STATE = -4    /* call order violated (solve before setup/upload) */
+};
+
+/* per-instance solver status written by the kernel */
+enum {
+  CMPC_ST_SOLVED = 0,     /* optimum found */
+  CMPC_ST_EMPTY = 1,      /* no foot in contact over the horizon: forces are all zero */
+  CMPC_ST_MAXITER = 2,    /* active-set iteration cap hit */
+  CMPC_ST_INFEASIBLE = 3, /* cannot happen for this constraint set; kept for diagnostics */
+  CMPC_ST_WSOVERFLOW = 4, /* working set outgrew the launch's capacity tier; the engine re-solves
+                             these with the full-capacity kernel before returning */
+  CMPC_ST_CAPACITY = 5    /* instance has more contact foot-steps than the launch was sized for
+                             (only reachable through cmpc_batch_set_count with a wrong bound) */
+};
+
+/* ------------------------------------------------------------------------
+ * 1. reference interface (convexMPC_interface.h)
+ * ---------------------------------------------------------------------- */
+/* convexMPC_interface.h:44 / convexMPC_interface.cpp:44 */
+void setup_problem(double dt, int horizon, double mu, double f_max);
+/* convexMPC_interface.h:45 / convexMPC_interface.cpp:89 — solves on return */
+void update_problem_data(double* p, double* v, double* q, double* w, double* r, double yaw, double* weights,
+                         double* state_trajectory, double alpha, int* gait);
+/* convexMPC_interface.h:48 / convexMPC_interface.cpp:132 — solves on return */
+void update_problem_data_floats(float* p, float* v, float* q, float* w, float* r, float roll, float pitch,
+                                float yaw, float* weights, float* state_trajectory, float alpha, int* gait);
+/* convexMPC_interface.h:46 / convexMPC_interface.cpp:156 */
+double get_solution(int index);
+/* convexMPC_interface.h:47 / convexMPC_interface.cpp:109.  The JCQP (ADMM)
+ * settings are accepted and ignored: the GPU path always returns the exact
+ * active-set optimum that the use_jcqp == 0 (qpOASES) branch computes. */
+void update_solver_settings(int max_iter, double rho, double sigma, double solver_alpha, double terminate,
+                            double use_jcqp);
+/* convexMPC_interface.h:52 / convexMPC_interface.cpp:151 */
+void update_x_drag(float x_drag);
+/* The reference hands the adaptive hook its inputs through two globals,
+ * `Eigen::Matrix<float,6,1> f_ext` (convexMPC_interface.h:54, written at
+ * ConvexMPCLocomotion.cpp:771) and `float simulation_time`
+ * (be2r_cmpc_unitree.hpp:156).  A C-ABI cannot export an Eigen object, so the
+ * controller calls these two setters where it used to assign the globals. */
+void cmpc_set_external_force(const float f_ext[6]);
+void cmpc_set_simulation_time(float t);
+/* f_est after the last solve (SolverMPC.h:76 `extern f_est`) */
+void cmpc_get_disturbance_estimate(float f_est[6]);
+
+/* ------------------------------------------------------------------------
+ * 2. batched engine
+ * ---------------------------------------------------------------------- */
+typedef struct cmpc_batch cmpc_batch;
+
+/* Host-side view of one batch of inputs, structure-of-arrays, instance-major.
+ * Field meaning is update_data_t's (convexMPC_interface.h:23-42). */
+typedef struct {
+  const float* p;        /* [count][3]  */
+  const float* v;        /* [count][3]  */
+  const float* q;        /* [count][4]  w,x,y,z */
+  const float* w;        /* [count][3]  */
+  const float* r;        /* [count][12] r[axis*4+leg] */
+  const float* weights;  /* [count][12] */
+  const float* traj;     /* [count][12*horizon] */
+  const float* alpha;    /* [count] */
+  const uint8_t* gait;   /* [count][4*horizon] gait[step*4+leg] */
+  const float* x_drag;   /* [count] */
+  const float* f_dist;   /* [count][6] disturbance estimate xi applied as Q_qp*xi in g
+                            (SolverMPC.cpp:810); NULL = zeros (SolverMPC.cpp:813) */
+} cmpc_inputs;
+
+typedef struct {
+  double* forces;     /* [count][12*horizon] q_soln (zeros for swing feet); may be NULL */
+  double* objective;  /* [count] 0.5 x'Hx + g'x of the reduced QP; may be NULL */
+  int32_t* status;    /* [count] CMPC_ST_*; may be NULL */
+  int32_t* iterations;/* [count] working-set changes (qpOASES' nWSR analogue); may be NULL */
+  int8_t* active;     /* [count][20*horizon] primal activity of fmat rows: -1 lower, 0, +1 upper; may be NULL */
+} cmpc_outputs;
+
+int cmpc_device_count(void);
+const char* cmpc_last_error(void);
+
+int cmpc_batch_create(cmpc_batch** out, int device, int capacity);
+void cmpc_batch_destroy(cmpc_batch* b);
+/* setup_problem for the whole batch.  mass/inertia NULL-able: defaults are the
+ * reference's hard-coded 12 kg and diag(.07,.26,.242) (RobotState.h:24, RobotState.cpp:49). */
+int cmpc_batch_setup(cmpc_batch* b, double dt, int horizon, double mu, double f_max);
+int cmpc_batch_set_robot(cmpc_batch* b, double mass, const double inertia_diag[3]);
+/* Pack `count` host instances into pinned records and copy them to the device (async on the batch stream). */
+int cmpc_batch_upload(cmpc_batch* b, int count, const cmpc_inputs* in);
+/* Launch the fused condensation + QP kernel over the uploaded instances (async). */
+int cmpc_batch_solve(cmpc_batch* b);
+/* Copy results back and wait. */
+int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out);
+/* upload + solve + download: the end-to-end call with host buffers. */
+int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const cmpc_outputs* out);
+int cmpc_batch_sync(cmpc_batch* b);
+
+/* Adaptive-MPC periodic disturbance estimation fused into the solve launch
+ * (SolverMPC.cpp:688-798).  windows_t/windows_d hold, per instance, the last
+ * CMPC_ADAPT_WINDOW samples of time and f_ext[3]; sim_time is the time the
+ * compensating force is evaluated at.  mode 0: estimate only (history 400..500
+ * samples, g sees no disturbance); mode 1: estimate and apply xi in g in the
+ * same launch.  Pass NULL windows to switch the stage off again. */
+int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows_t, const float* windows_d,
+                                  const float* sim_time, int mode);
+/* est[count][4] = stat, amp, freq(Hz), phase; f_est[count][6] */
+int cmpc_batch_download_disturbance(cmpc_batch* b, double* est, float* f_est);
+
+/* Device-resident access for callers that generate or keep inputs in HBM
+ * (bench `value` path, multi-GPU shards): record layout is documented in
+ * DESIGN.md; pointers are CUDA device pointers carried as void*. */
+int cmpc_batch_device_records(cmpc_batch* b, void** records, size_t* stride_bytes);
+int cmpc_batch_device_forces(cmpc_batch* b, void** forces);
+/* Re-use the last uploaded instances: mark `count` records as present without copying. */
+int cmpc_batch_set_count(cmpc_batch* b, int count, int max_contact_feet);
+/* Timing helpers (CUDA events on the batch stream): ms of the last solve launch(es). */
+int cmpc_batch_last_solve_ms(cmpc_batch* b, float* ms);
+int cmpc_batch_kernel_launches(cmpc_batch* b, long long* launches);
+/* Algorithmic FP64 flop count of the last solve, accumulated by the kernel from its own loop counters. */
+int cmpc_batch_last_flops(cmpc_batch* b, double* flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,187 @@
+"""ctypes binding of the C-ABI in include/cmpc_b200.h (libcmpc_b200.so).
+
+There is no CPU path: every call below ends in the CUDA library, and loading
+or using it without a usable B200 raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libcmpc_b200.so")
+
+ST_SOLVED, ST_EMPTY, ST_MAXITER, ST_INFEASIBLE, ST_WSOVERFLOW, ST_CAPACITY = range(6)
+
+
+class Inputs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in
+                ("p", "v", "q", "w", "r", "weights", "traj", "alpha", "gait", "x_drag", "f_dist")]
+
+
+class Outputs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("forces", "objective", "status", "iterations", "active")]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libcmpc_b200.so is not built: run __graft_entry__.build() (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        L.cmpc_last_error.restype = C.c_char_p
+        L.cmpc_batch_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+        L.cmpc_batch_destroy.argtypes = [C.c_void_p]
+        L.cmpc_batch_setup.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double]
+        L.cmpc_batch_set_robot.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+        L.cmpc_batch_upload.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs)]
+        L.cmpc_batch_solve.argtypes = [C.c_void_p]
+        L.cmpc_batch_sync.argtypes = [C.c_void_p]
+        L.cmpc_batch_download.argtypes = [C.c_void_p, C.POINTER(Outputs)]
+        L.cmpc_batch_solve_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(Outputs)]
+        L.cmpc_batch_upload_disturbance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.cmpc_batch_download_disturbance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cmpc_batch_set_count.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cmpc_batch_last_solve_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.cmpc_batch_kernel_launches.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.cmpc_batch_last_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.cmpc_batch_device_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.cmpc_batch_device_forces.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.setup_problem.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double]
+        L.update_problem_data_floats.argtypes = [C.c_void_p] * 5 + [C.c_float] * 3 + [C.c_void_p] * 2 + [C.c_float,
+                                                                                                         C.c_void_p]
+        L.update_problem_data.argtypes = [C.c_void_p] * 5 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.get_solution.argtypes = [C.c_int]
+        L.get_solution.restype = C.c_double
+        L.update_x_drag.argtypes = [C.c_float]
+        L.update_solver_settings.argtypes = [C.c_int] + [C.c_double] * 5
+        L.cmpc_set_external_force.argtypes = [C.c_void_p]
+        L.cmpc_set_simulation_time.argtypes = [C.c_float]
+        L.cmpc_get_disturbance_estimate.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().cmpc_last_error().decode()))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Batch:
+    """Batched engine handle; mirrors setup_problem / update_problem_data / get_solution for many instances."""
+
+    def __init__(self, capacity, device=0):
+        self._h = C.c_void_p()
+        self.capacity = capacity
+        _check(lib().cmpc_batch_create(C.byref(self._h), device, capacity), "cmpc_batch_create")
+        self.horizon = 0
+        self.count = 0
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            lib().cmpc_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setup(self, dt, horizon, mu, f_max):
+        _check(lib().cmpc_batch_setup(self._h, dt, horizon, mu, f_max), "cmpc_batch_setup")
+        self.horizon = horizon
+
+    def set_robot(self, mass, inertia):
+        arr = (C.c_double * 3)(*inertia)
+        _check(lib().cmpc_batch_set_robot(self._h, mass, arr), "cmpc_batch_set_robot")
+
+    def _inputs(self, inst, count, f_dist=None):
+        f32 = lambda k: np.ascontiguousarray(inst[k][:count], dtype=np.float32)
+        arrs = {k: f32(k) for k in ("p", "v", "q", "w", "r", "weights", "traj", "alpha", "x_drag")}
+        arrs["gait"] = np.ascontiguousarray(inst["gait"][:count], dtype=np.uint8)
+        assert arrs["traj"].shape[1] == 12 * self.horizon and arrs["gait"].shape[1] == 4 * self.horizon
+        if f_dist is not None:
+            arrs["f_dist"] = np.ascontiguousarray(f_dist[:count], dtype=np.float32)
+        s = Inputs()
+        for k, a in arrs.items():
+            setattr(s, k, a.ctypes.data)
+        if f_dist is None:
+            s.f_dist = None
+        self._keep = arrs
+        return s
+
+    def upload(self, inst, count=None, f_dist=None):
+        count = len(inst["p"]) if count is None else count
+        s = self._inputs(inst, count, f_dist)
+        _check(lib().cmpc_batch_upload(self._h, count, C.byref(s)), "cmpc_batch_upload")
+        self.count = count
+
+    def solve(self):
+        _check(lib().cmpc_batch_solve(self._h), "cmpc_batch_solve")
+
+    def sync(self):
+        _check(lib().cmpc_batch_sync(self._h), "cmpc_batch_sync")
+
+    def _outputs(self, count, want_active=True):
+        h = self.horizon
+        res = {"forces": np.zeros((count, 12 * h)), "objective": np.zeros(count),
+               "status": np.zeros(count, dtype=np.int32), "iterations": np.zeros(count, dtype=np.int32)}
+        if want_active:
+            res["active"] = np.zeros((count, 20 * h), dtype=np.int8)
+        o = Outputs()
+        for k, a in res.items():
+            setattr(o, k, a.ctypes.data)
+        return o, res
+
+    def download(self, want_active=True):
+        o, res = self._outputs(self.count, want_active)
+        _check(lib().cmpc_batch_download(self._h, C.byref(o)), "cmpc_batch_download")
+        return res
+
+    def solve_host(self, inst, count=None, f_dist=None, want_active=True):
+        count = len(inst["p"]) if count is None else count
+        s = self._inputs(inst, count, f_dist)
+        o, res = self._outputs(count, want_active)
+        _check(lib().cmpc_batch_solve_host(self._h, count, C.byref(s), C.byref(o)), "cmpc_batch_solve_host")
+        self.count = count
+        return res
+
+    def last_solve_ms(self):
+        ms = C.c_float()
+        _check(lib().cmpc_batch_last_solve_ms(self._h, C.byref(ms)), "cmpc_batch_last_solve_ms")
+        return ms.value
+
+    def launches(self):
+        n = C.c_longlong()
+        _check(lib().cmpc_batch_kernel_launches(self._h, C.byref(n)), "cmpc_batch_kernel_launches")
+        return n.value
+
+    def last_flops(self):
+        f = C.c_double()
+        _check(lib().cmpc_batch_last_flops(self._h, C.byref(f)), "cmpc_batch_last_flops")
+        return f.value
+
+    def upload_disturbance(self, win_t, win_d, sim_time, mode):
+        if win_t is None:
+            _check(lib().cmpc_batch_upload_disturbance(self._h, 0, None, None, None, -1), "upload_disturbance")
+            return
+        wt = np.ascontiguousarray(win_t, dtype=np.float32)
+        wd = np.ascontiguousarray(win_d, dtype=np.float32)
+        stt = np.ascontiguousarray(sim_time, dtype=np.float32)
+        _check(lib().cmpc_batch_upload_disturbance(self._h, len(wt), _ptr(wt), _ptr(wd), _ptr(stt), mode),
+               "cmpc_batch_upload_disturbance")
+
+    def download_disturbance(self):
+        est = np.zeros((self.count, 4))
+        fest = np.zeros((self.count, 6), dtype=np.float32)
+        _check(lib().cmpc_batch_download_disturbance(self._h, _ptr(est), _ptr(fest)), "download_disturbance")
+        return est, fest

@@ -1,0 +1,536 @@
+// Host side of the C-ABI in include/cmpc_b200.h: the batched engine
+// (cmpc_batch_*) and, on top of it, the reference's single-instance interface
+// (convexMPC_interface.cpp:44-162) symbol for symbol.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cmpc_device.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail_cuda(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice ||
+          e == cudaErrorInvalidDeviceFunction)
+             ? CMPC_E_NODEVICE
+             : CMPC_E_CUDA;
+}
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+  } while (0)
+
+int fail_arg(const char* what) {
+  g_err = what;
+  return CMPC_E_ARG;
+}
+
+// horizon sums of the discretisation polynomials, DESIGN.md §3:
+//   c1(k) = dt, c2(k) = k dt^2 + dt^2/2, c3(k) = (k dt)^2 dt/2 + k dt^3/2 + dt^3/6
+//   sig_xy[a][b] = sum_{r=max(a,b)}^{h-1} cx(r-a) cy(r-b)
+void build_sigma(int h, double dt, std::vector<double>& sig) {
+  std::vector<double> c1(h), c2(h), c3(h);
+  for (int k = 0; k < h; k++) {
+    double tau = k * dt;
+    c1[k] = dt;
+    c2[k] = tau * dt + 0.5 * dt * dt;
+    c3[k] = 0.5 * tau * tau * dt + 0.5 * tau * dt * dt + dt * dt * dt / 6.0;
+  }
+  sig.assign((size_t)CMPC_SIG_COUNT * h * h, 0.0);
+  auto fill = [&](int t, const std::vector<double>& x, const std::vector<double>& y) {
+    for (int a = 0; a < h; a++)
+      for (int b = 0; b < h; b++) {
+        double s = 0;
+        for (int r = std::max(a, b); r < h; r++) s += x[r - a] * y[r - b];
+        sig[(size_t)t * h * h + a * h + b] = s;
+      }
+  };
+  fill(CMPC_SIG_11, c1, c1);
+  fill(CMPC_SIG_22, c2, c2);
+  fill(CMPC_SIG_33, c3, c3);
+  fill(CMPC_SIG_23, c2, c3);
+  fill(CMPC_SIG_12, c1, c2);
+}
+
+}  // namespace
+
+struct cmpc_batch {
+  int device = 0;
+  int capacity = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // problem setup
+  bool is_setup = false;
+  int h = 0;
+  int rec_stride = 0;
+  double dt = 0, mu = 0, f_max = 0;
+  double mass = 12.0;
+  double inertia[3] = {0.07, 0.26, 0.242};
+  // buffers (sized for capacity x CMPC_MAX_HORIZON so setup never reallocates)
+  unsigned char* h_rec = nullptr;  // pinned
+  unsigned char* d_rec = nullptr;
+  double* d_sigma = nullptr;
+  double* d_forces = nullptr;
+  double* d_obj = nullptr;
+  int* d_status = nullptr;
+  int* d_iters = nullptr;
+  signed char* d_active = nullptr;
+  int* d_overflow = nullptr;  // [capacity] list + [1] count at the end
+  unsigned long long* d_flops = nullptr;
+  float* d_win_t = nullptr;
+  float* d_win_d = nullptr;
+  double* d_est = nullptr;
+  float* d_fest = nullptr;
+  // pinned result staging
+  double* h_forces = nullptr;
+  double* h_obj = nullptr;
+  int* h_status = nullptr;
+  int* h_iters = nullptr;
+  signed char* h_active = nullptr;
+  unsigned long long* h_flops = nullptr;
+  // state
+  int count = 0;
+  int max_contact = 0;  // max contact foot-steps over the uploaded instances
+  int adapt_mode = -1;
+  int tpi = 64;
+  long long launches = 0;
+  bool timed = false;
+};
+
+extern "C" {
+
+const char* cmpc_last_error(void) { return g_err.c_str(); }
+
+int cmpc_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail_cuda(e, "cudaGetDeviceCount");
+    return 0;
+  }
+  return n;
+}
+
+int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
+  if (!out || capacity < 1) return fail_arg("cmpc_batch_create: bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_err = "cmpc_batch_create: no CUDA device (this engine has no CPU path)";
+    return CMPC_E_NODEVICE;
+  }
+  if (device < 0 || device >= ndev) return fail_arg("cmpc_batch_create: device out of range");
+  CK(cudaSetDevice(device));
+  cmpc_batch* b = new cmpc_batch();
+  b->device = device;
+  b->capacity = capacity;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  b->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&b->ev0));
+  CK(cudaEventCreate(&b->ev1));
+  const size_t cap = (size_t)capacity;
+  const int hm = CMPC_MAX_HORIZON;
+  const size_t rec_max = (size_t)cmpc_rec_stride(hm);
+  CK(cudaMallocHost(&b->h_rec, cap * rec_max));
+  CK(cudaMalloc(&b->d_rec, cap * rec_max));
+  CK(cudaMalloc(&b->d_sigma, sizeof(double) * CMPC_SIG_COUNT * hm * hm));
+  CK(cudaMalloc(&b->d_forces, sizeof(double) * cap * 12 * hm));
+  CK(cudaMalloc(&b->d_obj, sizeof(double) * cap));
+  CK(cudaMalloc(&b->d_status, sizeof(int) * cap));
+  CK(cudaMalloc(&b->d_iters, sizeof(int) * cap));
+  CK(cudaMalloc(&b->d_active, cap * 20 * hm));
+  CK(cudaMalloc(&b->d_overflow, sizeof(int) * (cap + 1)));
+  CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long)));
+  CK(cudaMallocHost(&b->h_forces, sizeof(double) * cap * 12 * hm));
+  CK(cudaMallocHost(&b->h_obj, sizeof(double) * cap));
+  CK(cudaMallocHost(&b->h_status, sizeof(int) * cap));
+  CK(cudaMallocHost(&b->h_iters, sizeof(int) * cap));
+  CK(cudaMallocHost(&b->h_active, cap * 20 * hm));
+  CK(cudaMallocHost(&b->h_flops, sizeof(unsigned long long)));
+  *b->h_flops = 0;
+  *out = b;
+  return CMPC_OK;
+}
+
+void cmpc_batch_destroy(cmpc_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  cudaStreamSynchronize(b->stream);
+  cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
+  cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_overflow); cudaFree(b->d_flops);
+  cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_est); cudaFree(b->d_fest);
+  cudaFreeHost(b->h_forces); cudaFreeHost(b->h_obj); cudaFreeHost(b->h_status); cudaFreeHost(b->h_iters);
+  cudaFreeHost(b->h_active); cudaFreeHost(b->h_flops);
+  cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
+  cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int cmpc_batch_setup(cmpc_batch* b, double dt, int horizon, double mu, double f_max) {
+  if (!b) return fail_arg("cmpc_batch_setup: null batch");
+  if (horizon < 1 || horizon > CMPC_MAX_HORIZON) return fail_arg("cmpc_batch_setup: horizon must be 1..19 (SolverMPC.cpp:113)");
+  if (!(mu > 0) || !(dt > 0)) return fail_arg("cmpc_batch_setup: dt and mu must be positive");
+  CK(cudaSetDevice(b->device));
+  const bool same = b->is_setup && b->h == horizon && b->dt == dt;
+  b->h = horizon;
+  b->dt = dt;
+  b->mu = mu;
+  b->f_max = f_max;
+  b->rec_stride = cmpc_rec_stride(horizon);
+  if (!same) {
+    // the reference narrows dt to float (problem_setup.dt, convexMPC_interface.h:17)
+    std::vector<double> sig;
+    build_sigma(horizon, (double)(float)dt, sig);
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpyAsync(b->d_sigma, sig.data(), sizeof(double) * sig.size(), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    b->count = 0;
+  }
+  b->is_setup = true;
+  return CMPC_OK;
+}
+
+int cmpc_batch_set_robot(cmpc_batch* b, double mass, const double inertia_diag[3]) {
+  if (!b || !(mass > 0)) return fail_arg("cmpc_batch_set_robot: bad arguments");
+  b->mass = mass;
+  if (inertia_diag)
+    for (int i = 0; i < 3; i++) b->inertia[i] = inertia_diag[i];
+  return CMPC_OK;
+}
+
+int cmpc_batch_upload(cmpc_batch* b, int count, const cmpc_inputs* in) {
+  if (!b || !in) return fail_arg("cmpc_batch_upload: null argument");
+  if (!b->is_setup) { g_err = "cmpc_batch_upload: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  if (count < 0 || count > b->capacity) return fail_arg("cmpc_batch_upload: count exceeds capacity");
+  if (!in->p || !in->v || !in->q || !in->w || !in->r || !in->weights || !in->traj || !in->alpha || !in->gait ||
+      !in->x_drag)
+    return fail_arg("cmpc_batch_upload: null input array");
+  CK(cudaSetDevice(b->device));
+  const int h = b->h, stride = b->rec_stride;
+  int maxc = 0;
+  for (int i = 0; i < count; i++) {
+    unsigned char* rec = b->h_rec + (size_t)i * stride;
+    float* f = reinterpret_cast<float*>(rec);
+    std::memcpy(f + CMPC_REC_P, in->p + 3 * (size_t)i, 12);
+    std::memcpy(f + CMPC_REC_V, in->v + 3 * (size_t)i, 12);
+    std::memcpy(f + CMPC_REC_Q, in->q + 4 * (size_t)i, 16);
+    std::memcpy(f + CMPC_REC_W, in->w + 3 * (size_t)i, 12);
+    std::memcpy(f + CMPC_REC_R, in->r + 12 * (size_t)i, 48);
+    std::memcpy(f + CMPC_REC_WEIGHTS, in->weights + 12 * (size_t)i, 48);
+    f[CMPC_REC_ALPHA] = in->alpha[i];
+    f[CMPC_REC_XDRAG] = in->x_drag[i];
+    if (in->f_dist) std::memcpy(f + CMPC_REC_FDIST, in->f_dist + 6 * (size_t)i, 24);
+    else std::memset(f + CMPC_REC_FDIST, 0, 24);
+    f[CMPC_REC_SIMTIME] = 0.f;
+    f[CMPC_REC_RSV] = 0.f;
+    f[CMPC_REC_RSV + 1] = 0.f;
+    std::memcpy(f + CMPC_REC_TRAJ, in->traj + 12 * (size_t)h * i, 48 * (size_t)h);
+    unsigned char* gz = rec + 4 * (CMPC_REC_TRAJ + 12 * h);
+    const unsigned char* gsrc = in->gait + 4 * (size_t)h * i;
+    int c = 0;
+    for (int k = 0; k < 4 * h; k++) {
+      gz[k] = gsrc[k];
+      double ub = (double)gsrc[k] * (double)(float)b->f_max;
+      c += !(ub < 0.01 && ub > -0.01);
+    }
+    for (int k = 4 * h; k < stride - 4 * (CMPC_REC_TRAJ + 12 * h); k++) gz[k] = 0;
+    maxc = std::max(maxc, c);
+  }
+  b->count = count;
+  b->max_contact = maxc;
+  if (count > 0)
+    CK(cudaMemcpyAsync(b->d_rec, b->h_rec, (size_t)count * stride, cudaMemcpyHostToDevice, b->stream));
+  return CMPC_OK;
+}
+
+int cmpc_batch_set_count(cmpc_batch* b, int count, int max_contact_feet) {
+  if (!b || count < 0 || count > b->capacity) return fail_arg("cmpc_batch_set_count: bad arguments");
+  if (!b->is_setup) { g_err = "cmpc_batch_set_count: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  if (max_contact_feet < 0 || max_contact_feet > 4 * b->h) return fail_arg("cmpc_batch_set_count: bad contact bound");
+  b->count = count;
+  b->max_contact = max_contact_feet;
+  return CMPC_OK;
+}
+
+int cmpc_batch_solve(cmpc_batch* b) {
+  if (!b) return fail_arg("cmpc_batch_solve: null batch");
+  if (!b->is_setup) { g_err = "cmpc_batch_solve: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  CK(cudaSetDevice(b->device));
+  CK(cudaEventRecord(b->ev0, b->stream));
+  CK(cudaMemsetAsync(b->d_flops, 0, sizeof(unsigned long long), b->stream));
+  if (b->count > 0) {
+    CmpcParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.horizon = b->h;
+    P.count = b->count;
+    P.rec_stride = b->rec_stride;
+    P.nmax = std::max(3, 3 * b->max_contact);
+    P.qcap = P.nmax;
+    P.max_iter = 20 * P.nmax + 100;
+    P.adapt_mode = b->adapt_mode;
+    P.dt = (double)(float)b->dt;
+    P.mu_inv = (double)(1.f / (float)b->mu);
+    P.f_max = (double)(float)b->f_max;
+    P.mass_inv = 1.0 / (double)(float)b->mass;
+    for (int i = 0; i < 3; i++) P.inertia[i] = (double)(float)b->inertia[i];
+    P.gravity = (double)(-9.8f);
+    P.tol_violation = 1e-9;
+    P.tol_active = 1e-6;
+    P.records = b->d_rec;
+    P.sigma = b->d_sigma;
+    P.worklist = nullptr;
+    P.overflow_list = b->d_overflow;
+    P.overflow_count = b->d_overflow + b->capacity;
+    P.forces = b->d_forces;
+    P.objective = b->d_obj;
+    P.status = b->d_status;
+    P.iterations = b->d_iters;
+    P.active = b->d_active;
+    P.flops = b->d_flops;
+    P.win_t = b->d_win_t;
+    P.win_d = b->d_win_d;
+    P.est = b->d_est;
+    P.f_est = b->d_fest;
+    const char* env_tpi = std::getenv("CMPC_TPI");
+    int tpi = env_tpi ? std::atoi(env_tpi) : b->tpi;
+    if (tpi != 32 && tpi != 64 && tpi != 128) tpi = 64;
+    size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap);
+    if (smem > 227 * 1024) {
+      g_err = "cmpc_batch_solve: instance too large for shared memory (n=" + std::to_string(P.nmax) + ")";
+      return CMPC_E_ARG;
+    }
+    int per_sm = cmpc_max_ctas_per_sm(tpi, smem);
+    if (per_sm < 1) {
+      g_err = "cmpc_batch_solve: kernel not launchable on this device (no sm_100a image?)";
+      return CMPC_E_NODEVICE;
+    }
+    int grid = std::min(b->count, b->sm_count * per_sm);
+    int rc = cmpc_launch_solve(P, tpi, grid, b->stream);
+    if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_solve_kernel launch");
+    b->launches++;
+  }
+  CK(cudaEventRecord(b->ev1, b->stream));
+  b->timed = true;
+  return CMPC_OK;
+}
+
+int cmpc_batch_sync(cmpc_batch* b) {
+  if (!b) return fail_arg("cmpc_batch_sync: null batch");
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  return CMPC_OK;
+}
+
+int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out) {
+  if (!b || !out) return fail_arg("cmpc_batch_download: null argument");
+  CK(cudaSetDevice(b->device));
+  const size_t n = (size_t)b->count;
+  const int h = b->h;
+  if (n > 0) {
+    if (out->forces) CK(cudaMemcpyAsync(b->h_forces, b->d_forces, sizeof(double) * n * 12 * h, cudaMemcpyDeviceToHost, b->stream));
+    if (out->objective) CK(cudaMemcpyAsync(b->h_obj, b->d_obj, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+    if (out->status) CK(cudaMemcpyAsync(b->h_status, b->d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, b->stream));
+    if (out->iterations) CK(cudaMemcpyAsync(b->h_iters, b->d_iters, sizeof(int) * n, cudaMemcpyDeviceToHost, b->stream));
+    if (out->active) CK(cudaMemcpyAsync(b->h_active, b->d_active, n * 20 * h, cudaMemcpyDeviceToHost, b->stream));
+  }
+  CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  if (n > 0) {
+    if (out->forces) std::memcpy(out->forces, b->h_forces, sizeof(double) * n * 12 * h);
+    if (out->objective) std::memcpy(out->objective, b->h_obj, sizeof(double) * n);
+    if (out->status) std::memcpy(out->status, b->h_status, sizeof(int) * n);
+    if (out->iterations) std::memcpy(out->iterations, b->h_iters, sizeof(int) * n);
+    if (out->active) std::memcpy(out->active, b->h_active, n * 20 * h);
+  }
+  return CMPC_OK;
+}
+
+int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const cmpc_outputs* out) {
+  int rc = cmpc_batch_upload(b, count, in);
+  if (rc) return rc;
+  rc = cmpc_batch_solve(b);
+  if (rc) return rc;
+  return cmpc_batch_download(b, out);
+}
+
+int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows_t, const float* windows_d,
+                                  const float* sim_time, int mode) {
+  (void)count; (void)windows_t; (void)windows_d; (void)sim_time; (void)mode;
+  if (!b) return fail_arg("cmpc_batch_upload_disturbance: null batch");
+  g_err = "cmpc_batch_upload_disturbance: estimator stage not built yet";
+  return CMPC_E_STATE;
+}
+
+int cmpc_batch_download_disturbance(cmpc_batch* b, double* est, float* f_est) {
+  (void)est; (void)f_est;
+  if (!b) return fail_arg("cmpc_batch_download_disturbance: null batch");
+  g_err = "cmpc_batch_download_disturbance: estimator stage not built yet";
+  return CMPC_E_STATE;
+}
+
+int cmpc_batch_device_records(cmpc_batch* b, void** records, size_t* stride_bytes) {
+  if (!b || !records || !stride_bytes) return fail_arg("cmpc_batch_device_records: null argument");
+  *records = b->d_rec;
+  *stride_bytes = (size_t)b->rec_stride;
+  return CMPC_OK;
+}
+
+int cmpc_batch_device_forces(cmpc_batch* b, void** forces) {
+  if (!b || !forces) return fail_arg("cmpc_batch_device_forces: null argument");
+  *forces = b->d_forces;
+  return CMPC_OK;
+}
+
+int cmpc_batch_last_solve_ms(cmpc_batch* b, float* ms) {
+  if (!b || !ms) return fail_arg("cmpc_batch_last_solve_ms: null argument");
+  if (!b->timed) { g_err = "cmpc_batch_last_solve_ms: nothing solved yet"; return CMPC_E_STATE; }
+  CK(cudaSetDevice(b->device));
+  CK(cudaEventSynchronize(b->ev1));
+  CK(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+  return CMPC_OK;
+}
+
+int cmpc_batch_kernel_launches(cmpc_batch* b, long long* launches) {
+  if (!b || !launches) return fail_arg("cmpc_batch_kernel_launches: null argument");
+  *launches = b->launches;
+  return CMPC_OK;
+}
+
+int cmpc_batch_last_flops(cmpc_batch* b, double* flops) {
+  if (!b || !flops) return fail_arg("cmpc_batch_last_flops: null argument");
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  *flops = (double)*b->h_flops;
+  return CMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// reference single-instance interface (convexMPC_interface.cpp)
+// ---------------------------------------------------------------------------
+namespace {
+struct Single {
+  std::mutex mu;
+  cmpc_batch* b = nullptr;
+  int horizon = 0;
+  bool has_solved = false;
+  float x_drag = 0.f;
+  float f_ext[6] = {0, 0, 0, 0, 0, 0};
+  float sim_time = 0.f;
+  float f_est[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<double> q_soln;
+};
+Single& single() {
+  static Single s;
+  return s;
+}
+void die(const char* where) {
+  std::fprintf(stderr, "[cmpc_b200] %s failed: %s\n", where, cmpc_last_error());
+  std::abort();  // no CPU fallback: a controller must not keep running on stale forces
+}
+}  // namespace
+
+void setup_problem(double dt, int horizon, double mu, double f_max) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (!s.b) {
+    const char* dev = std::getenv("CMPC_DEVICE");
+    if (cmpc_batch_create(&s.b, dev ? std::atoi(dev) : 0, 1) != CMPC_OK) die("setup_problem/cmpc_batch_create");
+  }
+  if (cmpc_batch_setup(s.b, dt, horizon, mu, f_max) != CMPC_OK) die("setup_problem");
+  s.horizon = horizon;
+  s.q_soln.assign(12 * horizon, 0.0);
+}
+
+static void solve_single(Single& s, const float* p, const float* v, const float* q, const float* w, const float* r,
+                         const float* weights, const float* traj, float alpha, const int* gait) {
+  if (!s.b) die("update_problem_data before setup_problem");
+  const int h = s.horizon;
+  std::vector<unsigned char> g8(4 * h);
+  for (int i = 0; i < 4 * h; i++) g8[i] = (unsigned char)gait[i];  // mint_to_u8, convexMPC_interface.cpp:76
+  float fd[6] = {0, 0, 0, 0, 0, 0};
+  cmpc_inputs in;
+  in.p = p; in.v = v; in.q = q; in.w = w; in.r = r; in.weights = weights; in.traj = traj;
+  in.alpha = &alpha; in.gait = g8.data(); in.x_drag = &s.x_drag; in.f_dist = fd;
+  cmpc_outputs out;
+  std::memset(&out, 0, sizeof(out));
+  out.forces = s.q_soln.data();
+  if (cmpc_batch_solve_host(s.b, 1, &in, &out) != CMPC_OK) die("update_problem_data");
+  s.has_solved = true;
+}
+
+void update_problem_data(double* p, double* v, double* q, double* w, double* r, double yaw, double* weights,
+                         double* state_trajectory, double alpha, int* gait) {
+  (void)yaw;
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  const int h = s.horizon;
+  float pf[3], vf[3], qf[4], wf[3], rf[12], wt[12];
+  std::vector<float> tr(12 * std::max(h, 1));
+  for (int i = 0; i < 3; i++) { pf[i] = (float)p[i]; vf[i] = (float)v[i]; wf[i] = (float)w[i]; }
+  for (int i = 0; i < 4; i++) qf[i] = (float)q[i];
+  for (int i = 0; i < 12; i++) { rf[i] = (float)r[i]; wt[i] = (float)weights[i]; }
+  for (int i = 0; i < 12 * h; i++) tr[i] = (float)state_trajectory[i];
+  solve_single(s, pf, vf, qf, wf, rf, wt, tr.data(), (float)alpha, gait);
+}
+
+void update_problem_data_floats(float* p, float* v, float* q, float* w, float* r, float roll, float pitch, float yaw,
+                                float* weights, float* state_trajectory, float alpha, int* gait) {
+  (void)roll; (void)pitch; (void)yaw;  // carried by update_data_t but unused by solve_mpc (RobotState.cpp:46)
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  solve_single(s, p, v, q, w, r, weights, state_trajectory, alpha, gait);
+}
+
+double get_solution(int index) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (!s.has_solved) return 0.0;  // convexMPC_interface.cpp:158
+  if (index < 0 || index >= (int)s.q_soln.size()) return 0.0;
+  return s.q_soln[index];
+}
+
+void update_solver_settings(int max_iter, double rho, double sigma, double solver_alpha, double terminate,
+                            double use_jcqp) {
+  (void)max_iter; (void)rho; (void)sigma; (void)solver_alpha; (void)terminate; (void)use_jcqp;
+}
+
+void update_x_drag(float x_drag) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  s.x_drag = x_drag;
+}
+
+void cmpc_set_external_force(const float f_ext[6]) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  for (int i = 0; i < 6; i++) s.f_ext[i] = f_ext[i];
+}
+
+void cmpc_set_simulation_time(float t) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  s.sim_time = t;
+}
+
+void cmpc_get_disturbance_estimate(float f_est[6]) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  for (int i = 0; i < 6; i++) f_est[i] = s.f_est[i];
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Shared host/device definitions of the batched convex-MPC engine.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/cmpc_b200.h"
+
+#define CMPC_MAX_FS 80 /* 4 * CMPC_MAX_HORIZON rounded up */
+
+// ---------------------------------------------------------------------------
+// Instance record (HBM, one per MPC instance, 16-byte aligned, fetched with a
+// single cp.async.bulk per instance).  Offsets in floats.  Field meaning is
+// update_data_t's (convexMPC_interface.h:23-42).
+// ---------------------------------------------------------------------------
+#define CMPC_REC_P 0         // p[3]
+#define CMPC_REC_V 3         // v[3]
+#define CMPC_REC_Q 6         // q[4]  w,x,y,z
+#define CMPC_REC_W 10        // w[3]
+#define CMPC_REC_R 13        // r[12] r[axis*4+leg]
+#define CMPC_REC_WEIGHTS 25  // weights[12]
+#define CMPC_REC_ALPHA 37
+#define CMPC_REC_XDRAG 38
+#define CMPC_REC_FDIST 39    // xi[6]: torque xyz, force xyz (SolverMPC.cpp:795)
+#define CMPC_REC_SIMTIME 45
+#define CMPC_REC_RSV 46      // 2 floats reserved
+#define CMPC_REC_TRAJ 48     // traj[12*h], then gait bytes [4*h], padded to 16 B
+
+static inline int cmpc_rec_stride(int h) {
+  int bytes = 4 * (CMPC_REC_TRAJ + 12 * h) + 4 * h;
+  return (bytes + 15) & ~15;
+}
+
+// sigma tables: five h*h double tables of horizon sums, see DESIGN.md §3
+//   sig[t][a*h+b] = sum_{r=max(a,b)}^{h-1} cx(r-a) * cy(r-b)
+#define CMPC_SIG_11 0
+#define CMPC_SIG_22 1
+#define CMPC_SIG_33 2
+#define CMPC_SIG_23 3
+#define CMPC_SIG_12 4
+#define CMPC_SIG_COUNT 5
+
+struct CmpcParams {
+  int horizon;
+  int count;        // instances (or worklist entries) this launch covers
+  int rec_stride;   // bytes
+  int nmax;         // max reduced variable count in this launch (3 * contact foot-steps)
+  int qcap;         // working-set capacity of this launch
+  int max_iter;
+  int adapt_mode;   // -1 off, 0 estimate only, 1 estimate and apply
+  int pad0;
+  double dt;        // (double)(float)dt
+  double mu_inv;    // (double)(1.f/(float)mu)   SolverMPC.cpp:657
+  double f_max;     // (double)(float)f_max
+  double mass_inv;  // 1/(double)(float)m
+  double inertia[3];
+  double gravity;   // (double)(-9.8f)          SolverMPC.cpp:592
+  double tol_violation;
+  double tol_active;
+  const unsigned char* records;
+  const double* sigma;
+  const int* worklist;        // optional indirection (tier-2 launch); NULL = identity
+  int* overflow_list;         // instances whose working set outgrew qcap
+  int* overflow_count;
+  double* forces;             // [count][12h]
+  double* objective;          // [count]
+  int* status;                // [count]
+  int* iterations;            // [count]
+  signed char* active;        // [count][20h]
+  unsigned long long* flops;  // single counter, algorithmic flops
+  const float* win_t;         // [count][400] or NULL
+  const float* win_d;
+  double* est;                // [count][4]
+  float* f_est;               // [count][6]
+};
+
+#ifdef __CUDACC__
+template <int TPI>
+__global__ void cmpc_solve_kernel(const __grid_constant__ CmpcParams P);
+#endif
+
+size_t cmpc_smem_bytes(int horizon, int nmax, int qcap);
+int cmpc_launch_solve(const CmpcParams& P, int tpi, int grid, void* stream);
+int cmpc_max_ctas_per_sm(int tpi, size_t smem);

@@ -1,0 +1,658 @@
+// Fused condensation + dense QP kernel of the B200 batched convex-MPC engine.
+//
+// One CTA owns one MPC instance at a time (persistent grid-stride loop, next
+// instance record prefetched into shared memory by cp.async.bulk while the
+// current one is solved).  Per instance, entirely in shared memory / registers:
+//
+//   A. state build          RobotState::set + quat_to_rpy      RobotState.cpp:10, SolverMPC.cpp:352
+//   B. ct_ss_mats + c2qp    closed form of the 31x31 exp()      SolverMPC.cpp:96, :260
+//   C. H, g of the reduced  2(Bqp'SBqp + aI), 2Bqp'S(Aqp x0 +   SolverMPC.cpp:806-814 and the
+//      (contact-only) QP    Qqp xi - Xd), swing feet eliminated swing elimination at :859-950
+//   D. K = H^-1             symmetric sweep in place
+//   E. QP                   Goldfarb-Idnani dual active set,    replaces qpOASES, SolverMPC.cpp:955
+//                           range-space form on K
+//   F. q_soln scatter, objective, primal activity mask          SolverMPC.cpp:970-983
+//
+// All arithmetic is FP64 on FP32 inputs (the reference computes A..C in FP32
+// and hands qpOASES doubles).  DESIGN.md §3 derives the closed forms.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "cmpc_device.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// shared memory carve-up (same arithmetic on host and device)
+// ---------------------------------------------------------------------------
+struct Carve {
+  int rec0, rec1, bars, sig, small, evec, agg, fs, fsinv, K, g, x, kn, z, v, s, rc, isact, act, u, d, r, col, Pp,
+      red, total;
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_stride) {
+  Carve c;
+  int o = 0;
+  int nc = nmax / 3, m = 5 * nc;
+  c.rec0 = o; o += align16(rec_stride);
+  c.rec1 = o; o += align16(rec_stride);
+  c.bars = o; o += 16;
+  c.sig = o; o += align16(8 * CMPC_SIG_COUNT * h * h);
+  c.small = o; o += align16(8 * (36 + 36 + 144 + 144 + 16));  // W, RW, PT, PO, scalars
+  c.evec = o; o += align16(8 * 12 * h);
+  c.agg = o; o += align16(8 * 10 * h);
+  c.fs = o; o += align16(4 * CMPC_MAX_FS);
+  c.fsinv = o; o += align16(4 * CMPC_MAX_FS);
+  c.K = o; o += align16(8 * nmax * nmax);
+  c.g = o; o += align16(8 * nmax);
+  c.x = o; o += align16(8 * nmax);
+  c.kn = o; o += align16(8 * nmax);
+  c.z = o; o += align16(8 * nmax);
+  c.v = o; o += align16(8 * nmax);
+  c.s = o; o += align16(8 * m);
+  c.rc = o; o += align16(8 * m);
+  c.isact = o; o += align16(m);
+  c.act = o; o += align16(2 * (qcap + 1));
+  c.u = o; o += align16(8 * (qcap + 1));
+  c.d = o; o += align16(8 * (qcap + 1));
+  c.r = o; o += align16(8 * (qcap + 1));
+  c.col = o; o += align16(8 * (qcap + 1));
+  c.Pp = o; o += align16(8 * ((qcap + 1) * (qcap + 2) / 2));
+  c.red = o; o += 512;
+  c.total = o;
+  return c;
+}
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
+// block reductions (TPI <= 128)
+// ---------------------------------------------------------------------------
+template <int TPI>
+__device__ __forceinline__ void block_argmin(double& val, int& idx, double* red, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, val, o);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+  }
+  if (TPI > 32) {
+    int* redi = reinterpret_cast<int*>(red + 8);
+    __syncthreads();
+    if ((tid & 31) == 0) { red[tid >> 5] = val; redi[tid >> 5] = idx; }
+    __syncthreads();
+    val = red[0]; idx = redi[0];
+#pragma unroll
+    for (int w = 1; w < TPI / 32; w++) {
+      double ov = red[w]; int oi = redi[w];
+      if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+  }
+}
+
+template <int TPI>
+__device__ __forceinline__ double block_sum(double val, double* red, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+  if (TPI > 32) {
+    __syncthreads();
+    if ((tid & 31) == 0) red[16 + (tid >> 5)] = val;
+    __syncthreads();
+    val = red[16];
+#pragma unroll
+    for (int w = 1; w < TPI / 32; w++) val += red[16 + w];
+  }
+  return val;
+}
+
+// constraint c = 5j+t of the reduced problem as  s(x) = va*x[ia] + vz*x[iz] - b >= 0
+//   t=0:  x/mu + z >= 0   t=1: -x/mu + z >= 0   t=2:  y/mu + z >= 0   t=3: -y/mu + z >= 0
+//   t=4:  -z + ub >= 0    (fmat rows, SolverMPC.cpp:660; the row-4 lower side z >= 0 is implied by t=0,1)
+__device__ __forceinline__ void cons_of(int c, double mu_inv, int& ia, double& va, int& iz, double& vz) {
+  int j = c / 5, t = c - 5 * j;
+  iz = 3 * j + 2;
+  if (t == 4) { ia = iz; va = 0.0; vz = -1.0; }
+  else { ia = 3 * j + (t >> 1); va = (t & 1) ? -mu_inv : mu_inv; vz = 1.0; }
+}
+
+__device__ __forceinline__ double& psym(double* Pp, int k, int l) {
+  return (k >= l) ? Pp[k * (k + 1) / 2 + l] : Pp[l * (l + 1) / 2 + k];
+}
+
+}  // namespace
+
+template <int TPI>
+__global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__ CmpcParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int h = P.horizon;
+  const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride);
+  unsigned char* recbuf[2] = {smem + cv.rec0, smem + cv.rec1};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.bars);
+  double* sig = reinterpret_cast<double*>(smem + cv.sig);
+  double* sW = reinterpret_cast<double*>(smem + cv.small);  // W[4][3][3]
+  double* sRW = sW + 36;                                    // (R^T W)[4][3][3]
+  double* sPT = sRW + 36;                                   // PT[4][4][3][3]
+  double* sPO = sPT + 144;                                  // PO[4][4][3][3]
+  double* sScal = sPO + 144;                                // broadcast scalars
+  double* ev = reinterpret_cast<double*>(smem + cv.evec);   // e[h][12]
+  double* agg = reinterpret_cast<double*>(smem + cv.agg);   // agg[h][10]
+  int* fs = reinterpret_cast<int*>(smem + cv.fs);           // reduced foot-step -> global foot-step k
+  int* fsinv = reinterpret_cast<int*>(smem + cv.fsinv);     // global foot-step -> reduced or -1
+  double* K = reinterpret_cast<double*>(smem + cv.K);
+  double* g = reinterpret_cast<double*>(smem + cv.g);
+  double* x = reinterpret_cast<double*>(smem + cv.x);
+  double* kn = reinterpret_cast<double*>(smem + cv.kn);
+  double* z = reinterpret_cast<double*>(smem + cv.z);
+  double* vv = reinterpret_cast<double*>(smem + cv.v);
+  double* s = reinterpret_cast<double*>(smem + cv.s);
+  double* rc = reinterpret_cast<double*>(smem + cv.rc);
+  unsigned char* isact = smem + cv.isact;
+  short* act = reinterpret_cast<short*>(smem + cv.act);
+  double* u = reinterpret_cast<double*>(smem + cv.u);
+  double* dvec = reinterpret_cast<double*>(smem + cv.d);
+  double* rvec = reinterpret_cast<double*>(smem + cv.r);
+  double* col = reinterpret_cast<double*>(smem + cv.col);
+  double* Pp = reinterpret_cast<double*>(smem + cv.Pp);
+  double* red = reinterpret_cast<double*>(smem + cv.red);
+  int* redi = reinterpret_cast<int*>(red + 32);  // shared ints: [0]=nc
+
+  // horizon-sum tables: once per CTA
+  for (int i = tid; i < CMPC_SIG_COUNT * h * h; i += TPI) sig[i] = P.sigma[i];
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  uint32_t phase[2] = {0u, 0u};
+  int slot = blockIdx.x;
+  if (slot < P.count && tid == 0) {
+    int inst = P.worklist ? P.worklist[slot] : slot;
+    mbar_expect_tx(&bars[0], (uint32_t)P.rec_stride);
+    bulk_g2s(recbuf[0], P.records + (size_t)inst * P.rec_stride, (uint32_t)P.rec_stride, &bars[0]);
+  }
+
+  const double dt = P.dt, mu_inv = P.mu_inv, minv = P.mass_inv;
+  double flops_acc = 0.0;
+
+  for (int buf = 0; slot < P.count; slot += gridDim.x, buf ^= 1) {
+    const int inst = P.worklist ? P.worklist[slot] : slot;
+    // prefetch the next record while this one is solved
+    {
+      int nslot = slot + gridDim.x;
+      if (tid == 0 && nslot < P.count) {
+        int ninst = P.worklist ? P.worklist[nslot] : nslot;
+        fence_proxy_async();
+        mbar_expect_tx(&bars[buf ^ 1], (uint32_t)P.rec_stride);
+        bulk_g2s(recbuf[buf ^ 1], P.records + (size_t)ninst * P.rec_stride, (uint32_t)P.rec_stride, &bars[buf ^ 1]);
+      }
+    }
+    mbar_wait(&bars[buf], phase[buf]);
+    phase[buf] ^= 1u;
+    const float* rec = reinterpret_cast<const float*>(recbuf[buf]);
+    const unsigned char* gait = recbuf[buf] + 4 * (CMPC_REC_TRAJ + 12 * h);
+
+    // ---- A1. contact foot-steps (the reference keeps a foot-step unless its fz bound is ~0) ----
+    if (tid < 32) {
+      int cnt = 0;
+      for (int base = 0; base < 4 * h; base += 32) {
+        int k = base + tid;
+        bool keep = false;
+        if (k < 4 * h) {
+          double ub = (double)gait[k] * P.f_max;
+          keep = !(ub < 0.01 && ub > -0.01);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, keep);
+        int pos = cnt + __popc(mask & ((1u << tid) - 1u));
+        if (k < 4 * h) fsinv[k] = keep ? pos : -1;
+        if (keep) fs[pos] = k;
+        cnt += __popc(mask);
+      }
+      if (tid == 0) redi[0] = cnt;
+    }
+    // ---- A2. rotation, inertia, per-thread copies (cheap, avoids a round of syncs) ----
+    double R[9], Ii[9];
+    {
+      double qw = rec[CMPC_REC_Q + 0], qx = rec[CMPC_REC_Q + 1], qy = rec[CMPC_REC_Q + 2], qz = rec[CMPC_REC_Q + 3];
+      double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+      double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx;
+      double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+      R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+      R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+      R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+      double Iw[9];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          Iw[i * 3 + j] = R[i * 3 + 0] * P.inertia[0] * R[j * 3 + 0] + R[i * 3 + 1] * P.inertia[1] * R[j * 3 + 1] +
+                          R[i * 3 + 2] * P.inertia[2] * R[j * 3 + 2];
+      double c00 = Iw[4] * Iw[8] - Iw[5] * Iw[7], c01 = Iw[5] * Iw[6] - Iw[3] * Iw[8], c02 = Iw[3] * Iw[7] - Iw[4] * Iw[6];
+      double id = 1.0 / (Iw[0] * c00 + Iw[1] * c01 + Iw[2] * c02);
+      Ii[0] = c00 * id; Ii[1] = (Iw[2] * Iw[7] - Iw[1] * Iw[8]) * id; Ii[2] = (Iw[1] * Iw[5] - Iw[2] * Iw[4]) * id;
+      Ii[3] = c01 * id; Ii[4] = (Iw[0] * Iw[8] - Iw[2] * Iw[6]) * id; Ii[5] = (Iw[2] * Iw[3] - Iw[0] * Iw[5]) * id;
+      Ii[6] = c02 * id; Ii[7] = (Iw[1] * Iw[6] - Iw[0] * Iw[7]) * id; Ii[8] = (Iw[0] * Iw[4] - Iw[1] * Iw[3]) * id;
+    }
+    // W_f = I^-1 [r_f]x  and  RW_f = R^T W_f
+    for (int e = tid; e < 72; e += TPI) {
+      int which = e / 36, ee = e - 36 * which;
+      int f = ee / 9, i = (ee % 9) / 3, j = ee % 3;
+      double rx = rec[CMPC_REC_R + 0 * 4 + f], ry = rec[CMPC_REC_R + 1 * 4 + f], rz = rec[CMPC_REC_R + 2 * 4 + f];
+      // column j of the cross-product matrix [r]x
+      double c0 = (j == 0) ? 0.0 : (j == 1 ? -rz : ry);
+      double c1 = (j == 0) ? rz : (j == 1 ? 0.0 : -rx);
+      double c2 = (j == 0) ? -ry : (j == 1 ? rx : 0.0);
+      double w0 = Ii[0] * c0 + Ii[1] * c1 + Ii[2] * c2;
+      double w1 = Ii[3] * c0 + Ii[4] * c1 + Ii[5] * c2;
+      double w2 = Ii[6] * c0 + Ii[7] * c1 + Ii[8] * c2;
+      if (which == 0) sW[f * 9 + i * 3 + j] = (i == 0) ? w0 : (i == 1 ? w1 : w2);
+      else sRW[f * 9 + i * 3 + j] = R[0 * 3 + i] * w0 + R[1 * 3 + i] * w1 + R[2 * 3 + i] * w2;
+    }
+    // ---- B/C. weighted tracking error of the free response, e_r = S (Adt^(r+1) x0 + sum_k Adt^k Qdt xi - Xd_r) ----
+    {
+      const double xd = rec[CMPC_REC_XDRAG];
+      // quat_to_rpy, SolverMPC.cpp:352-361 (x0 = roll, pitch, yaw, p, omega, v, g)
+      double qw = rec[CMPC_REC_Q + 0], qx = rec[CMPC_REC_Q + 1], qy = rec[CMPC_REC_Q + 2], qz = rec[CMPC_REC_Q + 3];
+      double as = fmin(-2.0 * (qx * qz - qw * qy), 0.99999);
+      double yaw = atan2(2.0 * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+      double pitch = asin(as);
+      double roll = atan2(2.0 * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+      double om[3] = {rec[CMPC_REC_W + 0], rec[CMPC_REC_W + 1], rec[CMPC_REC_W + 2]};
+      double v0[3] = {rec[CMPC_REC_V + 0], rec[CMPC_REC_V + 1], rec[CMPC_REC_V + 2]};
+      double ft[3] = {rec[CMPC_REC_FDIST + 0], rec[CMPC_REC_FDIST + 1], rec[CMPC_REC_FDIST + 2]};
+      double ff[3] = {rec[CMPC_REC_FDIST + 3], rec[CMPC_REC_FDIST + 4], rec[CMPC_REC_FDIST + 5]};
+      double th0[3] = {roll, pitch, yaw};
+      double az = xd * v0[0] + P.gravity;  // row 11 of A x0
+      for (int idx = tid; idx < 12 * h; idx += TPI) {
+        int r = idx / 12, c = idx - 12 * r;
+        double T = (double)(r + 1) * dt, T2 = 0.5 * T * T;
+        double val;
+        if (c < 3) {
+          double rto = R[0 * 3 + c] * om[0] + R[1 * 3 + c] * om[1] + R[2 * 3 + c] * om[2];
+          double rtf = R[0 * 3 + c] * ft[0] + R[1 * 3 + c] * ft[1] + R[2 * 3 + c] * ft[2];
+          val = th0[c] + T * rto + T2 * rtf;
+        } else if (c < 6) {
+          int a = c - 3;
+          val = (double)rec[CMPC_REC_P + a] + T * v0[a] + T2 * ff[a];
+          if (a == 2) val += T2 * az + (T * T * T / 6.0) * xd * ff[0];
+        } else if (c < 9) {
+          int a = c - 6;
+          val = om[a] + T * ft[a];
+        } else {
+          int a = c - 9;
+          val = v0[a] + T * ff[a];
+          if (a == 2) val += T * az + T2 * xd * ff[0];
+        }
+        ev[idx] = (double)rec[CMPC_REC_WEIGHTS + c] * (val - (double)rec[CMPC_REC_TRAJ + idx]);
+      }
+    }
+    __syncthreads();
+    const int nc = redi[0];
+    const int n = 3 * nc, m = 5 * nc;
+    // foot-pair blocks  PT = RW_i^T S_theta RW_j,  PO = W_i^T S_omega W_j
+    for (int e = tid; e < 288; e += TPI) {
+      int which = e / 144, ee = e - 144 * which;
+      int fi = ee / 36, fj = (ee / 9) & 3, a = (ee % 9) / 3, b = ee % 3;
+      const double* Mi = (which == 0 ? sRW : sW) + fi * 9;
+      const double* Mj = (which == 0 ? sRW : sW) + fj * 9;
+      int wo = which == 0 ? 0 : 6;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) acc += Mi[k * 3 + a] * (double)rec[CMPC_REC_WEIGHTS + wo + k] * Mj[k * 3 + b];
+      (which == 0 ? sPT : sPO)[ee] = acc;
+    }
+    // horizon aggregates of e:  agg[c][0:3]=sum c2 e_theta, [3:6]=sum c1 e_omega,
+    // [6:9]=(sum c2 e_p + c1 e_v)/m, [9]=xd/m (sum c3 e_pz + c2 e_vz)
+    {
+      const double xd = rec[CMPC_REC_XDRAG];
+      for (int idx = tid; idx < 10 * h; idx += TPI) {
+        int c = idx / 10, comp = idx - 10 * c;
+        double acc = 0.0;
+        for (int r = c; r < h; r++) {
+          double tau = (double)(r - c) * dt;
+          double c1 = dt, c2 = tau * dt + 0.5 * dt * dt, c3 = 0.5 * tau * tau * dt + 0.5 * tau * dt * dt + dt * dt * dt / 6.0;
+          const double* e = ev + 12 * r;
+          if (comp < 3) acc += c2 * e[comp];
+          else if (comp < 6) acc += c1 * e[6 + comp - 3];
+          else if (comp < 9) acc += (c2 * e[3 + comp - 6] + c1 * e[9 + comp - 6]) * minv;
+          else acc += (c3 * e[5] + c2 * e[11]) * xd * minv;
+        }
+        agg[idx] = acc;
+      }
+    }
+    __syncthreads();
+
+    int status = CMPC_ST_SOLVED;
+    int iters = 0;
+    if (nc == 0) {
+      status = CMPC_ST_EMPTY;
+    } else if (n > P.nmax) {
+      status = CMPC_ST_CAPACITY;  // launch was sized for fewer contact foot-steps than this instance has
+    } else {
+      // ---- C. gradient and Hessian of the reduced QP ----
+      const double xd = rec[CMPC_REC_XDRAG];
+      const double alpha2 = 2.0 * (double)rec[CMPC_REC_ALPHA];
+      const double wpz = rec[CMPC_REC_WEIGHTS + 5], wvz = rec[CMPC_REC_WEIGHTS + 11];
+      const double m2 = minv * minv;
+      for (int I = tid; I < n; I += TPI) {
+        int j = I / 3, comp = I - 3 * j;
+        int k = fs[j], step = k >> 2, f = k & 3;
+        const double* a = agg + 10 * step;
+        double acc = sRW[f * 9 + 0 + comp] * a[0] + sRW[f * 9 + 3 + comp] * a[1] + sRW[f * 9 + 6 + comp] * a[2] +
+                     sW[f * 9 + 0 + comp] * a[3] + sW[f * 9 + 3 + comp] * a[4] + sW[f * 9 + 6 + comp] * a[5] + a[6 + comp];
+        if (comp == 0) acc += a[9];
+        g[I] = 2.0 * acc;
+      }
+      for (int idx = tid; idx < n * n; idx += TPI) {
+        int I = idx / n, J = idx - I * n;
+        int j1 = I / 3, c1 = I - 3 * j1, j2 = J / 3, c2 = J - 3 * j2;
+        int k1 = fs[j1], k2 = fs[j2];
+        int a = k1 >> 2, fi = k1 & 3, b = k2 >> 2, fj = k2 & 3;
+        int ab = a * h + b, ba = b * h + a;
+        double s11 = sig[CMPC_SIG_11 * h * h + ab], s22 = sig[CMPC_SIG_22 * h * h + ab];
+        double val = s22 * sPT[(fi * 4 + fj) * 9 + c1 * 3 + c2] + s11 * sPO[(fi * 4 + fj) * 9 + c1 * 3 + c2];
+        double pv = 0.0;
+        if (c1 == c2) pv = s22 * (double)rec[CMPC_REC_WEIGHTS + 3 + c1] + s11 * (double)rec[CMPC_REC_WEIGHTS + 9 + c1];
+        if (c1 == 2 && c2 == 0)
+          pv += xd * (wpz * sig[CMPC_SIG_23 * h * h + ab] + wvz * sig[CMPC_SIG_12 * h * h + ab]);
+        if (c1 == 0 && c2 == 2)
+          pv += xd * (wpz * sig[CMPC_SIG_23 * h * h + ba] + wvz * sig[CMPC_SIG_12 * h * h + ba]);
+        if (c1 == 0 && c2 == 0) pv += xd * xd * (wpz * sig[CMPC_SIG_33 * h * h + ab] + wvz * s22);
+        val = 2.0 * (val + pv * m2);
+        if (I == J) val += alpha2;
+        K[idx] = val;
+      }
+      __syncthreads();
+      // ---- D. K <- H^-1 by symmetric sweeps (H is SPD: 2aI + 2B'SB, a > 0) ----
+      for (int k = 0; k < n; k++) {
+        for (int i = tid; i < n; i += TPI) kn[i] = K[k * n + i];
+        __syncthreads();
+        const double dinv = 1.0 / kn[k];
+        for (int j = tid; j < n; j += TPI) {
+          const double cj = kn[j];
+          const double cjd = cj * dinv;
+          if (j == k) {
+            for (int i = 0; i < n; i++) K[i * n + j] = (i == k) ? -dinv : kn[i] * dinv;
+          } else {
+            for (int i = 0; i < n; i++) {
+              double ci = kn[i];
+              K[i * n + j] = (i == k) ? cjd : fma(-ci, cjd, K[i * n + j]);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // swept matrix is -H^-1: x = -H^-1 g = K_swept g; then flip the sign of K
+      for (int i = tid; i < n; i += TPI) {
+        double acc = 0.0;
+        for (int j = 0; j < n; j++) acc = fma(K[j * n + i], g[j], acc);
+        x[i] = acc;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < n * n; idx += TPI) K[idx] = -K[idx];
+      for (int c = tid; c < m; c += TPI) {
+        int ia, iz; double va, vz;
+        cons_of(c, mu_inv, ia, va, iz, vz);
+        double b = 0.0;
+        if (c % 5 == 4) b = -(double)gait[fs[c / 5]] * P.f_max;
+        s[c] = va * x[ia] + vz * x[iz] - b;
+        rc[c] = 0.0;
+        isact[c] = 0;
+      }
+      __syncthreads();
+      flops_acc += 2.0 * (double)n * n * n * 0.5 + 12.0 * (double)n * n + 2.0 * (double)n * n;
+
+      // ---- E. Goldfarb-Idnani dual active set on K ----
+      int q = 0;
+      bool done = false;
+      while (!done) {
+        double best = 1e300; int bidx = -1;
+        for (int c = tid; c < m; c += TPI)
+          if (!isact[c]) { double sv = s[c]; if (sv < best) { best = sv; bidx = c; } }
+        block_argmin<TPI>(best, bidx, red, tid);
+        if (!(best < -P.tol_violation)) break;
+        const int p = bidx;
+        int pia, piz; double pva, pvz;
+        cons_of(p, mu_inv, pia, pva, piz, pvz);
+        double up = 0.0;
+        while (true) {
+          iters++;
+          if (iters > P.max_iter) { status = CMPC_ST_MAXITER; done = true; break; }
+          for (int i = tid; i < n; i += TPI) kn[i] = pva * K[pia * n + i] + pvz * K[piz * n + i];
+          __syncthreads();
+          const double scale = pva * kn[pia] + pvz * kn[piz];
+          for (int k = tid; k < q; k += TPI) {
+            int ia, iz; double va, vz;
+            cons_of(act[k], mu_inv, ia, va, iz, vz);
+            dvec[k] = va * kn[ia] + vz * kn[iz];
+          }
+          __syncthreads();
+          double dr = 0.0, ratio = 1e300; int kd = -1;
+          for (int k = tid; k < q; k += TPI) {
+            double acc = 0.0;
+            for (int l = 0; l < q; l++) acc = fma(psym(Pp, k, l), dvec[l], acc);
+            rvec[k] = acc;
+            rc[act[k]] = acc;
+            dr = fma(dvec[k], acc, dr);
+            if (acc > 0.0) { double t = u[k] / acc; if (t < ratio) { ratio = t; kd = k; } }
+          }
+          dr = block_sum<TPI>(dr, red, tid);
+          block_argmin<TPI>(ratio, kd, red, tid);
+          __syncthreads();
+          const double rho2 = scale - dr;
+          const bool dependent = !(rho2 > 1e-12 * scale);
+          if (!dependent) {
+            // v = N r gathered per variable from the (at most five) rows of its foot-step
+            for (int i = tid; i < n; i += TPI) {
+              int j = i / 3, comp = i - 3 * j;
+              const double* rj = rc + 5 * j;
+              double val;
+              if (comp == 0) val = mu_inv * (rj[0] - rj[1]);
+              else if (comp == 1) val = mu_inv * (rj[2] - rj[3]);
+              else val = rj[0] + rj[1] + rj[2] + rj[3] - rj[4];
+              vv[i] = val;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += TPI) {
+              double acc = kn[i];
+              for (int l = 0; l < n; l++) {
+                double vl = vv[l];
+                if (vl != 0.0) acc = fma(-K[l * n + i], vl, acc);
+              }
+              z[i] = acc;
+            }
+            __syncthreads();
+          }
+          const double t2 = dependent ? 1e300 : -s[p] / rho2;
+          const double t1 = ratio;
+          const double t = fmin(t1, t2);
+          if (t >= 1e299) { status = CMPC_ST_INFEASIBLE; done = true; break; }
+          const bool full = (t2 <= t1);
+          __syncthreads();  // everyone has read s[p], u[], rvec[] decisions
+          if (!dependent) {
+            for (int i = tid; i < n; i += TPI) x[i] = fma(t, z[i], x[i]);
+            for (int c = tid; c < m; c += TPI) {
+              int ia, iz; double va, vz;
+              cons_of(c, mu_inv, ia, va, iz, vz);
+              s[c] = fma(t, va * z[ia] + vz * z[iz], s[c]);
+            }
+          }
+          for (int k = tid; k < q; k += TPI) {
+            u[k] = fma(-t, rvec[k], u[k]);
+            rc[act[k]] = 0.0;
+          }
+          up += t;
+          flops_acc += 2.0 * (4.0 * n + 4.0 * q + (double)q * q + 3.0 * n * (2.0 * q < n ? 2.0 * q : (double)n) + 4.0 * m + n);
+          if (full) {
+            if (q >= P.qcap) { status = CMPC_ST_WSOVERFLOW; done = true; break; }
+            const double inv = 1.0 / rho2;
+            for (int k = tid; k < q; k += TPI) {
+              double rk = rvec[k] * inv;
+              for (int l = 0; l <= k; l++) Pp[k * (k + 1) / 2 + l] = fma(rk, rvec[l], Pp[k * (k + 1) / 2 + l]);
+              Pp[q * (q + 1) / 2 + k] = -rk;
+            }
+            if (tid == 0) {
+              Pp[q * (q + 1) / 2 + q] = inv;
+              act[q] = (short)p;
+              u[q] = up;
+              isact[p] = 1;
+            }
+            q++;
+            flops_acc += 2.0 * (double)q * q;
+            __syncthreads();
+            break;
+          }
+          // partial step: constraint kd leaves the working set, p stays the candidate
+          for (int k = tid; k < q; k += TPI) col[k] = psym(Pp, k, kd);
+          __syncthreads();
+          {
+            const double inv = 1.0 / col[kd];
+            for (int k = tid; k < q; k += TPI) {
+              if (k == kd) continue;
+              double ck = col[k] * inv;
+              for (int l = 0; l <= k; l++)
+                if (l != kd) Pp[k * (k + 1) / 2 + l] = fma(-ck, col[l], Pp[k * (k + 1) / 2 + l]);
+            }
+          }
+          __syncthreads();
+          const int last = q - 1;
+          if (kd != last) {
+            for (int l = tid; l < last; l += TPI)
+              if (l != kd) psym(Pp, kd, l) = psym(Pp, last, l);
+            if (tid == 0) {
+              Pp[kd * (kd + 1) / 2 + kd] = Pp[last * (last + 1) / 2 + last];
+              isact[act[kd]] = 0;
+              act[kd] = act[last];
+              u[kd] = u[last];
+            }
+          } else if (tid == 0) {
+            isact[act[kd]] = 0;
+          }
+          q--;
+          flops_acc += 2.0 * (double)q * q;
+          __syncthreads();
+        }
+      }
+      // ---- objective 0.5 x'Hx + g'x = 0.5 g'x + 0.5 lambda'b at a KKT point ----
+      double part = 0.0;
+      for (int i = tid; i < n; i += TPI) part = fma(0.5 * g[i], x[i], part);
+      for (int k = tid; k < q; k += TPI) {
+        int c = act[k];
+        if (c % 5 == 4) part -= 0.5 * u[k] * (double)gait[fs[c / 5]] * P.f_max;
+      }
+      part = block_sum<TPI>(part, red, tid);
+      if (tid == 0) sScal[0] = part;
+      if (status == CMPC_ST_WSOVERFLOW && tid == 0 && P.overflow_list) {
+        int pos = atomicAdd(P.overflow_count, 1);
+        P.overflow_list[pos] = inst;
+      }
+    }
+    __syncthreads();
+    // ---- F. outputs ----
+    if (P.forces) {
+      double* out = P.forces + (size_t)inst * 12 * h;
+      for (int idx = tid; idx < 12 * h; idx += TPI) {
+        int k = idx / 3, comp = idx - 3 * k;
+        int j = fsinv[k];
+        out[idx] = (j >= 0 && status != CMPC_ST_CAPACITY) ? x[3 * j + comp] : 0.0;
+      }
+    }
+    if (P.active) {
+      signed char* out = P.active + (size_t)inst * 20 * h;
+      for (int idx = tid; idx < 20 * h; idx += TPI) {
+        int k = idx / 5, t = idx - 5 * k;
+        int j = fsinv[k];
+        signed char a = 0;
+        if (j >= 0 && status != CMPC_ST_CAPACITY) {
+          double fx = x[3 * j], fy = x[3 * j + 1], fz = x[3 * j + 2];
+          double row = (t == 0) ? fx * mu_inv + fz : (t == 1) ? -fx * mu_inv + fz : (t == 2) ? fy * mu_inv + fz
+                     : (t == 3) ? -fy * mu_inv + fz : fz;
+          if (row <= P.tol_active) a = -1;
+          if (t == 4 && row >= (double)gait[k] * P.f_max - P.tol_active) a = 1;
+        }
+        out[idx] = a;
+      }
+    }
+    if (tid == 0) {
+      if (P.objective) P.objective[inst] = (nc > 0 && status != CMPC_ST_CAPACITY) ? sScal[0] : 0.0;
+      if (P.status) P.status[inst] = status;
+      if (P.iterations) P.iterations[inst] = iters;
+    }
+    __syncthreads();  // record buffer and work arrays are reused by the next instance
+  }
+  if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops, (unsigned long long)flops_acc);
+}
+
+
+size_t cmpc_smem_bytes(int horizon, int nmax, int qcap) {
+  return (size_t)make_carve(horizon, nmax, qcap, cmpc_rec_stride(horizon)).total;
+}
+
+template <int TPI>
+static int launch_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(cmpc_solve_kernel<TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cmpc_solve_kernel<TPI><<<grid, TPI, smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+
+int cmpc_launch_solve(const CmpcParams& P, int tpi, int grid, void* stream) {
+  size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tpi == 32) return launch_t<32>(P, grid, smem, st);
+  if (tpi == 64) return launch_t<64>(P, grid, smem, st);
+  return launch_t<128>(P, grid, smem, st);
+}
+
+int cmpc_max_ctas_per_sm(int tpi, size_t smem) {
+  int nb = 0;
+  cudaError_t e;
+  if (tpi == 32) {
+    cudaFuncSetAttribute(cmpc_solve_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<32>, 32, smem);
+  } else if (tpi == 64) {
+    cudaFuncSetAttribute(cmpc_solve_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<64>, 64, smem);
+  } else {
+    cudaFuncSetAttribute(cmpc_solve_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<128>, 128, smem);
+  }
+  if (e != cudaSuccess) return -1;
+  return nb;
+}
