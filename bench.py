@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py — cMPC QP solves/sec (horizon 10, batched A1 trot) on N B200s, next to the
+reference's qpOASES path on the host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the fused condensation + QP kernel over one batch of 4096 synthetic
+randomised A1 trot instances (BASELINE.json configs[1]) per GPU.  Instances are independent, so the
+path shards with no collective (weak scaling: every rank solves its own 4096-instance batches).
+
+  value      solves/s with the instance records resident in HBM.  A ring of RING distinct batches
+             (> L2 in total) is uploaded once; timed steps walk the ring so every step reads cold
+             records.  CUDA events on the engine's stream, max over ranks.
+  e2e        the same metric through cmpc_batch_solve_host() with HOST buffers: pack into pinned
+             records, H2D, kernel, D2H of forces/status, every step inside the timed region.
+  roofline   the solve kernel against the measured FP64 FMA peak (it is FP64-pipe / latency
+             bound, not HBM bound; the HBM fraction is reported beside it).
+  cpu_baseline / --impl reference
+             the reference's CPU path: restated fp32 condensation + the reference's real
+             qpOASES 3.2.0 (oracle/_ref), one solve per thread on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "quad-periodic-mpc_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+HORIZON, DT, BATCH = 10, 0.03, 4096
+METRIC = "cmpc_qp_solves_per_sec_h10_batched"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def shard_bounds(total, rank, world):
+    """Contiguous split of `total` independent instances over `world` ranks."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_max(units, seconds):
+    """(sum of units, max of seconds) over ranks; identity without torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return units, seconds
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    a = torch.tensor([units], dtype=torch.float64, device=dev)
+    b = torch.tensor([seconds], dtype=torch.float64, device=dev)
+    dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    dist.all_reduce(b, op=dist.ReduceOp.MAX)
+    return a.item(), b.item()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_reference_run(steps, warmup, sample, threads=None):
+    """The reference's CPU implementation of the path on the host cores (oracle/_ref)."""
+    from cmpc_b200 import synth
+    from oracle import cmpc_oracle as O
+    if not O.available():
+        raise RuntimeError("oracle/_ref/libcmpc_ref.so is missing: build it where /root/reference exists")
+    threads = threads or len(os.sched_getaffinity(0))
+    inst = synth.make_batch(sample, horizon=HORIZON, dt=DT, seed=1234)
+    st = O.make_setup(DT, HORIZON, inst["mu"], inst["f_max"])
+    ups = (O.Update * sample)(*[O.make_update(inst, i, HORIZON) for i in range(sample)])
+    for _ in range(warmup):
+        O.solve_batch(st, ups, threads, use_float=True)
+    t0 = time.perf_counter()
+    ok_all = 0
+    for _ in range(steps):
+        _, ok = O.solve_batch(st, ups, threads, use_float=True)
+        ok_all += int(ok.sum())
+    dt = time.perf_counter() - t0
+    return {"value": steps * sample / dt, "seconds": dt, "threads": threads, "sample": sample, "solved": ok_all}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample = 1024
+    r = cpu_reference_run(args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "solves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 condensation + f64 qpOASES",
+        "data": "synthetic",
+        "config": {"workload": "A1 trot, horizon 10, dt 0.03, randomised states", "batch_per_step": sample},
+        "cpu_baseline": {"value": r["value"], "unit": "solves/s", "cores": r["threads"], "kind": "reference",
+                         "sample": "%d instances of the bench workload per step, qpOASES 3.2.0 compiled from the "
+                                   "reference's sources + restated fp32 condensation, one solve per thread" % sample},
+        "e2e": {"value": r["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from cmpc_b200 import engine, synth
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    h = HORIZON
+    rec_bytes = 4 * (48 + 12 * h) + 4 * h
+    rec_bytes = (rec_bytes + 15) & ~15
+    out_bytes = 12 * h * 8 + 20 * h + 8 + 4 + 4
+    ring = max(2, -(-int(1.25 * L2_BYTES) // (BATCH * (rec_bytes + out_bytes))))
+    total = ring * BATCH
+    inst = synth.make_batch(total, horizon=h, dt=DT, seed=1000 + rank)
+    b = engine.Batch(total, device=local_rank)
+    b.setup(DT, h, inst["mu"], inst["f_max"])
+    b.upload(inst)
+    b.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        b.sync()
+
+    # ---- device-resident throughput ----
+    for i in range(args.warmup):
+        b.solve_range((i % ring) * BATCH, BATCH)
+    b.sync()
+    b.reset_counters()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    b.mark(0)
+    for i in range(args.steps):
+        b.solve_range(((i + args.warmup) % ring) * BATCH, BATCH)
+    b.mark(1)
+    barrier()
+    region_ms = b.marked_ms()          # CUDA events on the launching stream around exactly K launches
+    clocks = sampler.stop()
+    launches = b.launches()
+    flops_total = b.last_flops()
+    units, seconds = allreduce_sum_max(float(args.steps * BATCH), region_ms / 1e3)
+    value = units / seconds
+
+    # ---- end to end through the host-buffer call ----
+    sub = {k: (v[:BATCH] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
+    be = engine.Batch(BATCH, device=local_rank)
+    be.setup(DT, h, inst["mu"], inst["f_max"])
+    for _ in range(max(1, args.warmup)):
+        res = be.solve_host(sub, want_active=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = be.solve_host(sub, want_active=False)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_units, e2e_seconds = allreduce_sum_max(float(args.steps * BATCH), e2e_wall)
+    assert (res["status"] == 0).all()
+    h2d = BATCH * rec_bytes
+    d2h = BATCH * (12 * h * 8 + 8 + 4 + 4) + 8
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        fp64 = engine.measure_fp64_peak(local_rank)
+        kms = region_ms / args.steps
+        fl = flops_total / args.steps
+        achieved = fl / (kms * 1e-3) / 1e12
+        hbm_bytes = BATCH * (rec_bytes + out_bytes)
+        hbm_ach = hbm_bytes / (kms * 1e-3) / 1e9
+        cpu = None
+        if world == 1 or True:
+            try:
+                c = cpu_reference_run(3, 1, 512)
+                cpu = {"value": c["value"], "unit": "solves/s", "cores": c["threads"], "kind": "reference",
+                       "sample": "3 x 512 instances of the bench workload, qpOASES 3.2.0 built from the reference's "
+                                 "sources + restated fp32 condensation, one solve per thread on all host cores"}
+            except Exception as e:  # the checker library did not travel
+                cpu = {"value": None, "unit": "solves/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        line = {
+            "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "batch 4096 A1 trot instances, horizon 10, dt 0.03, randomised states "
+                                   "(BASELINE.json configs[1]) per GPU per step",
+                       "batch_per_gpu": BATCH, "horizon": h, "ring_batches": ring,
+                       "l2": "inputs rotate through a ring of %d distinct resident batches (%.0f MB > L2)"
+                             % (ring, total * (rec_bytes + out_bytes) / 1e6),
+                       "sharding": "independent instances, no data-path collective"},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64, "unit": "TFLOP/s",
+                         "frac": achieved / fp64 if fp64 else None, "traffic": None,
+                         "kernel": "cmpc_solve_kernel", "kernel_ms": kms,
+                         "peak_source": "DFMA microbenchmark run in this process (cmpc_measure_fp64_peak)",
+                         "flops_per_launch": fl,
+                         "hbm": {"achieved": hbm_ach, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                 "frac": hbm_ach / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                                 "bytes_per_launch": hbm_bytes, "peak_source": peak_kind}},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_units / e2e_seconds, "unit": "solves/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_seconds / args.steps},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    b.close()
+    be.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,9 @@ int cmpc_batch_set_robot(cmpc_batch* b, double mass, const double inertia_diag[3
 int cmpc_batch_upload(cmpc_batch* b, int count, const cmpc_inputs* in);
 /* Launch the fused condensation + QP kernel over the uploaded instances (async). */
 int cmpc_batch_solve(cmpc_batch* b);
+/* Same, restricted to the uploaded instances [first, first+count): lets a caller keep several
+ * batches resident in one buffer and solve them one after another (bench ring, multi-GPU shards). */
+int cmpc_batch_solve_range(cmpc_batch* b, int first, int count);
 /* Copy results back and wait. */
 int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out);
 /* upload + solve + download: the end-to-end call with host buffers. */
@@ -147,8 +150,17 @@ int cmpc_batch_set_count(cmpc_batch* b, int count, int max_contact_feet);
 /* Timing helpers (CUDA events on the batch stream): ms of the last solve launch(es). */
 int cmpc_batch_last_solve_ms(cmpc_batch* b, float* ms);
 int cmpc_batch_kernel_launches(cmpc_batch* b, long long* launches);
-/* Algorithmic FP64 flop count of the last solve, accumulated by the kernel from its own loop counters. */
+/* Region timing: record event 0 / 1 on the batch stream, then read the elapsed device time. */
+int cmpc_batch_mark(cmpc_batch* b, int which);
+int cmpc_batch_marked_ms(cmpc_batch* b, float* ms);
+/* Zero the launch and flop counters. */
+int cmpc_batch_reset_counters(cmpc_batch* b);
+/* Algorithmic FP64 flop count since the last reset, accumulated by the kernel from its own loop counters. */
 int cmpc_batch_last_flops(cmpc_batch* b, double* flops);
+
+/* Measured FP64 FMA throughput of the device (dependent-free DFMA chains on every SM), the
+ * denominator of the solve kernel's roofline; TFLOP/s. */
+int cmpc_measure_fp64_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

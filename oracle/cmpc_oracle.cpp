@@ -338,16 +338,27 @@ void condense(const cmpc_oracle_setup* st, const cmpc_oracle_update* up, const d
   const int n = 12 * h;
   o.H = Mat<T>(n, n);
   o.g.assign(n, T(0));
-  for (int i = 0; i < n; i++) {
-    for (int j = 0; j < n; j++) {
-      T s = 0;
-      for (int k = 0; k < 13 * h; k++) s += o.Bqp(k, i) * S[k] * o.Bqp(k, j);
-      if (i == j) s += (T)up->alpha;
-      o.H(i, j) = 2 * s;
+  // qH = 2 (Bqp' S Bqp + alpha I): row-scaled copy, then rank-1 accumulation over the 13h rows
+  // (dense like the reference's Eigen product; contiguous inner loop so the compiler vectorises it)
+  Mat<T> SB(13 * h, n);
+  for (int k = 0; k < 13 * h; k++)
+    for (int j = 0; j < n; j++) SB(k, j) = S[k] * o.Bqp(k, j);
+  for (int k = 0; k < 13 * h; k++) {
+    const T* bk = &o.Bqp.a[(size_t)k * n];
+    const T* sk = &SB.a[(size_t)k * n];
+    const T ek = e[k];
+    for (int i = 0; i < n; i++) {
+      const T bi = bk[i];
+      if (bi == T(0)) continue;
+      T* hi = &o.H.a[(size_t)i * n];
+      for (int j = 0; j < n; j++) hi[j] += bi * sk[j];
+      o.g[i] += bi * ek;
     }
-    T s = 0;
-    for (int k = 0; k < 13 * h; k++) s += o.Bqp(k, i) * e[k];
-    o.g[i] = 2 * s;
+  }
+  for (int i = 0; i < n; i++) {
+    o.H(i, i) += (T)up->alpha;
+    for (int j = 0; j < n; j++) o.H(i, j) *= 2;
+    o.g[i] *= 2;
   }
 }
 
@@ -561,12 +572,17 @@ int cmpc_oracle_adapt_step(cmpc_oracle_adapt* a, double sim_time, double f_ext3,
 // partition over `threads` std::threads.  Returns 0.
 }  // extern "C"
 
+#include <malloc.h>
 #include <thread>
 extern "C" int cmpc_oracle_solve_batch(const cmpc_oracle_setup* st, const cmpc_oracle_update* ups, int count,
                                        int use_float, int threads, double* forces_out /* count x 12h */,
                                        int* ok_out /* count */) {
   const int h = st->horizon;
   if (threads < 1) threads = 1;
+  // keep the per-solve work matrices (100-200 KB each) on the heap arenas: the default mmap
+  // threshold turns every solve into mmap/munmap + page faults, which serialises the threads
+  mallopt(M_MMAP_THRESHOLD, 256 << 20);
+  mallopt(M_TRIM_THRESHOLD, 512 << 20);
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; t++) {
     pool.emplace_back([=]() {

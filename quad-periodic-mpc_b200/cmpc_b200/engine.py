@@ -48,6 +48,11 @@ def lib():
         L.cmpc_batch_last_solve_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.cmpc_batch_kernel_launches.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.cmpc_batch_last_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.cmpc_batch_solve_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cmpc_batch_mark.argtypes = [C.c_void_p, C.c_int]
+        L.cmpc_batch_marked_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.cmpc_batch_reset_counters.argtypes = [C.c_void_p]
+        L.cmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.cmpc_batch_device_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.cmpc_batch_device_forces.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.setup_problem.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double]
@@ -68,6 +73,12 @@ def lib():
 def _check(rc, what):
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().cmpc_last_error().decode()))
+
+
+def measure_fp64_peak(device=0):
+    t = C.c_double()
+    _check(lib().cmpc_measure_fp64_peak(device, C.byref(t)), "cmpc_measure_fp64_peak")
+    return t.value
 
 
 def _ptr(a):
@@ -127,6 +138,20 @@ class Batch:
 
     def solve(self):
         _check(lib().cmpc_batch_solve(self._h), "cmpc_batch_solve")
+
+    def solve_range(self, first, count):
+        _check(lib().cmpc_batch_solve_range(self._h, first, count), "cmpc_batch_solve_range")
+
+    def mark(self, which):
+        _check(lib().cmpc_batch_mark(self._h, which), "cmpc_batch_mark")
+
+    def marked_ms(self):
+        ms = C.c_float()
+        _check(lib().cmpc_batch_marked_ms(self._h, C.byref(ms)), "cmpc_batch_marked_ms")
+        return ms.value
+
+    def reset_counters(self):
+        _check(lib().cmpc_batch_reset_counters(self._h), "cmpc_batch_reset_counters")
 
     def sync(self):
         _check(lib().cmpc_batch_sync(self._h), "cmpc_batch_sync")

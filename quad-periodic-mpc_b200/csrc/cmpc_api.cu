@@ -70,7 +70,7 @@ struct cmpc_batch {
   int capacity = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, mark0 = nullptr, mark1 = nullptr;
   // problem setup
   bool is_setup = false;
   int h = 0;
@@ -162,6 +162,9 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMallocHost(&b->h_active, cap * 20 * hm));
   CK(cudaMallocHost(&b->h_flops, sizeof(unsigned long long)));
   *b->h_flops = 0;
+  CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long)));
+  CK(cudaEventCreate(&b->mark0));
+  CK(cudaEventCreate(&b->mark1));
   *out = b;
   return CMPC_OK;
 }
@@ -175,7 +178,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFreeHost(b->h_forces); cudaFreeHost(b->h_obj); cudaFreeHost(b->h_status); cudaFreeHost(b->h_iters);
   cudaFreeHost(b->h_active); cudaFreeHost(b->h_flops);
-  cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
+  cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->mark0); cudaEventDestroy(b->mark1);
   cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -268,15 +271,20 @@ int cmpc_batch_set_count(cmpc_batch* b, int count, int max_contact_feet) {
 
 int cmpc_batch_solve(cmpc_batch* b) {
   if (!b) return fail_arg("cmpc_batch_solve: null batch");
+  return cmpc_batch_solve_range(b, 0, b->count);
+}
+
+int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
+  if (!b) return fail_arg("cmpc_batch_solve_range: null batch");
   if (!b->is_setup) { g_err = "cmpc_batch_solve: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  if (first < 0 || count < 0 || first + count > b->count) return fail_arg("cmpc_batch_solve_range: range outside the uploaded instances");
   CK(cudaSetDevice(b->device));
   CK(cudaEventRecord(b->ev0, b->stream));
-  CK(cudaMemsetAsync(b->d_flops, 0, sizeof(unsigned long long), b->stream));
-  if (b->count > 0) {
+  if (count > 0) {
     CmpcParams P;
     std::memset(&P, 0, sizeof(P));
     P.horizon = b->h;
-    P.count = b->count;
+    P.count = count;
     P.rec_stride = b->rec_stride;
     P.nmax = std::max(3, 3 * b->max_contact);
     P.qcap = P.nmax;
@@ -290,16 +298,16 @@ int cmpc_batch_solve(cmpc_batch* b) {
     P.gravity = (double)(-9.8f);
     P.tol_violation = 1e-9;
     P.tol_active = 1e-6;
-    P.records = b->d_rec;
+    P.records = b->d_rec + (size_t)first * b->rec_stride;
     P.sigma = b->d_sigma;
     P.worklist = nullptr;
     P.overflow_list = b->d_overflow;
     P.overflow_count = b->d_overflow + b->capacity;
-    P.forces = b->d_forces;
-    P.objective = b->d_obj;
-    P.status = b->d_status;
-    P.iterations = b->d_iters;
-    P.active = b->d_active;
+    P.forces = b->d_forces + (size_t)first * 12 * b->h;
+    P.objective = b->d_obj + first;
+    P.status = b->d_status + first;
+    P.iterations = b->d_iters + first;
+    P.active = b->d_active + (size_t)first * 20 * b->h;
     P.flops = b->d_flops;
     P.win_t = b->d_win_t;
     P.win_d = b->d_win_d;
@@ -318,7 +326,7 @@ int cmpc_batch_solve(cmpc_batch* b) {
       g_err = "cmpc_batch_solve: kernel not launchable on this device (no sm_100a image?)";
       return CMPC_E_NODEVICE;
     }
-    int grid = std::min(b->count, b->sm_count * per_sm);
+    int grid = std::min(count, b->sm_count * per_sm);
     int rc = cmpc_launch_solve(P, tpi, grid, b->stream);
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_solve_kernel launch");
     b->launches++;
@@ -401,6 +409,29 @@ int cmpc_batch_last_solve_ms(cmpc_batch* b, float* ms) {
   CK(cudaSetDevice(b->device));
   CK(cudaEventSynchronize(b->ev1));
   CK(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+  return CMPC_OK;
+}
+
+int cmpc_batch_mark(cmpc_batch* b, int which) {
+  if (!b || (which != 0 && which != 1)) return fail_arg("cmpc_batch_mark: bad arguments");
+  CK(cudaSetDevice(b->device));
+  CK(cudaEventRecord(which ? b->mark1 : b->mark0, b->stream));
+  return CMPC_OK;
+}
+
+int cmpc_batch_marked_ms(cmpc_batch* b, float* ms) {
+  if (!b || !ms) return fail_arg("cmpc_batch_marked_ms: null argument");
+  CK(cudaSetDevice(b->device));
+  CK(cudaEventSynchronize(b->mark1));
+  CK(cudaEventElapsedTime(ms, b->mark0, b->mark1));
+  return CMPC_OK;
+}
+
+int cmpc_batch_reset_counters(cmpc_batch* b) {
+  if (!b) return fail_arg("cmpc_batch_reset_counters: null batch");
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemsetAsync(b->d_flops, 0, sizeof(unsigned long long), b->stream));
+  b->launches = 0;
   return CMPC_OK;
 }
 
@@ -534,3 +565,40 @@ void cmpc_get_disturbance_estimate(float f_est[6]) {
 }
 
 }  // extern "C"
+
+int cmpc_run_dfma_peak(int sm_count, void* stream, double* out_dev, int iters);
+
+extern "C" int cmpc_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail_arg("cmpc_measure_fp64_peak: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_err = "cmpc_measure_fp64_peak: no such CUDA device";
+    return CMPC_E_NODEVICE;
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr;
+  CK(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int iters = 20000;
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0, 0));
+    int rc = cmpc_run_dfma_peak(prop.multiProcessorCount, nullptr, d, iters);
+    if (rc) return fail_cuda((cudaError_t)rc, "cmpc_dfma_peak_kernel");
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8.0 * iters * 256.0 * 8.0 * prop.multiProcessorCount;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return CMPC_OK;
+}

@@ -656,3 +656,22 @@ int cmpc_max_ctas_per_sm(int tpi, size_t smem) {
   if (e != cudaSuccess) return -1;
   return nb;
 }
+
+// ---------------------------------------------------------------------------
+// FP64 roofline denominator: independent DFMA chains on every SM
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cmpc_dfma_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;
+}
+
+int cmpc_run_dfma_peak(int sm_count, void* stream, double* out_dev, int iters) {
+  cmpc_dfma_peak_kernel<<<sm_count * 8, 256, 0, (cudaStream_t)stream>>>(out_dev, iters, 1.0);
+  return (int)cudaGetLastError();
+}

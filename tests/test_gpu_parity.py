@@ -1,0 +1,196 @@
+"""GPU tests: the CUDA path, called through the C-ABI, against the golden qpOASES vectors, against the
+oracle on seeded batches, and through size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CASES, F_ABS, F_REL, OBJ_REL, golden_case, assert_forces_close
+from oracle import cmpc_numpy as N
+from oracle import cmpc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from cmpc_b200 import engine, synth
+
+
+def solve(inst, f_dist=None, capacity=None):
+    b = engine.Batch(capacity or len(inst["p"]))
+    b.setup(inst["dt"], inst["horizon"], inst.get("mu", 0.4), inst.get("f_max", 120.0))
+    res = b.solve_host(inst, f_dist=f_dist)
+    b.close()
+    return res
+
+
+def full_mask(forces, gait, h, mu, f_max):
+    out = np.zeros((len(forces), 20 * h), dtype=np.int8)
+    for i in range(len(forces)):
+        steps = np.flatnonzero(gait[i])
+        keep = N.contact_vars(gait[i], h)
+        m = N.active_mask(forces[i][keep], mu, f_max)
+        out[i].reshape(-1, 5)[steps] = m
+    return out
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_golden_parity(built_lib, golden, case):
+    inst = golden_case(golden, case)
+    h = inst["horizon"]
+    res = solve(inst)
+    assert (res["status"] == engine.ST_SOLVED).all()
+    ref = golden[case + "_forces"]
+    assert_forces_close(res["forces"], ref, case)
+    obj = golden[case + "_objective"]
+    assert (np.abs(res["objective"] - obj) <= OBJ_REL * np.abs(obj)).all()
+    # bit-exact contact / constraint-active mask
+    assert (res["active"] == full_mask(ref, inst["gait"], h, inst["mu"], inst["f_max"])).all()
+    # swing feet carry exactly zero force (SolverMPC.cpp:973-976)
+    swing = np.repeat(inst["gait"] == 0, 3, axis=1)
+    assert (res["forces"][swing] == 0.0).all()
+    # working-set changes track qpOASES' nWSR (same active-set family; not required to be equal)
+    assert np.abs(res["iterations"] - golden[case + "_nwsr"]).max() <= 16
+
+
+@pytest.mark.skipif(not O.available(), reason="oracle/_ref did not travel")
+@pytest.mark.parametrize("h,gaits,spread,seed,nseg", [
+    (10, ("trot",), 1.0, 101, None), (10, ("trot",), 3.0, 102, None),
+    (16, ("trot", "bound", "pace", "gallop"), 1.5, 103, 10), (10, ("stand",), 2.0, 104, None),
+    (5, ("trot",), 1.0, 105, 10), (1, ("stand",), 1.0, 106, None), (12, ("walk2", "trotrun"), 2.0, 107, 10)])
+def test_live_oracle_parity(built_lib, h, gaits, spread, seed, nseg):
+    B = 96
+    inst = synth.make_batch(B, horizon=h, seed=seed, gaits=gaits, spread=spread, n_segment=nseg)
+    res = solve(inst)
+    st = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    checked = 0
+    for i in range(B):
+        r = O.solve(st, O.make_update(inst, i, h))
+        if not r["ok"]:
+            continue  # reference itself failed (nWSR > 100): nothing to compare against
+        checked += 1
+        assert res["status"][i] in (engine.ST_SOLVED, engine.ST_EMPTY)
+        assert_forces_close(res["forces"][i], r["x"], "instance %d" % i)
+        if r["n_var"]:
+            assert abs(res["objective"][i] - r["objective"]) <= OBJ_REL * abs(r["objective"])
+    assert checked >= B * 0.9
+    ref_mask = full_mask(res["forces"], inst["gait"], h, inst["mu"], inst["f_max"])
+    assert (res["active"] == ref_mask).all()
+
+
+@pytest.mark.skipif(not O.available(), reason="oracle/_ref did not travel")
+def test_disturbance_hook_parity(built_lib):
+    # g gains 2 Bqp' S Qqp xi (SolverMPC.cpp:810)
+    h, B = 10, 32
+    inst = synth.make_batch(B, horizon=h, seed=201)
+    rng = np.random.default_rng(5)
+    fd = (rng.normal(0, 1.0, (B, 6)) * np.array([0.3, 0.3, 0.3, 3, 3, 3])).astype(np.float32)
+    res = solve(inst, f_dist=fd)
+    res0 = solve(inst)
+    st = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    for i in range(B):
+        r = O.solve(st, O.make_update(inst, i, h), f_dist=fd[i].astype(np.float64))
+        assert_forces_close(res["forces"][i], r["x"], "xi instance %d" % i)
+    assert np.abs(res["forces"] - res0["forces"]).max() > 1e-2   # the hook does move the forces
+
+
+def test_edge_cases(built_lib):
+    h = 10
+    inst = synth.make_batch(8, horizon=h, seed=301)
+    inst["gait"][0] = 0                      # nothing in contact
+    inst["gait"][1] = 0
+    inst["gait"][1][4 * 3 + 2] = 1           # a single foot-step in contact
+    inst["gait"][2] = 1                      # everything in contact
+    res = solve(inst)
+    assert res["status"][0] == engine.ST_EMPTY and (res["forces"][0] == 0).all() and (res["active"][0] == 0).all()
+    assert res["status"][1] == engine.ST_SOLVED
+    nzcols = np.flatnonzero(res["forces"][1])
+    assert set(nzcols) <= {3 * 14, 3 * 14 + 1, 3 * 14 + 2}
+    assert (res["status"][2:] == engine.ST_SOLVED).all()
+    # empty batch and a capacity larger than the batch
+    b = engine.Batch(16)
+    b.setup(0.03, h, 0.4, 120.0)
+    out = b.solve_host(inst, count=0)
+    assert out["forces"].shape == (0, 120)
+    out = b.solve_host(inst, count=3)
+    assert (out["forces"] == res["forces"][:3]).all()
+    with pytest.raises(RuntimeError):
+        b.setup(0.03, 20, 0.4, 120.0)        # SolverMPC.cpp:113
+    with pytest.raises(RuntimeError):
+        engine.Batch(2).solve_host(inst, count=8)
+    b.close()
+
+
+def test_reference_single_instance_interface(built_lib, golden):
+    """setup_problem / update_problem_data_floats / get_solution, convexMPC_interface.h:44-52."""
+    import ctypes as C
+    L = engine.lib()
+    inst = golden_case(golden, "trot10")
+    h = 10
+    for i in range(4):
+        L.setup_problem(inst["dt"], h, inst["mu"], inst["f_max"])
+        L.update_x_drag(float(inst["x_drag"][i]))
+        L.update_solver_settings(100, 1e-7, 1e-8, 1.5, 0.1, 0.0)
+        arr = lambda k: np.ascontiguousarray(inst[k][i], dtype=np.float32)
+        p, v, q, w, r, wt, tr = [arr(k) for k in ("p", "v", "q", "w", "r", "weights", "traj")]
+        gait = np.ascontiguousarray(inst["gait"][i], dtype=np.int32)
+        L.update_problem_data_floats(p.ctypes.data, v.ctypes.data, q.ctypes.data, w.ctypes.data, r.ctypes.data,
+                                     float(inst["rpy"][i][0]), float(inst["rpy"][i][1]), float(inst["rpy"][i][2]),
+                                     wt.ctypes.data, tr.ctypes.data, float(inst["alpha"][i]), gait.ctypes.data)
+        got = np.array([L.get_solution(k) for k in range(12 * h)])
+        assert_forces_close(got, golden["trot10_forces"][i], "single-instance")
+    # the double-precision entry point narrows to float like mfp_to_flt (convexMPC_interface.cpp:69)
+    d = lambda k: np.ascontiguousarray(inst[k][0], dtype=np.float64)
+    p, v, q, w, r, wt, tr = [d(k) for k in ("p", "v", "q", "w", "r", "weights", "traj")]
+    gait = np.ascontiguousarray(inst["gait"][0], dtype=np.int32)
+    L.setup_problem(inst["dt"], h, inst["mu"], inst["f_max"])
+    L.update_x_drag(float(inst["x_drag"][0]))
+    L.update_problem_data(p.ctypes.data, v.ctypes.data, q.ctypes.data, w.ctypes.data, r.ctypes.data, 0.0,
+                          wt.ctypes.data, tr.ctypes.data, float(inst["alpha"][0]), gait.ctypes.data)
+    got = np.array([L.get_solution(k) for k in range(12 * h)])
+    assert_forces_close(got, golden["trot10_forces"][0], "single-instance double")
+
+
+@pytest.mark.parametrize("B,h,gaits,nseg", [(4096, 10, ("trot",), None), (65536, 10, ("trot",), None),
+                                            (8192, 16, ("trot", "bound", "pace", "gallop"), 10)])
+def test_full_size_properties(built_lib, B, h, gaits, nseg):
+    """BASELINE.json sizes, checked through properties that need no CPU solve."""
+    inst = synth.make_batch(B, horizon=h, seed=401, gaits=gaits, spread=1.5, n_segment=nseg)
+    mu, fmax = inst["mu"], inst["f_max"]
+    res = solve(inst)
+    assert (res["status"] == engine.ST_SOLVED).all()
+    f = res["forces"].reshape(B, -1, 3)
+    mui = float(np.float32(1.0) / np.float32(mu))
+    # primal feasibility of every fmat row
+    assert (f[..., 2] >= -1e-8).all() and (f[..., 2] <= fmax + 1e-8).all()
+    assert (np.abs(f[..., 0]) * mui <= f[..., 2] + 1e-8).all() and (np.abs(f[..., 1]) * mui <= f[..., 2] + 1e-8).all()
+    # swing feet exactly zero
+    assert (f[inst["gait"] == 0] == 0.0).all()
+    # determinism and order independence: a permuted batch gives bit-identical per-instance answers
+    perm = np.random.default_rng(0).permutation(B)
+    pin = {k: (v[perm] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
+    res_p = solve(pin)
+    assert (res_p["forces"] == res["forces"][perm]).all()
+    assert (res_p["active"] == res["active"][perm]).all()
+    # leg relabelling symmetry: swapping legs 0<->1 and 2<->3 permutes the answer
+    sw = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
+    sub = slice(0, 512)
+    legperm = [1, 0, 3, 2]
+    sw["r"] = inst["r"].reshape(B, 3, 4)[:, :, legperm].reshape(B, 12)
+    sw["gait"] = inst["gait"].reshape(B, h, 4)[:, :, legperm].reshape(B, 4 * h)
+    for k in sw:
+        if isinstance(sw[k], np.ndarray):
+            sw[k] = np.ascontiguousarray(sw[k][sub])
+    res_s = solve(sw)
+    f_s = res_s["forces"].reshape(512, h, 4, 3)[:, :, legperm].reshape(512, -1)
+    assert np.abs(f_s - res["forces"][sub]).max() <= 1e-7
+    # optimality spot check on a few instances: KKT stationarity with numpy-built H, g
+    for i in range(0, B, B // 6):
+        H, g = N.condense_closed(inst, i)
+        keep = N.contact_vars(inst["gait"][i], h)
+        x = res["forces"][i][keep]
+        grad = H[np.ix_(keep, keep)] @ x + g[keep]
+        xg, _ = N.gi_solve(H[np.ix_(keep, keep)], g[keep], mu, fmax)
+        assert np.abs(x - xg).max() <= F_ABS
+        # stationarity in the free directions: gradient vanishes on foot-steps with no active row
+        m = res["active"][i].reshape(-1, 5)[np.flatnonzero(inst["gait"][i])]
+        free = np.repeat(~(m != 0).any(1), 3)
+        assert np.abs(grad[free]).max(initial=0.0) <= 1e-8
