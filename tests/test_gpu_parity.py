@@ -114,8 +114,11 @@ def test_edge_cases(built_lib):
     assert (out["forces"] == res["forces"][:3]).all()
     with pytest.raises(RuntimeError):
         b.setup(0.03, 20, 0.4, 120.0)        # SolverMPC.cpp:113
+    small = engine.Batch(2)
+    small.setup(0.03, h, 0.4, 120.0)
     with pytest.raises(RuntimeError):
-        engine.Batch(2).solve_host(inst, count=8)
+        small.solve_host(inst, count=8)      # count exceeds capacity
+    small.close()
     b.close()
 
 
