@@ -287,7 +287,6 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
     P.count = count;
     P.rec_stride = b->rec_stride;
     P.nmax = std::max(3, 3 * b->max_contact);
-    P.qcap = P.nmax;
     P.max_iter = 20 * P.nmax + 100;
     P.adapt_mode = b->adapt_mode;
     P.dt = (double)(float)b->dt;
@@ -313,23 +312,46 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
     P.win_d = b->d_win_d;
     P.est = b->d_est;
     P.f_est = b->d_fest;
-    const char* env_tpi = std::getenv("CMPC_TPI");
-    int tpi = env_tpi ? std::atoi(env_tpi) : b->tpi;
-    if (tpi != 32 && tpi != 64 && tpi != 128) tpi = 64;
-    size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap);
-    if (smem > 227 * 1024) {
-      g_err = "cmpc_batch_solve: instance too large for shared memory (n=" + std::to_string(P.nmax) + ")";
-      return CMPC_E_ARG;
+    // kernel shape by reduced problem size; CMPC_SHAPE overrides (0..3) for experiments
+    int shape = P.nmax <= 64 ? CMPC_SHAPE_64 : (P.nmax <= 128 ? CMPC_SHAPE_128 : CMPC_SHAPE_MEM);
+    if (const char* e = std::getenv("CMPC_SHAPE")) {
+      int sh = std::atoi(e);
+      if (sh == CMPC_SHAPE_MEM || (sh == CMPC_SHAPE_128 && P.nmax <= 128) ||
+          ((sh == CMPC_SHAPE_64 || sh == CMPC_SHAPE_64W) && P.nmax <= 64))
+        shape = sh;
     }
-    int per_sm = cmpc_max_ctas_per_sm(tpi, smem);
-    if (per_sm < 1) {
-      g_err = "cmpc_batch_solve: kernel not launchable on this device (no sm_100a image?)";
-      return CMPC_E_NODEVICE;
+    // two working-set capacity tiers: a small first tier keeps shared memory (and so occupancy) low;
+    // the few instances that outgrow it are re-solved from scratch by a full-capacity launch
+    int qcap1 = 32;
+    if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
+    if (qcap1 < 1 || qcap1 > P.nmax) qcap1 = P.nmax;
+    for (int tier = 0; tier < 2; tier++) {
+      if (tier == 0) {
+        P.qcap = qcap1;
+        if (qcap1 < P.nmax) CK(cudaMemsetAsync(P.overflow_count, 0, sizeof(int), b->stream));
+        else P.overflow_list = nullptr;
+      } else {
+        if (qcap1 >= P.nmax) break;
+        P.qcap = P.nmax;
+        P.worklist = b->d_overflow;
+        P.count_ptr = b->d_overflow + b->capacity;
+        P.overflow_list = nullptr;
+      }
+      size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap, shape);
+      if (smem > 227 * 1024) {
+        g_err = "cmpc_batch_solve: instance too large for shared memory (n=" + std::to_string(P.nmax) + ")";
+        return CMPC_E_ARG;
+      }
+      int per_sm = cmpc_max_ctas_per_sm(shape, smem);
+      if (per_sm < 1) {
+        g_err = "cmpc_batch_solve: kernel not launchable on this device (no sm_100a image?)";
+        return CMPC_E_NODEVICE;
+      }
+      int grid = std::min(count, b->sm_count * per_sm);
+      int rc = cmpc_launch_solve(P, shape, grid, b->stream);
+      if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_solve_kernel launch");
+      b->launches++;
     }
-    int grid = std::min(count, b->sm_count * per_sm);
-    int rc = cmpc_launch_solve(P, tpi, grid, b->stream);
-    if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_solve_kernel launch");
-    b->launches++;
   }
   CK(cudaEventRecord(b->ev1, b->stream));
   b->timed = true;

@@ -59,6 +59,7 @@ struct CmpcParams {
   const unsigned char* records;
   const double* sigma;
   const int* worklist;        // optional indirection (tier-2 launch); NULL = identity
+  const int* count_ptr;       // optional device-side instance count (tier-2 launch), capped by `count`
   int* overflow_list;         // instances whose working set outgrew qcap
   int* overflow_count;
   double* forces;             // [count][12h]
@@ -73,11 +74,13 @@ struct CmpcParams {
   float* f_est;               // [count][6]
 };
 
-#ifdef __CUDACC__
-template <int TPI>
-__global__ void cmpc_solve_kernel(const __grid_constant__ CmpcParams P);
-#endif
+// kernel shapes (cmpc_kernels.cu): register-tile tiers by reduced problem size, shared-memory tier beyond
+#define CMPC_SHAPE_64 0    /* n <= 64, 64 threads, 8x8 register tiles */
+#define CMPC_SHAPE_64W 1   /* n <= 64, 128 threads, 8x4 register tiles */
+#define CMPC_SHAPE_128 2   /* n <= 128, 256 threads, 8x8 register tiles */
+#define CMPC_SHAPE_MEM 3   /* matrix in shared memory, 128 threads */
 
-size_t cmpc_smem_bytes(int horizon, int nmax, int qcap);
-int cmpc_launch_solve(const CmpcParams& P, int tpi, int grid, void* stream);
-int cmpc_max_ctas_per_sm(int tpi, size_t smem);
+size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape);
+int cmpc_shape_threads(int shape);
+int cmpc_launch_solve(const CmpcParams& P, int shape, int grid, void* stream);
+int cmpc_max_ctas_per_sm(int shape, size_t smem);

@@ -8,7 +8,9 @@
 //   B. ct_ss_mats + c2qp    closed form of the 31x31 exp()      SolverMPC.cpp:96, :260
 //   C. H, g of the reduced  2(Bqp'SBqp + aI), 2Bqp'S(Aqp x0 +   SolverMPC.cpp:806-814 and the
 //      (contact-only) QP    Qqp xi - Xd), swing feet eliminated swing elimination at :859-950
-//   D. K = H^-1             symmetric sweep in place
+//   D. K = H^-1             symmetric sweep; the matrix lives in REGISTER TILES (TM x TN per
+//                           thread, cyclic layout), one pivot column broadcast through shared
+//                           memory per step
 //   E. QP                   Goldfarb-Idnani dual active set,    replaces qpOASES, SolverMPC.cpp:955
 //                           range-space form on K
 //   F. q_soln scatter, objective, primal activity mask          SolverMPC.cpp:970-983
@@ -24,28 +26,46 @@
 namespace {
 
 // ---------------------------------------------------------------------------
+// kernel shapes.  TY x TX threads, each holding a TM x TN register tile of the
+// NPAD x NPAD (padded) Hessian; REG = false keeps the matrix in shared memory
+// (any n that fits), used beyond the register tiers.
+// ---------------------------------------------------------------------------
+template <int TY_, int TX_, int TM_, int TN_, bool REG_, int MINB_>
+struct Shape {
+  static constexpr int TY = TY_, TX = TX_, TM = TM_, TN = TN_, NT = TY_ * TX_, NPAD = TY_ * TM_, MINB = MINB_;
+  static constexpr bool REG = REG_;
+  static_assert(TY_ * TM_ == TX_ * TN_, "square padded matrix");
+  static_assert(TX_ % TY_ == 0, "column owner derivable from the row block");
+};
+using Shape64 = Shape<8, 8, 8, 8, true, 4>;       // n <= 64, 64 threads, 8x8 tiles
+using Shape64w = Shape<8, 16, 8, 4, true, 4>;     // n <= 64, 128 threads, 8x4 tiles
+using Shape128 = Shape<16, 16, 8, 8, true, 1>;    // n <= 128, 256 threads, 8x8 tiles
+using ShapeMem = Shape<8, 16, 8, 4, false, 1>;    // any n that fits shared memory, 128 threads
+
+// ---------------------------------------------------------------------------
 // shared memory carve-up (same arithmetic on host and device)
 // ---------------------------------------------------------------------------
 struct Carve {
-  int rec0, rec1, bars, sig, small, evec, agg, fs, fsinv, K, g, x, kn, z, v, s, rc, isact, act, u, d, r, col, Pp,
-      red, total;
+  int rec0, rec1, bars, small, evec, agg, fs, fsinv, rowinfo, cbuf, K, g, x, kn, z, v, s, rc, isact, act, u, d, r,
+      col, Pp, red, total;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_stride) {
+__host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_stride, int npad) {
   Carve c;
   int o = 0;
   int nc = nmax / 3, m = 5 * nc;
   c.rec0 = o; o += align16(rec_stride);
   c.rec1 = o; o += align16(rec_stride);
   c.bars = o; o += 16;
-  c.sig = o; o += align16(8 * CMPC_SIG_COUNT * h * h);
   c.small = o; o += align16(8 * (36 + 36 + 144 + 144 + 16));  // W, RW, PT, PO, scalars
   c.evec = o; o += align16(8 * 12 * h);
   c.agg = o; o += align16(8 * 10 * h);
   c.fs = o; o += align16(4 * CMPC_MAX_FS);
   c.fsinv = o; o += align16(4 * CMPC_MAX_FS);
+  c.rowinfo = o; o += align16(4 * (npad > nmax ? npad : nmax));
+  c.cbuf = o; o += align16(8 * 2 * (npad + 2));
   c.K = o; o += align16(8 * nmax * nmax);
   c.g = o; o += align16(8 * nmax);
   c.x = o; o += align16(8 * nmax);
@@ -100,9 +120,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------
-// block reductions (TPI <= 128)
+// block reductions
 // ---------------------------------------------------------------------------
-template <int TPI>
+template <int NT>
 __device__ __forceinline__ void block_argmin(double& val, int& idx, double* red, int tid) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -110,31 +130,31 @@ __device__ __forceinline__ void block_argmin(double& val, int& idx, double* red,
     int oi = __shfl_xor_sync(0xffffffffu, idx, o);
     if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
   }
-  if (TPI > 32) {
+  if (NT > 32) {
     int* redi = reinterpret_cast<int*>(red + 8);
     __syncthreads();
     if ((tid & 31) == 0) { red[tid >> 5] = val; redi[tid >> 5] = idx; }
     __syncthreads();
     val = red[0]; idx = redi[0];
 #pragma unroll
-    for (int w = 1; w < TPI / 32; w++) {
+    for (int w = 1; w < NT / 32; w++) {
       double ov = red[w]; int oi = redi[w];
       if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
     }
   }
 }
 
-template <int TPI>
+template <int NT>
 __device__ __forceinline__ double block_sum(double val, double* red, int tid) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-  if (TPI > 32) {
+  if (NT > 32) {
     __syncthreads();
     if ((tid & 31) == 0) red[16 + (tid >> 5)] = val;
     __syncthreads();
     val = red[16];
 #pragma unroll
-    for (int w = 1; w < TPI / 32; w++) val += red[16 + w];
+    for (int w = 1; w < NT / 32; w++) val += red[16 + w];
   }
   return val;
 }
@@ -153,17 +173,147 @@ __device__ __forceinline__ double& psym(double* Pp, int k, int l) {
   return (k >= l) ? Pp[k * (k + 1) / 2 + l] : Pp[l * (l + 1) / 2 + k];
 }
 
+// per-instance constants the Hessian entries are assembled from
+struct HessCtx {
+  const double* sig;   // global, 5 tables of h*h
+  const double* sPT;   // shared, [4][4][3][3]
+  const double* sPO;
+  int h;
+  const double* wp;    // shared, position weights [3] then velocity weights [3]
+  double xd, m2, alpha2;
+};
+
+// H[(step a, foot fi, comp c1), (step b, foot fj, comp c2)], DESIGN.md §3
+__device__ __forceinline__ double hess_entry(const HessCtx& C, int ri, int rj, bool diag) {
+  const int a = ri & 0xff, fi = (ri >> 8) & 3, c1 = ri >> 16;
+  const int b = rj & 0xff, fj = (rj >> 8) & 3, c2 = rj >> 16;
+  const int hh = C.h * C.h, ab = a * C.h + b, ba = b * C.h + a;
+  const double s11 = __ldg(C.sig + CMPC_SIG_11 * hh + ab), s22 = __ldg(C.sig + CMPC_SIG_22 * hh + ab);
+  const int pidx = (fi * 4 + fj) * 9 + c1 * 3 + c2;
+  double val = s22 * C.sPT[pidx] + s11 * C.sPO[pidx];
+  double pv = 0.0;
+  if (c1 == c2) pv = s22 * C.wp[c1] + s11 * C.wp[3 + c1];
+  if (C.xd != 0.0) {
+    if (c1 == 2 && c2 == 0) pv += C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_23 * hh + ab) + C.wp[5] * __ldg(C.sig + CMPC_SIG_12 * hh + ab));
+    if (c1 == 0 && c2 == 2) pv += C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_23 * hh + ba) + C.wp[5] * __ldg(C.sig + CMPC_SIG_12 * hh + ba));
+    if (c1 == 0 && c2 == 0) pv += C.xd * C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_33 * hh + ab) + C.wp[5] * s22);
+  }
+  val = 2.0 * (val + pv * C.m2);
+  if (diag) val += C.alpha2;
+  return val;
+}
+
+// D (register tiers): build H into the thread's tile, sweep every pivot k < n, store -swept = H^-1.
+// Row i = ty + TY*a (a < TM), column j = tx + TX*b (b < TN).  Pivot k lives in row block a = k / TY of
+// threads ty = k % TY and in column block b = k / TX of threads tx = k % TX; the pivot loop is unrolled
+// over a so every register index is a compile-time constant.
+template <class S>
+__device__ __forceinline__ void build_invert_regtile(const HessCtx& C, const int* rowinfo, int n, int tid, double* cbuf,
+                                                     double* K) {
+  constexpr int TY = S::TY, TX = S::TX, TM = S::TM, TN = S::TN, NPAD = S::NPAD;
+  const int ty = tid / TX, tx = tid - ty * TX;
+  double A[TM][TN];
+  {
+    int ri[TM], rj[TN];
+#pragma unroll
+    for (int a = 0; a < TM; a++) ri[a] = rowinfo[ty + TY * a];
+#pragma unroll
+    for (int b = 0; b < TN; b++) rj[b] = rowinfo[tx + TX * b];
+#pragma unroll
+    for (int a = 0; a < TM; a++)
+#pragma unroll
+      for (int b = 0; b < TN; b++) {
+        const int i = ty + TY * a, j = tx + TX * b;
+        double v = (i == j) ? 1.0 : 0.0;  // identity padding beyond n
+        if (ri[a] >= 0 && rj[b] >= 0) v = hess_entry(C, ri[a], rj[b], i == j);
+        A[a][b] = v;
+      }
+  }
+  int par = 0;
+#pragma unroll
+  for (int a = 0; a < TM; a++) {
+    const int b = (a * TY) / TX;          // column block of the pivots of this row block
+    const int txo = (a * TY) % TX;        // column-owner tx = kk + txo
+    if (TY * a < n) {
+      for (int kk = 0; kk < TY; kk++) {
+        const int k = kk + TY * a;
+        if (k >= n) break;
+        double* cb = cbuf + par * (NPAD + 2);
+        if (tx == kk + txo) {
+#pragma unroll
+          for (int aa = 0; aa < TM; aa++) cb[ty + TY * aa] = A[aa][b];
+          if (ty == kk) cb[NPAD] = 1.0 / A[a][b];
+        }
+        __syncthreads();
+        const double dinv = cb[NPAD];
+        double ci[TM], cjd[TN];
+#pragma unroll
+        for (int aa = 0; aa < TM; aa++) ci[aa] = cb[ty + TY * aa];
+#pragma unroll
+        for (int bb = 0; bb < TN; bb++) cjd[bb] = cb[tx + TX * bb] * dinv;
+#pragma unroll
+        for (int aa = 0; aa < TM; aa++)
+#pragma unroll
+          for (int bb = 0; bb < TN; bb++) A[aa][bb] = fma(-ci[aa], cjd[bb], A[aa][bb]);
+        if (ty == kk) {
+#pragma unroll
+          for (int bb = 0; bb < TN; bb++) A[a][bb] = cjd[bb];
+        }
+        if (tx == kk + txo) {
+#pragma unroll
+          for (int aa = 0; aa < TM; aa++) A[aa][b] = ci[aa] * dinv;
+          if (ty == kk) A[a][b] = -dinv;
+        }
+        par ^= 1;
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < TM; a++)
+#pragma unroll
+    for (int b = 0; b < TN; b++) {
+      const int i = ty + TY * a, j = tx + TX * b;
+      if (i < n && j < n) K[i * n + j] = -A[a][b];
+    }
+}
+
+// D (shared-memory tier): same sweep with the matrix in shared memory
+template <int NT>
+__device__ __forceinline__ void build_invert_smem(const HessCtx& C, const int* rowinfo, int n, int tid, double* kn,
+                                                  double* K) {
+  for (int i = 0; i < n; i++) {
+    const int ri = rowinfo[i];
+    for (int j = tid; j < n; j += NT) K[i * n + j] = hess_entry(C, ri, rowinfo[j], i == j);
+  }
+  __syncthreads();
+  for (int k = 0; k < n; k++) {
+    for (int i = tid; i < n; i += NT) kn[i] = K[k * n + i];
+    __syncthreads();
+    const double dinv = 1.0 / kn[k];
+    for (int j = tid; j < n; j += NT) {
+      const double cjd = kn[j] * dinv;
+      if (j == k) {
+        for (int i = 0; i < n; i++) K[i * n + j] = (i == k) ? -dinv : kn[i] * dinv;
+      } else {
+        for (int i = 0; i < n; i++) K[i * n + j] = (i == k) ? cjd : fma(-kn[i], cjd, K[i * n + j]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < n * n; idx += NT) K[idx] = -K[idx];
+}
+
 }  // namespace
 
-template <int TPI>
-__global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__ CmpcParams P) {
+template <class S>
+__global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid_constant__ CmpcParams P) {
+  constexpr int NT = S::NT;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const int h = P.horizon;
-  const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride);
+  const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride, S::NPAD);
   unsigned char* recbuf[2] = {smem + cv.rec0, smem + cv.rec1};
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.bars);
-  double* sig = reinterpret_cast<double*>(smem + cv.sig);
   double* sW = reinterpret_cast<double*>(smem + cv.small);  // W[4][3][3]
   double* sRW = sW + 36;                                    // (R^T W)[4][3][3]
   double* sPT = sRW + 36;                                   // PT[4][4][3][3]
@@ -173,6 +323,8 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
   double* agg = reinterpret_cast<double*>(smem + cv.agg);   // agg[h][10]
   int* fs = reinterpret_cast<int*>(smem + cv.fs);           // reduced foot-step -> global foot-step k
   int* fsinv = reinterpret_cast<int*>(smem + cv.fsinv);     // global foot-step -> reduced or -1
+  int* rowinfo = reinterpret_cast<int*>(smem + cv.rowinfo); // reduced variable -> step | foot<<8 | comp<<16
+  double* cbuf = reinterpret_cast<double*>(smem + cv.cbuf);
   double* K = reinterpret_cast<double*>(smem + cv.K);
   double* g = reinterpret_cast<double*>(smem + cv.g);
   double* x = reinterpret_cast<double*>(smem + cv.x);
@@ -191,8 +343,7 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
   double* red = reinterpret_cast<double*>(smem + cv.red);
   int* redi = reinterpret_cast<int*>(red + 32);  // shared ints: [0]=nc
 
-  // horizon-sum tables: once per CTA
-  for (int i = tid; i < CMPC_SIG_COUNT * h * h; i += TPI) sig[i] = P.sigma[i];
+  const int count = P.count_ptr ? min(*P.count_ptr, P.count) : P.count;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -202,7 +353,7 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
 
   uint32_t phase[2] = {0u, 0u};
   int slot = blockIdx.x;
-  if (slot < P.count && tid == 0) {
+  if (slot < count && tid == 0) {
     int inst = P.worklist ? P.worklist[slot] : slot;
     mbar_expect_tx(&bars[0], (uint32_t)P.rec_stride);
     bulk_g2s(recbuf[0], P.records + (size_t)inst * P.rec_stride, (uint32_t)P.rec_stride, &bars[0]);
@@ -211,12 +362,12 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
   const double dt = P.dt, mu_inv = P.mu_inv, minv = P.mass_inv;
   double flops_acc = 0.0;
 
-  for (int buf = 0; slot < P.count; slot += gridDim.x, buf ^= 1) {
+  for (int buf = 0; slot < count; slot += gridDim.x, buf ^= 1) {
     const int inst = P.worklist ? P.worklist[slot] : slot;
     // prefetch the next record while this one is solved
     {
       int nslot = slot + gridDim.x;
-      if (tid == 0 && nslot < P.count) {
+      if (tid == 0 && nslot < count) {
         int ninst = P.worklist ? P.worklist[nslot] : nslot;
         fence_proxy_async();
         mbar_expect_tx(&bars[buf ^ 1], (uint32_t)P.rec_stride);
@@ -246,7 +397,7 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
       }
       if (tid == 0) redi[0] = cnt;
     }
-    // ---- A2. rotation, inertia, per-thread copies (cheap, avoids a round of syncs) ----
+    // ---- A2. rotation, inertia: per-thread copies (cheap, avoids a round of syncs) ----
     double R[9], Ii[9];
     {
       double qw = rec[CMPC_REC_Q + 0], qx = rec[CMPC_REC_Q + 1], qy = rec[CMPC_REC_Q + 2], qz = rec[CMPC_REC_Q + 3];
@@ -270,7 +421,7 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
       Ii[6] = c02 * id; Ii[7] = (Iw[1] * Iw[6] - Iw[0] * Iw[7]) * id; Ii[8] = (Iw[0] * Iw[4] - Iw[1] * Iw[3]) * id;
     }
     // W_f = I^-1 [r_f]x  and  RW_f = R^T W_f
-    for (int e = tid; e < 72; e += TPI) {
+    for (int e = tid; e < 72; e += NT) {
       int which = e / 36, ee = e - 36 * which;
       int f = ee / 9, i = (ee % 9) / 3, j = ee % 3;
       double rx = rec[CMPC_REC_R + 0 * 4 + f], ry = rec[CMPC_REC_R + 1 * 4 + f], rz = rec[CMPC_REC_R + 2 * 4 + f];
@@ -281,8 +432,11 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
       double w0 = Ii[0] * c0 + Ii[1] * c1 + Ii[2] * c2;
       double w1 = Ii[3] * c0 + Ii[4] * c1 + Ii[5] * c2;
       double w2 = Ii[6] * c0 + Ii[7] * c1 + Ii[8] * c2;
+      double r0 = (i == 0) ? R[0] : (i == 1 ? R[1] : R[2]);
+      double r1 = (i == 0) ? R[3] : (i == 1 ? R[4] : R[5]);
+      double r2 = (i == 0) ? R[6] : (i == 1 ? R[7] : R[8]);
       if (which == 0) sW[f * 9 + i * 3 + j] = (i == 0) ? w0 : (i == 1 ? w1 : w2);
-      else sRW[f * 9 + i * 3 + j] = R[0 * 3 + i] * w0 + R[1 * 3 + i] * w1 + R[2 * 3 + i] * w2;
+      else sRW[f * 9 + i * 3 + j] = r0 * w0 + r1 * w1 + r2 * w2;
     }
     // ---- B/C. weighted tracking error of the free response, e_r = S (Adt^(r+1) x0 + sum_k Adt^k Qdt xi - Xd_r) ----
     {
@@ -293,31 +447,33 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
       double yaw = atan2(2.0 * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
       double pitch = asin(as);
       double roll = atan2(2.0 * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
-      double om[3] = {rec[CMPC_REC_W + 0], rec[CMPC_REC_W + 1], rec[CMPC_REC_W + 2]};
-      double v0[3] = {rec[CMPC_REC_V + 0], rec[CMPC_REC_V + 1], rec[CMPC_REC_V + 2]};
-      double ft[3] = {rec[CMPC_REC_FDIST + 0], rec[CMPC_REC_FDIST + 1], rec[CMPC_REC_FDIST + 2]};
-      double ff[3] = {rec[CMPC_REC_FDIST + 3], rec[CMPC_REC_FDIST + 4], rec[CMPC_REC_FDIST + 5]};
-      double th0[3] = {roll, pitch, yaw};
-      double az = xd * v0[0] + P.gravity;  // row 11 of A x0
-      for (int idx = tid; idx < 12 * h; idx += TPI) {
+      const double om0 = rec[CMPC_REC_W + 0], om1 = rec[CMPC_REC_W + 1], om2 = rec[CMPC_REC_W + 2];
+      const double ft0 = rec[CMPC_REC_FDIST + 0], ft1 = rec[CMPC_REC_FDIST + 1], ft2 = rec[CMPC_REC_FDIST + 2];
+      const double ffx = rec[CMPC_REC_FDIST + 3];
+      const double az = xd * (double)rec[CMPC_REC_V + 0] + P.gravity;  // row 11 of A x0
+      for (int idx = tid; idx < 12 * h; idx += NT) {
         int r = idx / 12, c = idx - 12 * r;
         double T = (double)(r + 1) * dt, T2 = 0.5 * T * T;
         double val;
         if (c < 3) {
-          double rto = R[0 * 3 + c] * om[0] + R[1 * 3 + c] * om[1] + R[2 * 3 + c] * om[2];
-          double rtf = R[0 * 3 + c] * ft[0] + R[1 * 3 + c] * ft[1] + R[2 * 3 + c] * ft[2];
-          val = th0[c] + T * rto + T2 * rtf;
+          double ra = (c == 0) ? R[0] : (c == 1 ? R[1] : R[2]);
+          double rb = (c == 0) ? R[3] : (c == 1 ? R[4] : R[5]);
+          double rcc = (c == 0) ? R[6] : (c == 1 ? R[7] : R[8]);
+          double rto = ra * om0 + rb * om1 + rcc * om2;
+          double rtf = ra * ft0 + rb * ft1 + rcc * ft2;
+          double th0 = (c == 0) ? roll : (c == 1 ? pitch : yaw);
+          val = th0 + T * rto + T2 * rtf;
         } else if (c < 6) {
           int a = c - 3;
-          val = (double)rec[CMPC_REC_P + a] + T * v0[a] + T2 * ff[a];
-          if (a == 2) val += T2 * az + (T * T * T / 6.0) * xd * ff[0];
+          val = (double)rec[CMPC_REC_P + a] + T * (double)rec[CMPC_REC_V + a] + T2 * (double)rec[CMPC_REC_FDIST + 3 + a];
+          if (a == 2) val += T2 * az + (T * T * T / 6.0) * xd * ffx;
         } else if (c < 9) {
           int a = c - 6;
-          val = om[a] + T * ft[a];
+          val = (double)rec[CMPC_REC_W + a] + T * (double)rec[CMPC_REC_FDIST + a];
         } else {
           int a = c - 9;
-          val = v0[a] + T * ff[a];
-          if (a == 2) val += T * az + T2 * xd * ff[0];
+          val = (double)rec[CMPC_REC_V + a] + T * (double)rec[CMPC_REC_FDIST + 3 + a];
+          if (a == 2) val += T * az + T2 * xd * ffx;
         }
         ev[idx] = (double)rec[CMPC_REC_WEIGHTS + c] * (val - (double)rec[CMPC_REC_TRAJ + idx]);
       }
@@ -325,8 +481,18 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
     __syncthreads();
     const int nc = redi[0];
     const int n = 3 * nc, m = 5 * nc;
+    // reduced variable -> (step, foot, component); -1 pads the register tiles
+    for (int i = tid; i < max(S::NPAD, n); i += NT) {
+      int info = -1;
+      if (i < n) {
+        int j = i / 3, comp = i - 3 * j, k = fs[j];
+        info = (k >> 2) | ((k & 3) << 8) | (comp << 16);
+      }
+      if (i < max(S::NPAD, P.nmax)) rowinfo[i] = info;
+    }
+    if (tid < 6) sScal[1 + tid] = (double)rec[CMPC_REC_WEIGHTS + (tid < 3 ? 3 + tid : 6 + tid)];  // wp, wv
     // foot-pair blocks  PT = RW_i^T S_theta RW_j,  PO = W_i^T S_omega W_j
-    for (int e = tid; e < 288; e += TPI) {
+    for (int e = tid; e < 288; e += NT) {
       int which = e / 144, ee = e - 144 * which;
       int fi = ee / 36, fj = (ee / 9) & 3, a = (ee % 9) / 3, b = ee % 3;
       const double* Mi = (which == 0 ? sRW : sW) + fi * 9;
@@ -341,7 +507,7 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
     // [6:9]=(sum c2 e_p + c1 e_v)/m, [9]=xd/m (sum c3 e_pz + c2 e_vz)
     {
       const double xd = rec[CMPC_REC_XDRAG];
-      for (int idx = tid; idx < 10 * h; idx += TPI) {
+      for (int idx = tid; idx < 10 * h; idx += NT) {
         int c = idx / 10, comp = idx - 10 * c;
         double acc = 0.0;
         for (int r = c; r < h; r++) {
@@ -362,15 +528,11 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
     int iters = 0;
     if (nc == 0) {
       status = CMPC_ST_EMPTY;
-    } else if (n > P.nmax) {
+    } else if (n > P.nmax || (S::REG && n > S::NPAD)) {
       status = CMPC_ST_CAPACITY;  // launch was sized for fewer contact foot-steps than this instance has
     } else {
       // ---- C. gradient and Hessian of the reduced QP ----
-      const double xd = rec[CMPC_REC_XDRAG];
-      const double alpha2 = 2.0 * (double)rec[CMPC_REC_ALPHA];
-      const double wpz = rec[CMPC_REC_WEIGHTS + 5], wvz = rec[CMPC_REC_WEIGHTS + 11];
-      const double m2 = minv * minv;
-      for (int I = tid; I < n; I += TPI) {
+      for (int I = tid; I < n; I += NT) {
         int j = I / 3, comp = I - 3 * j;
         int k = fs[j], step = k >> 2, f = k & 3;
         const double* a = agg + 10 * step;
@@ -379,54 +541,24 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
         if (comp == 0) acc += a[9];
         g[I] = 2.0 * acc;
       }
-      for (int idx = tid; idx < n * n; idx += TPI) {
-        int I = idx / n, J = idx - I * n;
-        int j1 = I / 3, c1 = I - 3 * j1, j2 = J / 3, c2 = J - 3 * j2;
-        int k1 = fs[j1], k2 = fs[j2];
-        int a = k1 >> 2, fi = k1 & 3, b = k2 >> 2, fj = k2 & 3;
-        int ab = a * h + b, ba = b * h + a;
-        double s11 = sig[CMPC_SIG_11 * h * h + ab], s22 = sig[CMPC_SIG_22 * h * h + ab];
-        double val = s22 * sPT[(fi * 4 + fj) * 9 + c1 * 3 + c2] + s11 * sPO[(fi * 4 + fj) * 9 + c1 * 3 + c2];
-        double pv = 0.0;
-        if (c1 == c2) pv = s22 * (double)rec[CMPC_REC_WEIGHTS + 3 + c1] + s11 * (double)rec[CMPC_REC_WEIGHTS + 9 + c1];
-        if (c1 == 2 && c2 == 0)
-          pv += xd * (wpz * sig[CMPC_SIG_23 * h * h + ab] + wvz * sig[CMPC_SIG_12 * h * h + ab]);
-        if (c1 == 0 && c2 == 2)
-          pv += xd * (wpz * sig[CMPC_SIG_23 * h * h + ba] + wvz * sig[CMPC_SIG_12 * h * h + ba]);
-        if (c1 == 0 && c2 == 0) pv += xd * xd * (wpz * sig[CMPC_SIG_33 * h * h + ab] + wvz * s22);
-        val = 2.0 * (val + pv * m2);
-        if (I == J) val += alpha2;
-        K[idx] = val;
-      }
+      HessCtx C;
+      C.sig = P.sigma; C.sPT = sPT; C.sPO = sPO; C.h = h;
+      C.wp = sScal + 1;
+      C.xd = rec[CMPC_REC_XDRAG];
+      C.m2 = minv * minv;
+      C.alpha2 = 2.0 * (double)rec[CMPC_REC_ALPHA];
+      // ---- D. K <- H^-1 (H is SPD: 2aI + 2B'SB, a > 0) ----
+      if (S::REG) build_invert_regtile<S>(C, rowinfo, n, tid, cbuf, K);
+      else build_invert_smem<NT>(C, rowinfo, n, tid, kn, K);
       __syncthreads();
-      // ---- D. K <- H^-1 by symmetric sweeps (H is SPD: 2aI + 2B'SB, a > 0) ----
-      for (int k = 0; k < n; k++) {
-        for (int i = tid; i < n; i += TPI) kn[i] = K[k * n + i];
-        __syncthreads();
-        const double dinv = 1.0 / kn[k];
-        for (int j = tid; j < n; j += TPI) {
-          const double cj = kn[j];
-          const double cjd = cj * dinv;
-          if (j == k) {
-            for (int i = 0; i < n; i++) K[i * n + j] = (i == k) ? -dinv : kn[i] * dinv;
-          } else {
-            for (int i = 0; i < n; i++) {
-              double ci = kn[i];
-              K[i * n + j] = (i == k) ? cjd : fma(-ci, cjd, K[i * n + j]);
-            }
-          }
-        }
-        __syncthreads();
-      }
-      // swept matrix is -H^-1: x = -H^-1 g = K_swept g; then flip the sign of K
-      for (int i = tid; i < n; i += TPI) {
+      // x = -H^-1 g, slacks of every candidate row
+      for (int i = tid; i < n; i += NT) {
         double acc = 0.0;
         for (int j = 0; j < n; j++) acc = fma(K[j * n + i], g[j], acc);
-        x[i] = acc;
+        x[i] = -acc;
       }
       __syncthreads();
-      for (int idx = tid; idx < n * n; idx += TPI) K[idx] = -K[idx];
-      for (int c = tid; c < m; c += TPI) {
+      for (int c = tid; c < m; c += NT) {
         int ia, iz; double va, vz;
         cons_of(c, mu_inv, ia, va, iz, vz);
         double b = 0.0;
@@ -443,9 +575,9 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
       bool done = false;
       while (!done) {
         double best = 1e300; int bidx = -1;
-        for (int c = tid; c < m; c += TPI)
+        for (int c = tid; c < m; c += NT)
           if (!isact[c]) { double sv = s[c]; if (sv < best) { best = sv; bidx = c; } }
-        block_argmin<TPI>(best, bidx, red, tid);
+        block_argmin<NT>(best, bidx, red, tid);
         if (!(best < -P.tol_violation)) break;
         const int p = bidx;
         int pia, piz; double pva, pvz;
@@ -454,17 +586,17 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
         while (true) {
           iters++;
           if (iters > P.max_iter) { status = CMPC_ST_MAXITER; done = true; break; }
-          for (int i = tid; i < n; i += TPI) kn[i] = pva * K[pia * n + i] + pvz * K[piz * n + i];
+          for (int i = tid; i < n; i += NT) kn[i] = pva * K[pia * n + i] + pvz * K[piz * n + i];
           __syncthreads();
           const double scale = pva * kn[pia] + pvz * kn[piz];
-          for (int k = tid; k < q; k += TPI) {
+          for (int k = tid; k < q; k += NT) {
             int ia, iz; double va, vz;
             cons_of(act[k], mu_inv, ia, va, iz, vz);
             dvec[k] = va * kn[ia] + vz * kn[iz];
           }
           __syncthreads();
           double dr = 0.0, ratio = 1e300; int kd = -1;
-          for (int k = tid; k < q; k += TPI) {
+          for (int k = tid; k < q; k += NT) {
             double acc = 0.0;
             for (int l = 0; l < q; l++) acc = fma(psym(Pp, k, l), dvec[l], acc);
             rvec[k] = acc;
@@ -472,14 +604,14 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
             dr = fma(dvec[k], acc, dr);
             if (acc > 0.0) { double t = u[k] / acc; if (t < ratio) { ratio = t; kd = k; } }
           }
-          dr = block_sum<TPI>(dr, red, tid);
-          block_argmin<TPI>(ratio, kd, red, tid);
+          dr = block_sum<NT>(dr, red, tid);
+          block_argmin<NT>(ratio, kd, red, tid);
           __syncthreads();
           const double rho2 = scale - dr;
           const bool dependent = !(rho2 > 1e-12 * scale);
           if (!dependent) {
             // v = N r gathered per variable from the (at most five) rows of its foot-step
-            for (int i = tid; i < n; i += TPI) {
+            for (int i = tid; i < n; i += NT) {
               int j = i / 3, comp = i - 3 * j;
               const double* rj = rc + 5 * j;
               double val;
@@ -489,7 +621,7 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
               vv[i] = val;
             }
             __syncthreads();
-            for (int i = tid; i < n; i += TPI) {
+            for (int i = tid; i < n; i += NT) {
               double acc = kn[i];
               for (int l = 0; l < n; l++) {
                 double vl = vv[l];
@@ -506,14 +638,14 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
           const bool full = (t2 <= t1);
           __syncthreads();  // everyone has read s[p], u[], rvec[] decisions
           if (!dependent) {
-            for (int i = tid; i < n; i += TPI) x[i] = fma(t, z[i], x[i]);
-            for (int c = tid; c < m; c += TPI) {
+            for (int i = tid; i < n; i += NT) x[i] = fma(t, z[i], x[i]);
+            for (int c = tid; c < m; c += NT) {
               int ia, iz; double va, vz;
               cons_of(c, mu_inv, ia, va, iz, vz);
               s[c] = fma(t, va * z[ia] + vz * z[iz], s[c]);
             }
           }
-          for (int k = tid; k < q; k += TPI) {
+          for (int k = tid; k < q; k += NT) {
             u[k] = fma(-t, rvec[k], u[k]);
             rc[act[k]] = 0.0;
           }
@@ -522,7 +654,7 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
           if (full) {
             if (q >= P.qcap) { status = CMPC_ST_WSOVERFLOW; done = true; break; }
             const double inv = 1.0 / rho2;
-            for (int k = tid; k < q; k += TPI) {
+            for (int k = tid; k < q; k += NT) {
               double rk = rvec[k] * inv;
               for (int l = 0; l <= k; l++) Pp[k * (k + 1) / 2 + l] = fma(rk, rvec[l], Pp[k * (k + 1) / 2 + l]);
               Pp[q * (q + 1) / 2 + k] = -rk;
@@ -539,11 +671,11 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
             break;
           }
           // partial step: constraint kd leaves the working set, p stays the candidate
-          for (int k = tid; k < q; k += TPI) col[k] = psym(Pp, k, kd);
+          for (int k = tid; k < q; k += NT) col[k] = psym(Pp, k, kd);
           __syncthreads();
           {
             const double inv = 1.0 / col[kd];
-            for (int k = tid; k < q; k += TPI) {
+            for (int k = tid; k < q; k += NT) {
               if (k == kd) continue;
               double ck = col[k] * inv;
               for (int l = 0; l <= k; l++)
@@ -553,7 +685,7 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
           __syncthreads();
           const int last = q - 1;
           if (kd != last) {
-            for (int l = tid; l < last; l += TPI)
+            for (int l = tid; l < last; l += NT)
               if (l != kd) psym(Pp, kd, l) = psym(Pp, last, l);
             if (tid == 0) {
               Pp[kd * (kd + 1) / 2 + kd] = Pp[last * (last + 1) / 2 + last];
@@ -571,12 +703,12 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
       }
       // ---- objective 0.5 x'Hx + g'x = 0.5 g'x + 0.5 lambda'b at a KKT point ----
       double part = 0.0;
-      for (int i = tid; i < n; i += TPI) part = fma(0.5 * g[i], x[i], part);
-      for (int k = tid; k < q; k += TPI) {
+      for (int i = tid; i < n; i += NT) part = fma(0.5 * g[i], x[i], part);
+      for (int k = tid; k < q; k += NT) {
         int c = act[k];
         if (c % 5 == 4) part -= 0.5 * u[k] * (double)gait[fs[c / 5]] * P.f_max;
       }
-      part = block_sum<TPI>(part, red, tid);
+      part = block_sum<NT>(part, red, tid);
       if (tid == 0) sScal[0] = part;
       if (status == CMPC_ST_WSOVERFLOW && tid == 0 && P.overflow_list) {
         int pos = atomicAdd(P.overflow_count, 1);
@@ -584,77 +716,104 @@ __global__ void __launch_bounds__(TPI) cmpc_solve_kernel(const __grid_constant__
       }
     }
     __syncthreads();
-    // ---- F. outputs ----
-    if (P.forces) {
-      double* out = P.forces + (size_t)inst * 12 * h;
-      for (int idx = tid; idx < 12 * h; idx += TPI) {
-        int k = idx / 3, comp = idx - 3 * k;
-        int j = fsinv[k];
-        out[idx] = (j >= 0 && status != CMPC_ST_CAPACITY) ? x[3 * j + comp] : 0.0;
-      }
-    }
-    if (P.active) {
-      signed char* out = P.active + (size_t)inst * 20 * h;
-      for (int idx = tid; idx < 20 * h; idx += TPI) {
-        int k = idx / 5, t = idx - 5 * k;
-        int j = fsinv[k];
-        signed char a = 0;
-        if (j >= 0 && status != CMPC_ST_CAPACITY) {
-          double fx = x[3 * j], fy = x[3 * j + 1], fz = x[3 * j + 2];
-          double row = (t == 0) ? fx * mu_inv + fz : (t == 1) ? -fx * mu_inv + fz : (t == 2) ? fy * mu_inv + fz
-                     : (t == 3) ? -fy * mu_inv + fz : fz;
-          if (row <= P.tol_active) a = -1;
-          if (t == 4 && row >= (double)gait[k] * P.f_max - P.tol_active) a = 1;
+    // ---- F. outputs (an overflowed instance is left for the full-capacity launch) ----
+    if (status != CMPC_ST_WSOVERFLOW || !P.overflow_list) {
+      const bool have_x = (nc > 0 && status != CMPC_ST_CAPACITY);
+      if (P.forces) {
+        double* out = P.forces + (size_t)inst * 12 * h;
+        for (int idx = tid; idx < 12 * h; idx += NT) {
+          int k = idx / 3, comp = idx - 3 * k;
+          int j = fsinv[k];
+          out[idx] = (j >= 0 && have_x) ? x[3 * j + comp] : 0.0;
         }
-        out[idx] = a;
       }
-    }
-    if (tid == 0) {
-      if (P.objective) P.objective[inst] = (nc > 0 && status != CMPC_ST_CAPACITY) ? sScal[0] : 0.0;
-      if (P.status) P.status[inst] = status;
-      if (P.iterations) P.iterations[inst] = iters;
+      if (P.active) {
+        signed char* out = P.active + (size_t)inst * 20 * h;
+        for (int idx = tid; idx < 20 * h; idx += NT) {
+          int k = idx / 5, t = idx - 5 * k;
+          int j = fsinv[k];
+          signed char a = 0;
+          if (j >= 0 && have_x) {
+            double fx = x[3 * j], fy = x[3 * j + 1], fz = x[3 * j + 2];
+            double row = (t == 0) ? fx * mu_inv + fz : (t == 1) ? -fx * mu_inv + fz : (t == 2) ? fy * mu_inv + fz
+                       : (t == 3) ? -fy * mu_inv + fz : fz;
+            if (row <= P.tol_active) a = -1;
+            if (t == 4 && row >= (double)gait[k] * P.f_max - P.tol_active) a = 1;
+          }
+          out[idx] = a;
+        }
+      }
+      if (tid == 0) {
+        if (P.objective) P.objective[inst] = have_x ? sScal[0] : 0.0;
+        if (P.status) P.status[inst] = status;
+        if (P.iterations) P.iterations[inst] = iters;
+      }
     }
     __syncthreads();  // record buffer and work arrays are reused by the next instance
   }
   if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops, (unsigned long long)flops_acc);
 }
 
-
-size_t cmpc_smem_bytes(int horizon, int nmax, int qcap) {
-  return (size_t)make_carve(horizon, nmax, qcap, cmpc_rec_stride(horizon)).total;
-}
-
-template <int TPI>
-static int launch_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cmpc_solve_kernel<TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// ---------------------------------------------------------------------------
+// host-side launch plumbing
+// ---------------------------------------------------------------------------
+namespace {
+template <class S>
+int launch_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(cmpc_solve_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  cmpc_solve_kernel<TPI><<<grid, TPI, smem, st>>>(P);
+  cmpc_solve_kernel<S><<<grid, S::NT, smem, st>>>(P);
   return (int)cudaGetLastError();
 }
+template <class S>
+int occ_t(size_t smem) {
+  int nb = 0;
+  if (cudaFuncSetAttribute(cmpc_solve_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<S>, S::NT, smem) != cudaSuccess) return -1;
+  return nb;
+}
+int npad_of(int shape) {
+  switch (shape) {
+    case CMPC_SHAPE_64: return Shape64::NPAD;
+    case CMPC_SHAPE_64W: return Shape64w::NPAD;
+    case CMPC_SHAPE_128: return Shape128::NPAD;
+    default: return ShapeMem::NPAD;
+  }
+}
+}  // namespace
 
-int cmpc_launch_solve(const CmpcParams& P, int tpi, int grid, void* stream) {
-  size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (tpi == 32) return launch_t<32>(P, grid, smem, st);
-  if (tpi == 64) return launch_t<64>(P, grid, smem, st);
-  return launch_t<128>(P, grid, smem, st);
+size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape) {
+  return (size_t)make_carve(horizon, nmax, qcap, cmpc_rec_stride(horizon), npad_of(shape)).total;
 }
 
-int cmpc_max_ctas_per_sm(int tpi, size_t smem) {
-  int nb = 0;
-  cudaError_t e;
-  if (tpi == 32) {
-    cudaFuncSetAttribute(cmpc_solve_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<32>, 32, smem);
-  } else if (tpi == 64) {
-    cudaFuncSetAttribute(cmpc_solve_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<64>, 64, smem);
-  } else {
-    cudaFuncSetAttribute(cmpc_solve_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<128>, 128, smem);
+int cmpc_shape_threads(int shape) {
+  switch (shape) {
+    case CMPC_SHAPE_64: return Shape64::NT;
+    case CMPC_SHAPE_64W: return Shape64w::NT;
+    case CMPC_SHAPE_128: return Shape128::NT;
+    default: return ShapeMem::NT;
   }
-  if (e != cudaSuccess) return -1;
-  return nb;
+}
+
+int cmpc_launch_solve(const CmpcParams& P, int shape, int grid, void* stream) {
+  size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap, shape);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (shape) {
+    case CMPC_SHAPE_64: return launch_t<Shape64>(P, grid, smem, st);
+    case CMPC_SHAPE_64W: return launch_t<Shape64w>(P, grid, smem, st);
+    case CMPC_SHAPE_128: return launch_t<Shape128>(P, grid, smem, st);
+    default: return launch_t<ShapeMem>(P, grid, smem, st);
+  }
+}
+
+int cmpc_max_ctas_per_sm(int shape, size_t smem) {
+  switch (shape) {
+    case CMPC_SHAPE_64: return occ_t<Shape64>(smem);
+    case CMPC_SHAPE_64W: return occ_t<Shape64w>(smem);
+    case CMPC_SHAPE_128: return occ_t<Shape128>(smem);
+    default: return occ_t<ShapeMem>(smem);
+  }
 }
 
 // ---------------------------------------------------------------------------

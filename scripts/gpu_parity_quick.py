@@ -36,7 +36,8 @@ if __name__ == "__main__":
     run(10, ("trot",), 3.0, 4096, 2)
     run(16, ("trot", "bound", "pace", "gallop"), 1.5, 2048, 3, nseg=10)
     run(10, ("stand",), 2.0, 1024, 4)
-    for tpi in (32, 64, 128):
-        os.environ["CMPC_TPI"] = str(tpi)
-        print("TPI", tpi)
-        run(10, ("trot",), 1.0, 16384, 5, ncheck=8)
+    for shape in (0, 1, 3):
+        for qcap in (32, 64):
+            os.environ["CMPC_SHAPE"] = str(shape); os.environ["CMPC_QCAP1"] = str(qcap)
+            print("SHAPE", shape, "QCAP1", qcap)
+            run(10, ("trot",), 1.0, 16384, 5, ncheck=8)
