@@ -313,7 +313,7 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
     P.est = b->d_est;
     P.f_est = b->d_fest;
     // kernel shape by reduced problem size; CMPC_SHAPE overrides (0..3) for experiments
-    int shape = P.nmax <= 64 ? CMPC_SHAPE_64 : (P.nmax <= 128 ? CMPC_SHAPE_128 : CMPC_SHAPE_MEM);
+    int shape = P.nmax <= 64 ? CMPC_SHAPE_64W : (P.nmax <= 128 ? CMPC_SHAPE_128 : CMPC_SHAPE_MEM);
     if (const char* e = std::getenv("CMPC_SHAPE")) {
       int sh = std::atoi(e);
       if (sh == CMPC_SHAPE_MEM || (sh == CMPC_SHAPE_128 && P.nmax <= 128) ||
