@@ -190,12 +190,13 @@ def run_b200(args, rank, world, local_rank):
     sub = {k: (v[:BATCH] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
     be = engine.Batch(BATCH, device=local_rank)
     be.setup(DT, h, inst["mu"], inst["f_max"])
+    be.prepare_host(sub, want_active=False)   # host arrays bound once; every step below is one C-ABI call
     for _ in range(max(1, args.warmup)):
-        res = be.solve_host(sub, want_active=False)
+        res = be.solve_prepared()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = be.solve_host(sub, want_active=False)
+        res = be.solve_prepared()                # pack -> pinned -> H2D -> kernel -> D2H -> unpack, 4 chunks on 2 streams
     barrier()
     e2e_wall = time.perf_counter() - t0
     e2e_units, e2e_seconds = allreduce_sum_max(float(args.steps * BATCH), e2e_wall)

@@ -76,6 +76,9 @@ void cmpc_set_external_force(const float f_ext[6]);
 void cmpc_set_simulation_time(float t);
 /* f_est after the last solve (SolverMPC.h:76 `extern f_est`) */
 void cmpc_get_disturbance_estimate(float f_est[6]);
+/* Forget the accumulated f_ext / time history (the reference's file-scope vectors, SolverMPC.cpp:398-399,
+ * live for the life of the process; a test or a controller restart needs a way to clear them). */
+void cmpc_reset_history(void);
 
 /* ------------------------------------------------------------------------
  * 2. batched engine
@@ -134,7 +137,8 @@ int cmpc_batch_sync(cmpc_batch* b);
  * CMPC_ADAPT_WINDOW samples of time and f_ext[3]; sim_time is the time the
  * compensating force is evaluated at.  mode 0: estimate only (history 400..500
  * samples, g sees no disturbance); mode 1: estimate and apply xi in g in the
- * same launch.  Pass NULL windows to switch the stage off again. */
+ * same launch; mode 2: no new fit, refresh f_est[3] from the stored fit at sim_time and apply it
+ * (history beyond 500 samples; windows may be NULL).  mode < 0 switches the stage off again. */
 int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows_t, const float* windows_d,
                                   const float* sim_time, int mode);
 /* est[count][4] = stat, amp, freq(Hz), phase; f_est[count][6] */

@@ -180,6 +180,20 @@ class Batch:
         self.count = count
         return res
 
+    def prepare_host(self, inst, count=None, f_dist=None, want_active=True):
+        """Bind host input arrays and preallocated output arrays once; solve_prepared() then is one C call."""
+        count = len(inst["p"]) if count is None else count
+        s = self._inputs(inst, count, f_dist)
+        o, res = self._outputs(count, want_active)
+        self._prepared = (count, s, o, res)
+        return res
+
+    def solve_prepared(self):
+        count, s, o, res = self._prepared
+        _check(lib().cmpc_batch_solve_host(self._h, count, C.byref(s), C.byref(o)), "cmpc_batch_solve_host")
+        self.count = count
+        return res
+
     def last_solve_ms(self):
         ms = C.c_float()
         _check(lib().cmpc_batch_last_solve_ms(self._h, C.byref(ms)), "cmpc_batch_last_solve_ms")
@@ -196,12 +210,17 @@ class Batch:
         return f.value
 
     def upload_disturbance(self, win_t, win_d, sim_time, mode):
-        if win_t is None:
+        """mode 0 estimate, 1 estimate+apply, 2 apply the stored estimate (windows may be None), <0 off."""
+        if mode < 0:
             _check(lib().cmpc_batch_upload_disturbance(self._h, 0, None, None, None, -1), "upload_disturbance")
+            return
+        stt = np.ascontiguousarray(sim_time, dtype=np.float32)
+        if win_t is None:
+            _check(lib().cmpc_batch_upload_disturbance(self._h, len(stt), None, None, _ptr(stt), mode),
+                   "cmpc_batch_upload_disturbance")
             return
         wt = np.ascontiguousarray(win_t, dtype=np.float32)
         wd = np.ascontiguousarray(win_d, dtype=np.float32)
-        stt = np.ascontiguousarray(sim_time, dtype=np.float32)
         _check(lib().cmpc_batch_upload_disturbance(self._h, len(wt), _ptr(wt), _ptr(wd), _ptr(stt), mode),
                "cmpc_batch_upload_disturbance")
 

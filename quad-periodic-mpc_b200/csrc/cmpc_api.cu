@@ -63,14 +63,42 @@ void build_sigma(int h, double dt, std::vector<double>& sig) {
   fill(CMPC_SIG_12, c1, c2);
 }
 
+// Estimator tables: DFT twiddles for N = 400 and the two normalised Gaussian
+// kernels of gaussian_filter(), SolverMPC.cpp:404-419 (float kernel, float sum).
+void build_adapt_tables(std::vector<double>& tw, std::vector<float>& gk) {
+  const int N = CMPC_ADAPT_WINDOW;
+  tw.resize(2 * N);
+  for (int m = 0; m < N; m++) {
+    tw[2 * m] = std::cos(2.0 * M_PI * m / N);
+    tw[2 * m + 1] = -std::sin(2.0 * M_PI * m / N);  // e^{-2 pi i m / N}
+  }
+  gk.assign(CMPC_GK_TOTAL, 0.f);
+  const float sigmas[2] = {7.0f, 27.0f};
+  const int offs[2] = {0, 2 * CMPC_GK_R1 + 1};
+  for (int s = 0; s < 2; s++) {
+    float sigma = sigmas[s];
+    int radius = (int)std::ceil(3 * sigma);
+    float sum = 0.0f;
+    for (int i = -radius; i <= radius; i++) {
+      float v = (float)std::exp(-0.5 * (i * i) / (sigma * sigma));
+      gk[offs[s] + i + radius] = v;
+      sum += v;
+    }
+    for (int i = 0; i < 2 * radius + 1; i++) gk[offs[s] + i] /= sum;
+  }
+}
+
+constexpr int kMaxChunks = 8;
+
 }  // namespace
 
 struct cmpc_batch {
   int device = 0;
   int capacity = 0;
   int sm_count = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream[2] = {nullptr, nullptr};  // [0] is "the batch stream"; [1] only carries pipelined chunks
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, mark0 = nullptr, mark1 = nullptr;
+  cudaEvent_t chunk_done[kMaxChunks] = {};
   // problem setup
   bool is_setup = false;
   int h = 0;
@@ -87,10 +115,14 @@ struct cmpc_batch {
   int* d_status = nullptr;
   int* d_iters = nullptr;
   signed char* d_active = nullptr;
-  int* d_overflow = nullptr;  // [capacity] list + [1] count at the end
+  int* d_overflow[2] = {nullptr, nullptr};  // per stream: [capacity] list + [1] count at the end
   unsigned long long* d_flops = nullptr;
+  // adaptive stage
+  double* d_twiddle = nullptr;
+  float* d_gk = nullptr;
   float* d_win_t = nullptr;
   float* d_win_d = nullptr;
+  float* d_simtime = nullptr;
   double* d_est = nullptr;
   float* d_fest = nullptr;
   // pinned result staging
@@ -104,10 +136,143 @@ struct cmpc_batch {
   int count = 0;
   int max_contact = 0;  // max contact foot-steps over the uploaded instances
   int adapt_mode = -1;
-  int tpi = 64;
   long long launches = 0;
   bool timed = false;
 };
+
+namespace {
+
+// pack instances [first, first+count) into the pinned records; returns the max contact foot-steps
+int pack_records(cmpc_batch* b, const cmpc_inputs* in, int first, int count) {
+  const int h = b->h, stride = b->rec_stride;
+  const double fmax = (double)(float)b->f_max;
+  int maxc = 0;
+  for (int i = first; i < first + count; i++) {
+    unsigned char* rec = b->h_rec + (size_t)i * stride;
+    float* f = reinterpret_cast<float*>(rec);
+    std::memcpy(f + CMPC_REC_P, in->p + 3 * (size_t)i, 12);
+    std::memcpy(f + CMPC_REC_V, in->v + 3 * (size_t)i, 12);
+    std::memcpy(f + CMPC_REC_Q, in->q + 4 * (size_t)i, 16);
+    std::memcpy(f + CMPC_REC_W, in->w + 3 * (size_t)i, 12);
+    std::memcpy(f + CMPC_REC_R, in->r + 12 * (size_t)i, 48);
+    std::memcpy(f + CMPC_REC_WEIGHTS, in->weights + 12 * (size_t)i, 48);
+    f[CMPC_REC_ALPHA] = in->alpha[i];
+    f[CMPC_REC_XDRAG] = in->x_drag[i];
+    if (in->f_dist) std::memcpy(f + CMPC_REC_FDIST, in->f_dist + 6 * (size_t)i, 24);
+    else std::memset(f + CMPC_REC_FDIST, 0, 24);
+    f[CMPC_REC_SIMTIME] = 0.f;
+    f[CMPC_REC_RSV] = 0.f;
+    f[CMPC_REC_RSV + 1] = 0.f;
+    std::memcpy(f + CMPC_REC_TRAJ, in->traj + 12 * (size_t)h * i, 48 * (size_t)h);
+    unsigned char* gz = rec + 4 * (CMPC_REC_TRAJ + 12 * h);
+    const unsigned char* gsrc = in->gait + 4 * (size_t)h * i;
+    int c = 0;
+    for (int k = 0; k < 4 * h; k++) {
+      gz[k] = gsrc[k];
+      double ub = (double)gsrc[k] * fmax;
+      c += !(ub < 0.01 && ub > -0.01);
+    }
+    for (int k = 4 * h; k < stride - 4 * (CMPC_REC_TRAJ + 12 * h); k++) gz[k] = 0;
+    maxc = std::max(maxc, c);
+  }
+  return maxc;
+}
+
+int check_inputs(const cmpc_batch* b, int count, const cmpc_inputs* in, const char* who) {
+  if (!b || !in) return fail_arg("null argument");
+  if (!b->is_setup) { g_err = std::string(who) + ": call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  if (count < 0 || count > b->capacity) return fail_arg("count exceeds capacity");
+  if (!in->p || !in->v || !in->q || !in->w || !in->r || !in->weights || !in->traj || !in->alpha || !in->gait ||
+      !in->x_drag)
+    return fail_arg("null input array");
+  return CMPC_OK;
+}
+
+// enqueue the solve of the uploaded instances [first, first+count) on stream si
+int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
+  if (count <= 0) return CMPC_OK;
+  cudaStream_t st = b->stream[si];
+  CmpcParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.horizon = b->h;
+  P.count = count;
+  P.rec_stride = b->rec_stride;
+  P.nmax = std::max(3, 3 * max_contact);
+  P.max_iter = 20 * P.nmax + 100;
+  P.adapt_mode = b->adapt_mode;
+  P.dt = (double)(float)b->dt;
+  P.mu_inv = (double)(1.f / (float)b->mu);
+  P.f_max = (double)(float)b->f_max;
+  P.mass_inv = 1.0 / (double)(float)b->mass;
+  for (int i = 0; i < 3; i++) P.inertia[i] = (double)(float)b->inertia[i];
+  P.gravity = (double)(-9.8f);
+  P.tol_violation = 1e-9;
+  P.tol_active = 1e-6;
+  P.records = b->d_rec + (size_t)first * b->rec_stride;
+  P.sigma = b->d_sigma;
+  P.worklist = nullptr;
+  P.overflow_list = b->d_overflow[si];
+  P.overflow_count = b->d_overflow[si] + b->capacity;
+  P.forces = b->d_forces + (size_t)first * 12 * b->h;
+  P.objective = b->d_obj + first;
+  P.status = b->d_status + first;
+  P.iterations = b->d_iters + first;
+  P.active = b->d_active + (size_t)first * 20 * b->h;
+  P.flops = b->d_flops;
+  if (b->adapt_mode >= 0) {
+    P.twiddle = b->d_twiddle;
+    P.gk = b->d_gk;
+    P.win_t = b->d_win_t + (size_t)first * CMPC_ADAPT_WINDOW;
+    P.win_d = b->d_win_d + (size_t)first * CMPC_ADAPT_WINDOW;
+    P.sim_time = b->d_simtime + first;
+    P.est = b->d_est + (size_t)first * 4;
+    P.f_est = b->d_fest + (size_t)first * 6;
+  }
+  // kernel shape by reduced problem size; CMPC_SHAPE overrides (0..3) for experiments
+  int shape = P.nmax <= 64 ? CMPC_SHAPE_64W : (P.nmax <= 128 ? CMPC_SHAPE_128 : CMPC_SHAPE_MEM);
+  if (const char* e = std::getenv("CMPC_SHAPE")) {
+    int sh = std::atoi(e);
+    if (sh == CMPC_SHAPE_MEM || (sh == CMPC_SHAPE_128 && P.nmax <= 128) ||
+        ((sh == CMPC_SHAPE_64 || sh == CMPC_SHAPE_64W) && P.nmax <= 64))
+      shape = sh;
+  }
+  // two working-set capacity tiers: a small first tier keeps shared memory (and so occupancy) low;
+  // the few instances that outgrow it are re-solved from scratch by a full-capacity launch
+  int qcap1 = 32;
+  if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
+  if (qcap1 < 1 || qcap1 > P.nmax) qcap1 = P.nmax;
+  for (int tier = 0; tier < 2; tier++) {
+    if (tier == 0) {
+      P.qcap = qcap1;
+      if (qcap1 < P.nmax) CK(cudaMemsetAsync(P.overflow_count, 0, sizeof(int), st));
+      else P.overflow_list = nullptr;
+    } else {
+      if (qcap1 >= P.nmax) break;
+      P.qcap = P.nmax;
+      P.worklist = b->d_overflow[si];
+      P.count_ptr = b->d_overflow[si] + b->capacity;
+      P.overflow_list = nullptr;
+      if (P.adapt_mode == 0 || P.adapt_mode == 1) P.adapt_mode = 2;  // the estimate already exists
+    }
+    size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap, shape, P.adapt_mode >= 0);
+    if (smem > 227 * 1024) {
+      g_err = "cmpc_batch_solve: instance too large for shared memory (n=" + std::to_string(P.nmax) + ")";
+      return CMPC_E_ARG;
+    }
+    int per_sm = cmpc_max_ctas_per_sm(shape, smem, P.adapt_mode >= 0);
+    if (per_sm < 1) {
+      g_err = "cmpc_batch_solve: kernel not launchable on this device (no sm_100a image?)";
+      return CMPC_E_NODEVICE;
+    }
+    int grid = std::min(count, b->sm_count * per_sm);
+    int rc = cmpc_launch_solve(P, shape, grid, st);
+    if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_solve_kernel launch");
+    b->launches++;
+  }
+  return CMPC_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -139,9 +304,12 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   b->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&b->stream[i], cudaStreamNonBlocking));
   CK(cudaEventCreate(&b->ev0));
   CK(cudaEventCreate(&b->ev1));
+  CK(cudaEventCreate(&b->mark0));
+  CK(cudaEventCreate(&b->mark1));
+  for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->chunk_done[i], cudaEventDisableTiming));
   const size_t cap = (size_t)capacity;
   const int hm = CMPC_MAX_HORIZON;
   const size_t rec_max = (size_t)cmpc_rec_stride(hm);
@@ -153,8 +321,9 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMalloc(&b->d_status, sizeof(int) * cap));
   CK(cudaMalloc(&b->d_iters, sizeof(int) * cap));
   CK(cudaMalloc(&b->d_active, cap * 20 * hm));
-  CK(cudaMalloc(&b->d_overflow, sizeof(int) * (cap + 1)));
+  for (int i = 0; i < 2; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
   CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long)));
+  CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long)));
   CK(cudaMallocHost(&b->h_forces, sizeof(double) * cap * 12 * hm));
   CK(cudaMallocHost(&b->h_obj, sizeof(double) * cap));
   CK(cudaMallocHost(&b->h_status, sizeof(int) * cap));
@@ -162,9 +331,6 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMallocHost(&b->h_active, cap * 20 * hm));
   CK(cudaMallocHost(&b->h_flops, sizeof(unsigned long long)));
   *b->h_flops = 0;
-  CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long)));
-  CK(cudaEventCreate(&b->mark0));
-  CK(cudaEventCreate(&b->mark1));
   *out = b;
   return CMPC_OK;
 }
@@ -172,14 +338,17 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
 void cmpc_batch_destroy(cmpc_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  cudaStreamSynchronize(b->stream);
+  for (int i = 0; i < 2; i++) cudaStreamSynchronize(b->stream[i]);
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
-  cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_overflow); cudaFree(b->d_flops);
-  cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_est); cudaFree(b->d_fest);
+  cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops);
+  cudaFree(b->d_overflow[0]); cudaFree(b->d_overflow[1]);
+  cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
+  cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFreeHost(b->h_forces); cudaFreeHost(b->h_obj); cudaFreeHost(b->h_status); cudaFreeHost(b->h_iters);
   cudaFreeHost(b->h_active); cudaFreeHost(b->h_flops);
   cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->mark0); cudaEventDestroy(b->mark1);
-  cudaStreamDestroy(b->stream);
+  for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->chunk_done[i]);
+  for (int i = 0; i < 2; i++) cudaStreamDestroy(b->stream[i]);
   delete b;
 }
 
@@ -198,9 +367,9 @@ int cmpc_batch_setup(cmpc_batch* b, double dt, int horizon, double mu, double f_
     // the reference narrows dt to float (problem_setup.dt, convexMPC_interface.h:17)
     std::vector<double> sig;
     build_sigma(horizon, (double)(float)dt, sig);
-    CK(cudaStreamSynchronize(b->stream));
-    CK(cudaMemcpyAsync(b->d_sigma, sig.data(), sizeof(double) * sig.size(), cudaMemcpyHostToDevice, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+    CK(cudaMemcpyAsync(b->d_sigma, sig.data(), sizeof(double) * sig.size(), cudaMemcpyHostToDevice, b->stream[0]));
+    CK(cudaStreamSynchronize(b->stream[0]));
     b->count = 0;
   }
   b->is_setup = true;
@@ -216,47 +385,13 @@ int cmpc_batch_set_robot(cmpc_batch* b, double mass, const double inertia_diag[3
 }
 
 int cmpc_batch_upload(cmpc_batch* b, int count, const cmpc_inputs* in) {
-  if (!b || !in) return fail_arg("cmpc_batch_upload: null argument");
-  if (!b->is_setup) { g_err = "cmpc_batch_upload: call cmpc_batch_setup first"; return CMPC_E_STATE; }
-  if (count < 0 || count > b->capacity) return fail_arg("cmpc_batch_upload: count exceeds capacity");
-  if (!in->p || !in->v || !in->q || !in->w || !in->r || !in->weights || !in->traj || !in->alpha || !in->gait ||
-      !in->x_drag)
-    return fail_arg("cmpc_batch_upload: null input array");
+  int rc = check_inputs(b, count, in, "cmpc_batch_upload");
+  if (rc) return rc;
   CK(cudaSetDevice(b->device));
-  const int h = b->h, stride = b->rec_stride;
-  int maxc = 0;
-  for (int i = 0; i < count; i++) {
-    unsigned char* rec = b->h_rec + (size_t)i * stride;
-    float* f = reinterpret_cast<float*>(rec);
-    std::memcpy(f + CMPC_REC_P, in->p + 3 * (size_t)i, 12);
-    std::memcpy(f + CMPC_REC_V, in->v + 3 * (size_t)i, 12);
-    std::memcpy(f + CMPC_REC_Q, in->q + 4 * (size_t)i, 16);
-    std::memcpy(f + CMPC_REC_W, in->w + 3 * (size_t)i, 12);
-    std::memcpy(f + CMPC_REC_R, in->r + 12 * (size_t)i, 48);
-    std::memcpy(f + CMPC_REC_WEIGHTS, in->weights + 12 * (size_t)i, 48);
-    f[CMPC_REC_ALPHA] = in->alpha[i];
-    f[CMPC_REC_XDRAG] = in->x_drag[i];
-    if (in->f_dist) std::memcpy(f + CMPC_REC_FDIST, in->f_dist + 6 * (size_t)i, 24);
-    else std::memset(f + CMPC_REC_FDIST, 0, 24);
-    f[CMPC_REC_SIMTIME] = 0.f;
-    f[CMPC_REC_RSV] = 0.f;
-    f[CMPC_REC_RSV + 1] = 0.f;
-    std::memcpy(f + CMPC_REC_TRAJ, in->traj + 12 * (size_t)h * i, 48 * (size_t)h);
-    unsigned char* gz = rec + 4 * (CMPC_REC_TRAJ + 12 * h);
-    const unsigned char* gsrc = in->gait + 4 * (size_t)h * i;
-    int c = 0;
-    for (int k = 0; k < 4 * h; k++) {
-      gz[k] = gsrc[k];
-      double ub = (double)gsrc[k] * (double)(float)b->f_max;
-      c += !(ub < 0.01 && ub > -0.01);
-    }
-    for (int k = 4 * h; k < stride - 4 * (CMPC_REC_TRAJ + 12 * h); k++) gz[k] = 0;
-    maxc = std::max(maxc, c);
-  }
+  b->max_contact = pack_records(b, in, 0, count);
   b->count = count;
-  b->max_contact = maxc;
   if (count > 0)
-    CK(cudaMemcpyAsync(b->d_rec, b->h_rec, (size_t)count * stride, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(b->d_rec, b->h_rec, (size_t)count * b->rec_stride, cudaMemcpyHostToDevice, b->stream[0]));
   return CMPC_OK;
 }
 
@@ -279,81 +414,10 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
   if (!b->is_setup) { g_err = "cmpc_batch_solve: call cmpc_batch_setup first"; return CMPC_E_STATE; }
   if (first < 0 || count < 0 || first + count > b->count) return fail_arg("cmpc_batch_solve_range: range outside the uploaded instances");
   CK(cudaSetDevice(b->device));
-  CK(cudaEventRecord(b->ev0, b->stream));
-  if (count > 0) {
-    CmpcParams P;
-    std::memset(&P, 0, sizeof(P));
-    P.horizon = b->h;
-    P.count = count;
-    P.rec_stride = b->rec_stride;
-    P.nmax = std::max(3, 3 * b->max_contact);
-    P.max_iter = 20 * P.nmax + 100;
-    P.adapt_mode = b->adapt_mode;
-    P.dt = (double)(float)b->dt;
-    P.mu_inv = (double)(1.f / (float)b->mu);
-    P.f_max = (double)(float)b->f_max;
-    P.mass_inv = 1.0 / (double)(float)b->mass;
-    for (int i = 0; i < 3; i++) P.inertia[i] = (double)(float)b->inertia[i];
-    P.gravity = (double)(-9.8f);
-    P.tol_violation = 1e-9;
-    P.tol_active = 1e-6;
-    P.records = b->d_rec + (size_t)first * b->rec_stride;
-    P.sigma = b->d_sigma;
-    P.worklist = nullptr;
-    P.overflow_list = b->d_overflow;
-    P.overflow_count = b->d_overflow + b->capacity;
-    P.forces = b->d_forces + (size_t)first * 12 * b->h;
-    P.objective = b->d_obj + first;
-    P.status = b->d_status + first;
-    P.iterations = b->d_iters + first;
-    P.active = b->d_active + (size_t)first * 20 * b->h;
-    P.flops = b->d_flops;
-    P.win_t = b->d_win_t;
-    P.win_d = b->d_win_d;
-    P.est = b->d_est;
-    P.f_est = b->d_fest;
-    // kernel shape by reduced problem size; CMPC_SHAPE overrides (0..3) for experiments
-    int shape = P.nmax <= 64 ? CMPC_SHAPE_64W : (P.nmax <= 128 ? CMPC_SHAPE_128 : CMPC_SHAPE_MEM);
-    if (const char* e = std::getenv("CMPC_SHAPE")) {
-      int sh = std::atoi(e);
-      if (sh == CMPC_SHAPE_MEM || (sh == CMPC_SHAPE_128 && P.nmax <= 128) ||
-          ((sh == CMPC_SHAPE_64 || sh == CMPC_SHAPE_64W) && P.nmax <= 64))
-        shape = sh;
-    }
-    // two working-set capacity tiers: a small first tier keeps shared memory (and so occupancy) low;
-    // the few instances that outgrow it are re-solved from scratch by a full-capacity launch
-    int qcap1 = 32;
-    if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
-    if (qcap1 < 1 || qcap1 > P.nmax) qcap1 = P.nmax;
-    for (int tier = 0; tier < 2; tier++) {
-      if (tier == 0) {
-        P.qcap = qcap1;
-        if (qcap1 < P.nmax) CK(cudaMemsetAsync(P.overflow_count, 0, sizeof(int), b->stream));
-        else P.overflow_list = nullptr;
-      } else {
-        if (qcap1 >= P.nmax) break;
-        P.qcap = P.nmax;
-        P.worklist = b->d_overflow;
-        P.count_ptr = b->d_overflow + b->capacity;
-        P.overflow_list = nullptr;
-      }
-      size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap, shape);
-      if (smem > 227 * 1024) {
-        g_err = "cmpc_batch_solve: instance too large for shared memory (n=" + std::to_string(P.nmax) + ")";
-        return CMPC_E_ARG;
-      }
-      int per_sm = cmpc_max_ctas_per_sm(shape, smem);
-      if (per_sm < 1) {
-        g_err = "cmpc_batch_solve: kernel not launchable on this device (no sm_100a image?)";
-        return CMPC_E_NODEVICE;
-      }
-      int grid = std::min(count, b->sm_count * per_sm);
-      int rc = cmpc_launch_solve(P, shape, grid, b->stream);
-      if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_solve_kernel launch");
-      b->launches++;
-    }
-  }
-  CK(cudaEventRecord(b->ev1, b->stream));
+  CK(cudaEventRecord(b->ev0, b->stream[0]));
+  int rc = launch_range(b, first, count, b->max_contact, 0);
+  if (rc) return rc;
+  CK(cudaEventRecord(b->ev1, b->stream[0]));
   b->timed = true;
   return CMPC_OK;
 }
@@ -361,55 +425,136 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
 int cmpc_batch_sync(cmpc_batch* b) {
   if (!b) return fail_arg("cmpc_batch_sync: null batch");
   CK(cudaSetDevice(b->device));
-  CK(cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
   return CMPC_OK;
+}
+
+static int enqueue_d2h(cmpc_batch* b, const cmpc_outputs* out, int first, int n, cudaStream_t st) {
+  const int h = b->h;
+  const size_t f = (size_t)first, c = (size_t)n;
+  if (n <= 0) return CMPC_OK;
+  if (out->forces) CK(cudaMemcpyAsync(b->h_forces + f * 12 * h, b->d_forces + f * 12 * h, sizeof(double) * c * 12 * h, cudaMemcpyDeviceToHost, st));
+  if (out->objective) CK(cudaMemcpyAsync(b->h_obj + f, b->d_obj + f, sizeof(double) * c, cudaMemcpyDeviceToHost, st));
+  if (out->status) CK(cudaMemcpyAsync(b->h_status + f, b->d_status + f, sizeof(int) * c, cudaMemcpyDeviceToHost, st));
+  if (out->iterations) CK(cudaMemcpyAsync(b->h_iters + f, b->d_iters + f, sizeof(int) * c, cudaMemcpyDeviceToHost, st));
+  if (out->active) CK(cudaMemcpyAsync(b->h_active + f * 20 * h, b->d_active + f * 20 * h, c * 20 * h, cudaMemcpyDeviceToHost, st));
+  return CMPC_OK;
+}
+
+static void unpack_results(cmpc_batch* b, const cmpc_outputs* out, int first, int n) {
+  const int h = b->h;
+  const size_t f = (size_t)first, c = (size_t)n;
+  if (n <= 0) return;
+  if (out->forces) std::memcpy(out->forces + f * 12 * h, b->h_forces + f * 12 * h, sizeof(double) * c * 12 * h);
+  if (out->objective) std::memcpy(out->objective + f, b->h_obj + f, sizeof(double) * c);
+  if (out->status) std::memcpy(out->status + f, b->h_status + f, sizeof(int) * c);
+  if (out->iterations) std::memcpy(out->iterations + f, b->h_iters + f, sizeof(int) * c);
+  if (out->active) std::memcpy(out->active + f * 20 * h, b->h_active + f * 20 * h, c * 20 * h);
 }
 
 int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out) {
   if (!b || !out) return fail_arg("cmpc_batch_download: null argument");
   CK(cudaSetDevice(b->device));
-  const size_t n = (size_t)b->count;
-  const int h = b->h;
-  if (n > 0) {
-    if (out->forces) CK(cudaMemcpyAsync(b->h_forces, b->d_forces, sizeof(double) * n * 12 * h, cudaMemcpyDeviceToHost, b->stream));
-    if (out->objective) CK(cudaMemcpyAsync(b->h_obj, b->d_obj, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
-    if (out->status) CK(cudaMemcpyAsync(b->h_status, b->d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, b->stream));
-    if (out->iterations) CK(cudaMemcpyAsync(b->h_iters, b->d_iters, sizeof(int) * n, cudaMemcpyDeviceToHost, b->stream));
-    if (out->active) CK(cudaMemcpyAsync(b->h_active, b->d_active, n * 20 * h, cudaMemcpyDeviceToHost, b->stream));
-  }
-  CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
-  if (n > 0) {
-    if (out->forces) std::memcpy(out->forces, b->h_forces, sizeof(double) * n * 12 * h);
-    if (out->objective) std::memcpy(out->objective, b->h_obj, sizeof(double) * n);
-    if (out->status) std::memcpy(out->status, b->h_status, sizeof(int) * n);
-    if (out->iterations) std::memcpy(out->iterations, b->h_iters, sizeof(int) * n);
-    if (out->active) std::memcpy(out->active, b->h_active, n * 20 * h);
-  }
+  CK(cudaStreamSynchronize(b->stream[1]));
+  int rc = enqueue_d2h(b, out, 0, b->count, b->stream[0]);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(b->stream[0]));
+  unpack_results(b, out, 0, b->count);
   return CMPC_OK;
 }
 
+// End-to-end call with host buffers.  The batch is cut into chunks that alternate between two
+// streams: while chunk c is copied in and solved, the host packs chunk c+1 into pinned records, and
+// the results of earlier chunks are copied out and unpacked while later chunks are still being solved.
 int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const cmpc_outputs* out) {
-  int rc = cmpc_batch_upload(b, count, in);
+  int rc = check_inputs(b, count, in, "cmpc_batch_solve_host");
   if (rc) return rc;
-  rc = cmpc_batch_solve(b);
-  if (rc) return rc;
-  return cmpc_batch_download(b, out);
+  if (!out) return fail_arg("cmpc_batch_solve_host: null outputs");
+  CK(cudaSetDevice(b->device));
+  int nchunks = 1;
+  if (const char* e = std::getenv("CMPC_CHUNKS")) nchunks = std::atoi(e);
+  else if (count >= 2048) nchunks = 4;
+  nchunks = std::max(1, std::min(nchunks, kMaxChunks));
+  const int per = (count + nchunks - 1) / nchunks;
+  CK(cudaStreamSynchronize(b->stream[1]));
+  CK(cudaEventRecord(b->ev0, b->stream[0]));
+  b->count = count;
+  int maxc_all = 0, used = 0;
+  for (int c = 0; c < nchunks; c++) {
+    const int first = c * per, n = std::min(per, count - first);
+    if (n <= 0) break;
+    const int si = c & 1;
+    cudaStream_t st = b->stream[si];
+    const int maxc = pack_records(b, in, first, n);
+    maxc_all = std::max(maxc_all, maxc);
+    CK(cudaMemcpyAsync(b->d_rec + (size_t)first * b->rec_stride, b->h_rec + (size_t)first * b->rec_stride,
+                       (size_t)n * b->rec_stride, cudaMemcpyHostToDevice, st));
+    rc = launch_range(b, first, n, maxc, si);
+    if (rc) return rc;
+    rc = enqueue_d2h(b, out, first, n, st);
+    if (rc) return rc;
+    CK(cudaEventRecord(b->chunk_done[c], st));
+    used = c + 1;
+  }
+  b->max_contact = maxc_all;
+  for (int c = 0; c < used; c++) {
+    const int first = c * per, n = std::min(per, count - first);
+    CK(cudaEventSynchronize(b->chunk_done[c]));
+    unpack_results(b, out, first, n);
+  }
+  CK(cudaStreamWaitEvent(b->stream[0], b->chunk_done[used > 0 ? used - 1 : 0], 0));
+  CK(cudaEventRecord(b->ev1, b->stream[0]));
+  b->timed = true;
+  return CMPC_OK;
 }
 
 int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows_t, const float* windows_d,
                                   const float* sim_time, int mode) {
-  (void)count; (void)windows_t; (void)windows_d; (void)sim_time; (void)mode;
   if (!b) return fail_arg("cmpc_batch_upload_disturbance: null batch");
-  g_err = "cmpc_batch_upload_disturbance: estimator stage not built yet";
-  return CMPC_E_STATE;
+  CK(cudaSetDevice(b->device));
+  if (mode < 0 || (!windows_t && mode != 2)) {
+    b->adapt_mode = -1;
+    return CMPC_OK;
+  }
+  if (mode > 2) return fail_arg("cmpc_batch_upload_disturbance: mode must be 0, 1 or 2");
+  if (count < 0 || count > b->capacity) return fail_arg("cmpc_batch_upload_disturbance: count exceeds capacity");
+  if (!sim_time) return fail_arg("cmpc_batch_upload_disturbance: null sim_time");
+  const size_t cap = (size_t)b->capacity, N = CMPC_ADAPT_WINDOW;
+  if (!b->d_twiddle) {
+    std::vector<double> tw;
+    std::vector<float> gk;
+    build_adapt_tables(tw, gk);
+    CK(cudaMalloc(&b->d_twiddle, sizeof(double) * tw.size()));
+    CK(cudaMalloc(&b->d_gk, sizeof(float) * gk.size()));
+    CK(cudaMalloc(&b->d_win_t, sizeof(float) * cap * N));
+    CK(cudaMalloc(&b->d_win_d, sizeof(float) * cap * N));
+    CK(cudaMalloc(&b->d_simtime, sizeof(float) * cap));
+    CK(cudaMalloc(&b->d_est, sizeof(double) * cap * 4));
+    CK(cudaMalloc(&b->d_fest, sizeof(float) * cap * 6));
+    CK(cudaMemset(b->d_est, 0, sizeof(double) * cap * 4));
+    CK(cudaMemset(b->d_fest, 0, sizeof(float) * cap * 6));
+    CK(cudaMemcpy(b->d_twiddle, tw.data(), sizeof(double) * tw.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->d_gk, gk.data(), sizeof(float) * gk.size(), cudaMemcpyHostToDevice));
+  }
+  cudaStream_t st = b->stream[0];
+  if (windows_t && windows_d && mode != 2) {
+    CK(cudaMemcpyAsync(b->d_win_t, windows_t, sizeof(float) * (size_t)count * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->d_win_d, windows_d, sizeof(float) * (size_t)count * N, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(b->d_simtime, sim_time, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // the host arrays may be pageable and reused by the caller
+  b->adapt_mode = mode;
+  return CMPC_OK;
 }
 
 int cmpc_batch_download_disturbance(cmpc_batch* b, double* est, float* f_est) {
-  (void)est; (void)f_est;
   if (!b) return fail_arg("cmpc_batch_download_disturbance: null batch");
-  g_err = "cmpc_batch_download_disturbance: estimator stage not built yet";
-  return CMPC_E_STATE;
+  if (!b->d_est) { g_err = "cmpc_batch_download_disturbance: no disturbance data was uploaded"; return CMPC_E_STATE; }
+  CK(cudaSetDevice(b->device));
+  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+  if (est) CK(cudaMemcpy(est, b->d_est, sizeof(double) * (size_t)b->count * 4, cudaMemcpyDeviceToHost));
+  if (f_est) CK(cudaMemcpy(f_est, b->d_fest, sizeof(float) * (size_t)b->count * 6, cudaMemcpyDeviceToHost));
+  return CMPC_OK;
 }
 
 int cmpc_batch_device_records(cmpc_batch* b, void** records, size_t* stride_bytes) {
@@ -437,7 +582,7 @@ int cmpc_batch_last_solve_ms(cmpc_batch* b, float* ms) {
 int cmpc_batch_mark(cmpc_batch* b, int which) {
   if (!b || (which != 0 && which != 1)) return fail_arg("cmpc_batch_mark: bad arguments");
   CK(cudaSetDevice(b->device));
-  CK(cudaEventRecord(which ? b->mark1 : b->mark0, b->stream));
+  CK(cudaEventRecord(which ? b->mark1 : b->mark0, b->stream[0]));
   return CMPC_OK;
 }
 
@@ -452,7 +597,7 @@ int cmpc_batch_marked_ms(cmpc_batch* b, float* ms) {
 int cmpc_batch_reset_counters(cmpc_batch* b) {
   if (!b) return fail_arg("cmpc_batch_reset_counters: null batch");
   CK(cudaSetDevice(b->device));
-  CK(cudaMemsetAsync(b->d_flops, 0, sizeof(unsigned long long), b->stream));
+  CK(cudaMemsetAsync(b->d_flops, 0, sizeof(unsigned long long), b->stream[0]));
   b->launches = 0;
   return CMPC_OK;
 }
@@ -466,9 +611,45 @@ int cmpc_batch_kernel_launches(cmpc_batch* b, long long* launches) {
 int cmpc_batch_last_flops(cmpc_batch* b, double* flops) {
   if (!b || !flops) return fail_arg("cmpc_batch_last_flops: null argument");
   CK(cudaSetDevice(b->device));
-  CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
+  CK(cudaStreamSynchronize(b->stream[1]));
+  CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream[0]));
+  CK(cudaStreamSynchronize(b->stream[0]));
   *flops = (double)*b->h_flops;
+  return CMPC_OK;
+}
+
+int cmpc_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail_arg("cmpc_measure_fp64_peak: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_err = "cmpc_measure_fp64_peak: no such CUDA device";
+    return CMPC_E_NODEVICE;
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr;
+  CK(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int iters = 20000;
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0, 0));
+    int rc = cmpc_run_dfma_peak(prop.multiProcessorCount, nullptr, d, iters);
+    if (rc) return fail_cuda((cudaError_t)rc, "cmpc_dfma_peak_kernel");
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8.0 * iters * 256.0 * 8.0 * prop.multiProcessorCount;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
   return CMPC_OK;
 }
 
@@ -485,6 +666,8 @@ struct Single {
   float f_ext[6] = {0, 0, 0, 0, 0, 0};
   float sim_time = 0.f;
   float f_est[6] = {0, 0, 0, 0, 0, 0};
+  // adaptive bookkeeping of solve_mpc(), SolverMPC.cpp:688-798
+  std::vector<float> time_history, diff_history;
   std::vector<double> q_soln;
 };
 Single& single() {
@@ -515,6 +698,26 @@ static void solve_single(Single& s, const float* p, const float* v, const float*
   const int h = s.horizon;
   std::vector<unsigned char> g8(4 * h);
   for (int i = 0; i < 4 * h; i++) g8[i] = (unsigned char)gait[i];  // mint_to_u8, convexMPC_interface.cpp:76
+  // periodic-disturbance bookkeeping, SolverMPC.cpp:688-798: push the sample; fit the sinusoid while the
+  // history holds 400..500 samples; refresh f_est[3] from the stored fit afterwards; g sees f_est beyond 500
+  const int N = CMPC_ADAPT_WINDOW;
+  s.diff_history.push_back(s.f_ext[3]);
+  s.time_history.push_back(s.sim_time);
+  const size_t len = s.time_history.size();
+  int mode = -1;
+  if (len >= (size_t)N) mode = (len <= 500) ? 0 : 2;
+  if (mode == 0) {
+    if (cmpc_batch_upload_disturbance(s.b, 1, s.time_history.data() + (len - N), s.diff_history.data() + (len - N),
+                                      &s.sim_time, 0) != CMPC_OK)
+      die("update_problem_data/disturbance");
+  } else if (mode == 2) {
+    if (cmpc_batch_upload_disturbance(s.b, 1, nullptr, nullptr, &s.sim_time, 2) != CMPC_OK)
+      die("update_problem_data/disturbance");
+  }
+  if (len > 4096) {  // the reference lets the vectors grow without bound; only the last window is ever read
+    s.time_history.erase(s.time_history.begin(), s.time_history.end() - 1024);
+    s.diff_history.erase(s.diff_history.begin(), s.diff_history.end() - 1024);
+  }
   float fd[6] = {0, 0, 0, 0, 0, 0};
   cmpc_inputs in;
   in.p = p; in.v = v; in.q = q; in.w = w; in.r = r; in.weights = weights; in.traj = traj;
@@ -523,6 +726,7 @@ static void solve_single(Single& s, const float* p, const float* v, const float*
   std::memset(&out, 0, sizeof(out));
   out.forces = s.q_soln.data();
   if (cmpc_batch_solve_host(s.b, 1, &in, &out) != CMPC_OK) die("update_problem_data");
+  if (mode >= 0 && cmpc_batch_download_disturbance(s.b, nullptr, s.f_est) != CMPC_OK) die("update_problem_data/f_est");
   s.has_solved = true;
 }
 
@@ -586,41 +790,18 @@ void cmpc_get_disturbance_estimate(float f_est[6]) {
   for (int i = 0; i < 6; i++) f_est[i] = s.f_est[i];
 }
 
-}  // extern "C"
-
-int cmpc_run_dfma_peak(int sm_count, void* stream, double* out_dev, int iters);
-
-extern "C" int cmpc_measure_fp64_peak(int device, double* tflops) {
-  if (!tflops) return fail_arg("cmpc_measure_fp64_peak: null argument");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
-    g_err = "cmpc_measure_fp64_peak: no such CUDA device";
-    return CMPC_E_NODEVICE;
+void cmpc_reset_history(void) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  s.time_history.clear();
+  s.diff_history.clear();
+  for (int i = 0; i < 6; i++) s.f_est[i] = 0.f;
+  if (s.b && s.b->d_fest) {
+    cudaSetDevice(s.b->device);
+    cudaMemset(s.b->d_fest, 0, sizeof(float) * 6 * (size_t)s.b->capacity);
+    cudaMemset(s.b->d_est, 0, sizeof(double) * 4 * (size_t)s.b->capacity);
   }
-  CK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  double* d = nullptr;
-  CK(cudaMalloc(&d, 8));
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  const int iters = 20000;
-  double best = 0;
-  for (int rep = 0; rep < 4; rep++) {
-    CK(cudaEventRecord(e0, 0));
-    int rc = cmpc_run_dfma_peak(prop.multiProcessorCount, nullptr, d, iters);
-    if (rc) return fail_cuda((cudaError_t)rc, "cmpc_dfma_peak_kernel");
-    CK(cudaEventRecord(e1, 0));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    double fl = 2.0 * 8.0 * iters * 256.0 * 8.0 * prop.multiProcessorCount;
-    best = std::max(best, fl / (ms * 1e-3) / 1e12);
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d);
-  *tflops = best;
-  return CMPC_OK;
+  s.b ? (void)(s.b->adapt_mode = -1) : (void)0;
 }
+
+}  // extern "C"

@@ -1,7 +1,7 @@
 // Shared host/device definitions of the batched convex-MPC engine.
 #pragma once
-#include <stdint.h>
 #include <stddef.h>
+#include <stdint.h>
 
 #include "../../include/cmpc_b200.h"
 
@@ -39,6 +39,12 @@ static inline int cmpc_rec_stride(int h) {
 #define CMPC_SIG_12 4
 #define CMPC_SIG_COUNT 5
 
+// Gaussian kernels of the disturbance band-pass (SolverMPC.cpp:714-715: sigma 7 and 27,
+// radius ceil(3 sigma)), stored back to back
+#define CMPC_GK_R1 21
+#define CMPC_GK_R2 81
+#define CMPC_GK_TOTAL (2 * CMPC_GK_R1 + 1 + 2 * CMPC_GK_R2 + 1)
+
 struct CmpcParams {
   int horizon;
   int count;        // instances (or worklist entries) this launch covers
@@ -46,7 +52,7 @@ struct CmpcParams {
   int nmax;         // max reduced variable count in this launch (3 * contact foot-steps)
   int qcap;         // working-set capacity of this launch
   int max_iter;
-  int adapt_mode;   // -1 off, 0 estimate only, 1 estimate and apply
+  int adapt_mode;   // -1 off, 0 estimate only, 1 estimate and apply, 2 apply the stored estimate
   int pad0;
   double dt;        // (double)(float)dt
   double mu_inv;    // (double)(1.f/(float)mu)   SolverMPC.cpp:657
@@ -68,9 +74,13 @@ struct CmpcParams {
   int* iterations;            // [count]
   signed char* active;        // [count][20h]
   unsigned long long* flops;  // single counter, algorithmic flops
-  const float* win_t;         // [count][400] or NULL
-  const float* win_d;
-  double* est;                // [count][4]
+  // periodic-disturbance estimator (adapt_mode >= 0)
+  const double* twiddle;      // [400][2] cos, -sin of 2 pi m / 400
+  const float* gk;            // CMPC_GK_TOTAL normalised Gaussian taps
+  const float* win_t;         // [count][400]
+  const float* win_d;         // [count][400]
+  const float* sim_time;      // [count]
+  double* est;                // [count][4] stat, amp, freq, phase
   float* f_est;               // [count][6]
 };
 
@@ -80,7 +90,8 @@ struct CmpcParams {
 #define CMPC_SHAPE_128 2   /* n <= 128, 256 threads, 8x8 register tiles */
 #define CMPC_SHAPE_MEM 3   /* matrix in shared memory, 128 threads */
 
-size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape);
+size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape, bool adapt);
 int cmpc_shape_threads(int shape);
 int cmpc_launch_solve(const CmpcParams& P, int shape, int grid, void* stream);
-int cmpc_max_ctas_per_sm(int shape, size_t smem);
+int cmpc_max_ctas_per_sm(int shape, size_t smem, bool adapt);
+int cmpc_run_dfma_peak(int sm_count, void* stream, double* out_dev, int iters);

@@ -52,7 +52,7 @@ struct Carve {
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_stride, int npad) {
+__host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_stride, int npad, bool adapt) {
   Carve c;
   int o = 0;
   int nc = nmax / 3, m = 5 * nc;
@@ -66,7 +66,11 @@ __host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_s
   c.fsinv = o; o += align16(4 * CMPC_MAX_FS);
   c.rowinfo = o; o += align16(4 * (npad > nmax ? npad : nmax));
   c.cbuf = o; o += align16(8 * 2 * (npad + 2));
-  c.K = o; o += align16(8 * nmax * nmax);
+  {
+    int kb = 8 * nmax * nmax;  // the estimator stage borrows this region for 3 x 400 doubles of work space
+    if (adapt && kb < 8 * 3 * CMPC_ADAPT_WINDOW) kb = 8 * 3 * CMPC_ADAPT_WINDOW;
+    c.K = o; o += align16(kb);
+  }
   c.g = o; o += align16(8 * nmax);
   c.x = o; o += align16(8 * nmax);
   c.kn = o; o += align16(8 * nmax);
@@ -306,14 +310,15 @@ __device__ __forceinline__ void build_invert_smem(const HessCtx& C, const int* r
 }  // namespace
 
 #include "cmpc_sweep.cuh"
+#include "cmpc_adapt.cuh"
 
-template <class S>
+template <class S, bool ADAPT>
 __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid_constant__ CmpcParams P) {
   constexpr int NT = S::NT;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const int h = P.horizon;
-  const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride, S::NPAD);
+  const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride, S::NPAD, ADAPT);
   unsigned char* recbuf[2] = {smem + cv.rec0, smem + cv.rec1};
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.bars);
   double* sW = reinterpret_cast<double*>(smem + cv.small);  // W[4][3][3]
@@ -380,6 +385,31 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
     phase[buf] ^= 1u;
     const float* rec = reinterpret_cast<const float*>(recbuf[buf]);
     const unsigned char* gait = recbuf[buf] + 4 * (CMPC_REC_TRAJ + 12 * h);
+
+    // ---- 0. periodic-disturbance estimator (Adaptive MPC): xi for this instance, SolverMPC.cpp:688-798 ----
+    if (ADAPT) {
+      double* est_s = red + 40;  // 4 doubles of the reduction scratch
+      if (P.adapt_mode == 0 || P.adapt_mode == 1) {
+        estimate_disturbance<NT>(P, inst, tid, reinterpret_cast<double*>(smem + cv.K), red, est_s);
+      } else {
+        if (tid < 4) est_s[tid] = P.est[(size_t)inst * 4 + tid];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        // compensatory_force = amp + sin(2 pi t f + phase), written to f_est[3] (SolverMPC.cpp:766-772)
+        const double simt = (double)P.sim_time[inst];
+        const float comp = (float)(est_s[1] + sin(2.0 * M_PI * simt * est_s[2] + est_s[3]));
+        float* fe = P.f_est + (size_t)inst * 6;
+        fe[3] = comp;
+        if (P.adapt_mode == 0 || P.adapt_mode == 1)
+          for (int i = 0; i < 4; i++) P.est[(size_t)inst * 4 + i] = est_s[i];
+        if (P.adapt_mode >= 1) {  // g sees Q_qp * f_est (SolverMPC.cpp:810): overwrite the record's xi slots
+          float* xi = reinterpret_cast<float*>(recbuf[buf]) + CMPC_REC_FDIST;
+          for (int i = 0; i < 6; i++) xi[i] = (i == 3) ? comp : fe[i];
+        }
+      }
+      __syncthreads();
+    }
 
     // ---- A1. contact foot-steps (the reference keeps a foot-step unless its fz bound is ~0) ----
     if (tid < 32) {
@@ -760,19 +790,22 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
 // host-side launch plumbing
 // ---------------------------------------------------------------------------
 namespace {
-template <class S>
+template <class S, bool ADAPT>
 int launch_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cmpc_solve_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e =
+      cudaFuncSetAttribute(cmpc_solve_kernel<S, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  cmpc_solve_kernel<S><<<grid, S::NT, smem, st>>>(P);
+  cmpc_solve_kernel<S, ADAPT><<<grid, S::NT, smem, st>>>(P);
   return (int)cudaGetLastError();
 }
-template <class S>
+template <class S, bool ADAPT>
 int occ_t(size_t smem) {
   int nb = 0;
-  if (cudaFuncSetAttribute(cmpc_solve_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (cudaFuncSetAttribute(cmpc_solve_kernel<S, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
     return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<S>, S::NT, smem) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_solve_kernel<S, ADAPT>, S::NT, smem) != cudaSuccess)
+    return -1;
   return nb;
 }
 int npad_of(int shape) {
@@ -785,8 +818,8 @@ int npad_of(int shape) {
 }
 }  // namespace
 
-size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape) {
-  return (size_t)make_carve(horizon, nmax, qcap, cmpc_rec_stride(horizon), npad_of(shape)).total;
+size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape, bool adapt) {
+  return (size_t)make_carve(horizon, nmax, qcap, cmpc_rec_stride(horizon), npad_of(shape), adapt).total;
 }
 
 int cmpc_shape_threads(int shape) {
@@ -798,24 +831,23 @@ int cmpc_shape_threads(int shape) {
   }
 }
 
-int cmpc_launch_solve(const CmpcParams& P, int shape, int grid, void* stream) {
-  size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap, shape);
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (shape) {
-    case CMPC_SHAPE_64: return launch_t<Shape64>(P, grid, smem, st);
-    case CMPC_SHAPE_64W: return launch_t<Shape64w>(P, grid, smem, st);
-    case CMPC_SHAPE_128: return launch_t<Shape128>(P, grid, smem, st);
-    default: return launch_t<ShapeMem>(P, grid, smem, st);
+#define CMPC_DISPATCH(FN, ...)                                                                   \
+  switch (shape) {                                                                               \
+    case CMPC_SHAPE_64: return adapt ? FN<Shape64, true>(__VA_ARGS__) : FN<Shape64, false>(__VA_ARGS__);     \
+    case CMPC_SHAPE_64W: return adapt ? FN<Shape64w, true>(__VA_ARGS__) : FN<Shape64w, false>(__VA_ARGS__);  \
+    case CMPC_SHAPE_128: return adapt ? FN<Shape128, true>(__VA_ARGS__) : FN<Shape128, false>(__VA_ARGS__);  \
+    default: return adapt ? FN<ShapeMem, true>(__VA_ARGS__) : FN<ShapeMem, false>(__VA_ARGS__);              \
   }
+
+int cmpc_launch_solve(const CmpcParams& P, int shape, int grid, void* stream) {
+  const bool adapt = P.adapt_mode >= 0;
+  size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap, shape, adapt);
+  cudaStream_t st = (cudaStream_t)stream;
+  CMPC_DISPATCH(launch_t, P, grid, smem, st)
 }
 
-int cmpc_max_ctas_per_sm(int shape, size_t smem) {
-  switch (shape) {
-    case CMPC_SHAPE_64: return occ_t<Shape64>(smem);
-    case CMPC_SHAPE_64W: return occ_t<Shape64w>(smem);
-    case CMPC_SHAPE_128: return occ_t<Shape128>(smem);
-    default: return occ_t<ShapeMem>(smem);
-  }
+int cmpc_max_ctas_per_sm(int shape, size_t smem, bool adapt) {
+  CMPC_DISPATCH(occ_t, smem)
 }
 
 // ---------------------------------------------------------------------------

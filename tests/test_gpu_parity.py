@@ -197,3 +197,87 @@ def test_full_size_properties(built_lib, B, h, gaits, nseg):
         m = res["active"][i].reshape(-1, 5)[np.flatnonzero(inst["gait"][i])]
         free = np.repeat(~(m != 0).any(1), 3)
         assert np.abs(grad[free]).max(initial=0.0) <= 1e-8
+
+
+def test_disturbance_estimator_parity(built_lib, golden):
+    """Fused estimator stage against the oracle's restatement of fit_sin (SolverMPC.cpp:478-541)."""
+    t, d, est_ref = golden["dist_t"], golden["dist_d"], golden["dist_est"]
+    B, h = len(t), 10
+    inst = synth.make_batch(B, horizon=h, seed=501)
+    sim_time = t[:, -1].copy()
+    b = engine.Batch(B)
+    b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    plain = b.solve_host(inst)
+    # mode 1: estimate and apply in the same launch
+    b.upload_disturbance(t, d, sim_time, 1)
+    res = b.solve_host(inst)
+    est, fest = b.download_disturbance()
+    assert (est[:, 2] == est_ref[:, 2]).all()                      # same DFT peak bin -> identical frequency
+    np.testing.assert_allclose(est[:, :2], est_ref[:, :2], rtol=1e-10, atol=1e-12)
+    comp = est_ref[:, 1] + np.sin(2 * np.pi * sim_time.astype(np.float64) * est_ref[:, 2] + est_ref[:, 3])
+    np.testing.assert_allclose(fest[:, 3], comp.astype(np.float32), rtol=2e-7)
+    assert (fest[:, [0, 1, 2, 4, 5]] == 0).all()
+    # the fused launch equals an explicit-xi launch with the same f_est, bit for bit
+    b.upload_disturbance(None, None, None, -1)
+    explicit = b.solve_host(inst, f_dist=fest)
+    assert (explicit["forces"] == res["forces"]).all()
+    assert np.abs(res["forces"] - plain["forces"]).max() > 1e-3
+    # mode 0: estimate only, g sees no disturbance (history of 400..500 samples)
+    b.upload_disturbance(t, d, sim_time, 0)
+    res0 = b.solve_host(inst)
+    assert (res0["forces"] == plain["forces"]).all()
+    # mode 2: no new fit, stored estimate re-evaluated at a later time and applied
+    later = sim_time + np.float32(0.03)
+    b.upload_disturbance(None, None, later, 2)
+    res2 = b.solve_host(inst)
+    est2, fest2 = b.download_disturbance()
+    assert (est2 == est).all()
+    comp2 = est[:, 1] + np.sin(2 * np.pi * later.astype(np.float64) * est[:, 2])
+    np.testing.assert_allclose(fest2[:, 3], comp2.astype(np.float32), rtol=2e-7)
+    if O.available():
+        st = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"])
+        for i in range(B):
+            r = O.solve(st, O.make_update(inst, i, h), f_dist=fest2[i].astype(np.float64))
+            assert_forces_close(res2["forces"][i], r["x"], "adaptive instance %d" % i)
+    b.close()
+
+
+@pytest.mark.skipif(not O.available(), reason="oracle/_ref did not travel")
+def test_single_instance_adaptive_state_machine(built_lib, golden):
+    """The reference interface with the adaptive hook: 400 / 500-sample rules of SolverMPC.cpp:704-814."""
+    import ctypes as C
+    L = engine.lib()
+    L.cmpc_reset_history()
+    inst = golden_case(golden, "trot10")
+    h, i = 10, 0
+    arr = lambda k: np.ascontiguousarray(inst[k][i], dtype=np.float32)
+    p, v, q, w, r, wt, tr = [arr(k) for k in ("p", "v", "q", "w", "r", "weights", "traj")]
+    gait = np.ascontiguousarray(inst["gait"][i], dtype=np.int32)
+    st = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    upd = O.make_update(inst, i, h)
+    ad = O.Adapt()
+    fd_ref = np.zeros(6)
+    fest = np.zeros(6, dtype=np.float32)
+    fext = np.zeros(6, dtype=np.float32)
+    L.setup_problem(inst["dt"], h, inst["mu"], inst["f_max"])
+    L.update_x_drag(float(inst["x_drag"][i]))
+    checked = 0
+    for step in range(520):
+        tnow = np.float32(0.03 * step)
+        fext[3] = np.float32(0.4 + 1.3 * np.sin(2 * np.pi * 0.9 * float(tnow) + 0.3))
+        L.cmpc_set_external_force(fext.ctypes.data)
+        L.cmpc_set_simulation_time(float(tnow))
+        L.update_problem_data_floats(p.ctypes.data, v.ctypes.data, q.ctypes.data, w.ctypes.data, r.ctypes.data,
+                                     0.0, 0.0, 0.0, wt.ctypes.data, tr.ctypes.data, float(inst["alpha"][i]),
+                                     gait.ctypes.data)
+        use = O.lib().cmpc_oracle_adapt_step(C.byref(ad), float(tnow), float(fext[3]),
+                                             fd_ref.ctypes.data_as(C.POINTER(C.c_double)))
+        if step in (10, 398, 399, 450, 499, 500, 501, 519):
+            L.cmpc_get_disturbance_estimate(fest.ctypes.data)
+            assert abs(float(fest[3]) - float(ad.f_est[3])) <= 2e-6 * max(1.0, abs(float(ad.f_est[3]))), step
+            ref = O.solve(st, upd, f_dist=fd_ref if use else None)
+            got = np.array([L.get_solution(k) for k in range(12 * h)])
+            assert_forces_close(got, ref["x"], "adaptive step %d" % step)
+            checked += 1
+    assert checked == 8 and use == 1
+    L.cmpc_reset_history()
