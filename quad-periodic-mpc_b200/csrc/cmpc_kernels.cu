@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
       C.m2 = minv * minv;
       C.alpha2 = 2.0 * (double)rec[CMPC_REC_ALPHA];
       // ---- D. K <- H^-1 (H is SPD: 2aI + 2B'SB, a > 0) ----
-      if (S::REG) build_invert_regtile2<S>(C, rowinfo, n, tid, cbuf, K);
+      if (S::REG) build_invert_regtile2<S>(C, rowinfo, n, tid, cbuf, K, red);
       else build_invert_smem<NT>(C, rowinfo, n, tid, kn, K);
       __syncthreads();
       // x = -H^-1 g, slacks of every candidate row

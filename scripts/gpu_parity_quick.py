@@ -15,6 +15,7 @@ def run(h, gaits, spread, B, seed, nseg=None, ncheck=64):
     t1 = time.time()
     res = b.solve_host(inst)
     t2 = time.time()
+    b.upload(inst); b.solve(); b.solve(); b.sync()
     ms = b.last_solve_ms()
     st = O.make_setup(0.03, h, 0.4, 120.0)
     worst = 0; objrel = 0; itd = 0
