@@ -65,7 +65,7 @@ __host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_s
   c.fs = o; o += align16(4 * CMPC_MAX_FS);
   c.fsinv = o; o += align16(4 * CMPC_MAX_FS);
   c.rowinfo = o; o += align16(4 * (npad > nmax ? npad : nmax));
-  c.cbuf = o; o += align16(8 * 2 * (npad + 2));
+  c.cbuf = o; o += align16(8 * (2 * (npad + 2) + 2 * npad));  // pivot rows (x2) + diagonal copies (x2)
   {
     int kb = 8 * nmax * nmax;  // the estimator stage borrows this region for 3 x 400 doubles of work space
     if (adapt && kb < 8 * 3 * CMPC_ADAPT_WINDOW) kb = 8 * 3 * CMPC_ADAPT_WINDOW;
@@ -184,6 +184,7 @@ struct HessCtx {
   const double* sPO;
   int h;
   const double* wp;    // shared, position weights [3] then velocity weights [3]
+  const int* fs;       // shared, reduced foot-step -> global foot-step
   double xd, m2, alpha2;
 };
 
@@ -576,6 +577,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
       HessCtx C;
       C.sig = P.sigma; C.sPT = sPT; C.sPO = sPO; C.h = h;
       C.wp = sScal + 1;
+      C.fs = fs;
       C.xd = rec[CMPC_REC_XDRAG];
       C.m2 = minv * minv;
       C.alpha2 = 2.0 * (double)rec[CMPC_REC_ALPHA];
@@ -663,7 +665,8 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
             }
             __syncthreads();
           }
-          const double t2 = dependent ? 1e300 : -s[p] / rho2;
+          const double rho2_inv = dependent ? 0.0 : fast_rcp(rho2);
+          const double t2 = dependent ? 1e300 : -s[p] * rho2_inv;
           const double t1 = ratio;
           const double t = fmin(t1, t2);
           if (t >= 1e299) { status = CMPC_ST_INFEASIBLE; done = true; break; }
@@ -685,7 +688,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
           flops_acc += 2.0 * (4.0 * n + 4.0 * q + (double)q * q + 3.0 * n * (2.0 * q < n ? 2.0 * q : (double)n) + 4.0 * m + n);
           if (full) {
             if (q >= P.qcap) { status = CMPC_ST_WSOVERFLOW; done = true; break; }
-            const double inv = 1.0 / rho2;
+            const double inv = rho2_inv;
             for (int k = tid; k < q; k += NT) {
               double rk = rvec[k] * inv;
               for (int l = 0; l <= k; l++) Pp[k * (k + 1) / 2 + l] = fma(rk, rvec[l], Pp[k * (k + 1) / 2 + l]);

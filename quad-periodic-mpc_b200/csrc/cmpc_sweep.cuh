@@ -40,18 +40,42 @@ __device__ __forceinline__ void build_invert_regtile2(const HessCtx& C, const in
                                                       double* K, double* red) {
   constexpr int TY = S::TY, TX = S::TX, TM = S::TM, TN = S::TN, NPAD = S::NPAD, NT = S::NT;
   const int ty = tid / TX, tx = tid - ty * TX;
-  // H into shared memory: lower triangle evaluated once and mirrored; track the largest diagonal entry
+  // H into shared memory, one 3x3 foot-step pair block (j1 >= j2) per thread and mirrored: the horizon
+  // sums are fetched once per block and the component pattern of the x_drag terms is static.
   double dmax = 0.0;
   {
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int I = warp; I < n; I += NT / 32) {
-      const int ri = rowinfo[I];
-      for (int J = lane; J <= I; J += 32) {
-        const double v = hess_entry(C, ri, rowinfo[J], I == J);
-        K[I * n + J] = v;
-        K[J * n + I] = v;
-        if (I == J) dmax = fmax(dmax, v);
+    const int nc = n / 3, nb = nc * (nc + 1) / 2, hh = C.h * C.h;
+    for (int blk = tid; blk < nb; blk += NT) {
+      int j1 = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
+      while ((j1 + 1) * (j1 + 2) / 2 <= blk) j1++;
+      while (j1 * (j1 + 1) / 2 > blk) j1--;
+      const int j2 = blk - j1 * (j1 + 1) / 2;
+      const int k1 = C.fs[j1], k2 = C.fs[j2];
+      const int sa = k1 >> 2, fi = k1 & 3, sb = k2 >> 2, fj = k2 & 3;
+      const int ab = sa * C.h + sb, ba = sb * C.h + sa;
+      const double s11 = __ldg(C.sig + CMPC_SIG_11 * hh + ab), s22 = __ldg(C.sig + CMPC_SIG_22 * hh + ab);
+      double x20 = 0.0, x02 = 0.0, x00 = 0.0;  // x_drag couplings (z,x), (x,z), (x,x)
+      if (C.xd != 0.0) {
+        x20 = C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_23 * hh + ab) + C.wp[5] * __ldg(C.sig + CMPC_SIG_12 * hh + ab));
+        x02 = C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_23 * hh + ba) + C.wp[5] * __ldg(C.sig + CMPC_SIG_12 * hh + ba));
+        x00 = C.xd * C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_33 * hh + ab) + C.wp[5] * s22);
       }
+      const double* pt = C.sPT + (fi * 4 + fj) * 9;
+      const double* po = C.sPO + (fi * 4 + fj) * 9;
+#pragma unroll
+      for (int c1 = 0; c1 < 3; c1++)
+#pragma unroll
+        for (int c2 = 0; c2 < 3; c2++) {
+          double pv = 0.0;
+          if (c1 == c2) pv = s22 * C.wp[c1] + s11 * C.wp[3 + c1];
+          if (c1 == 2 && c2 == 0) pv += x20;
+          if (c1 == 0 && c2 == 2) pv += x02;
+          if (c1 == 0 && c2 == 0) pv += x00;
+          double v = 2.0 * (s22 * pt[c1 * 3 + c2] + s11 * po[c1 * 3 + c2] + pv * C.m2);
+          if (j1 == j2 && c1 == c2) { v += C.alpha2; dmax = fmax(dmax, v); }
+          K[(3 * j1 + c1) * n + 3 * j2 + c2] = v;
+          K[(3 * j2 + c2) * n + 3 * j1 + c1] = v;
+        }
     }
   }
   {
@@ -72,11 +96,20 @@ __device__ __forceinline__ void build_invert_regtile2(const HessCtx& C, const in
       const int i = ty + TY * a, j = tx + TX * b;
       A[a][b] = (i < n && j < n) ? K[i * n + j] * scale : (i == j ? 0.5 : 0.0);  // harmless padding beyond n
     }
+  // Look-ahead pivots: a shared copy of the (scaled) diagonal is advanced alongside the tiles with the
+  // very same fma, so every thread can form pivot k+1 and start its reciprocal while it is still
+  // applying pivot k -- the MUFU + Newton chain leaves the per-pivot critical path.
+  double* dg = cbuf + 2 * (NPAD + 2);  // two diagonal buffers of NPAD
+  for (int i = tid; i < NPAD; i += NT) dg[i] = (i < n) ? K[i * n + i] * scale : 0.5;
+  __syncthreads();
+  double dinv = fast_rcp(dg[0]);
   int par = 0;
 #pragma unroll 1
   for (int k = 0; k < n; k++) {
     const int a = k / TY, kk = k - a * TY;  // row block / row-owner ty
     double* cb = cbuf + par * (NPAD + 2);
+    const double* dold = dg + par * NPAD;
+    double* dnew = dg + (par ^ 1) * NPAD;
     if (ty == kk) {
 #pragma unroll
       for (int aa = 0; aa < TM; aa++) {
@@ -85,23 +118,32 @@ __device__ __forceinline__ void build_invert_regtile2(const HessCtx& C, const in
           for (int bb = 0; bb < TN; bb++) {
             const int j = tx + TX * bb;
             double v = A[aa][bb];
-            if (j == k) { cb[NPAD] = v; v -= 1.0; }
+            if (j == k) v -= 1.0;
             cb[j] = v;
           }
         }
       }
     }
     __syncthreads();
-    const double dinv = fast_rcp(cb[NPAD]);
     double ci[TM], cjd[TN];
 #pragma unroll
     for (int aa = 0; aa < TM; aa++) ci[aa] = cb[ty + TY * aa];
 #pragma unroll
     for (int bb = 0; bb < TN; bb++) cjd[bb] = cb[tx + TX * bb] * dinv;
+    // next pivot and its reciprocal (same arithmetic as the tile update below)
+    const int k1 = (k + 1 < n) ? k + 1 : k;
+    const double c1 = cb[k1];
+    const double dnext = fma(-c1, c1 * dinv, dold[k1]);
+    const double dinv_next = fast_rcp(dnext);
+    if (tid < NPAD) {
+      const double c = cb[tid];
+      dnew[tid] = fma(-c, c * dinv, dold[tid]);
+    }
 #pragma unroll
     for (int aa = 0; aa < TM; aa++)
 #pragma unroll
       for (int bb = 0; bb < TN; bb++) A[aa][bb] = fma(-ci[aa], cjd[bb], A[aa][bb]);
+    dinv = dinv_next;
     par ^= 1;
   }
   // -swept = (scaled H)^-1; undo the scaling and the +2 carried by every diagonal element
