@@ -117,6 +117,8 @@ struct cmpc_batch {
   signed char* d_active = nullptr;
   int* d_overflow[2] = {nullptr, nullptr};  // per stream: [capacity] list + [1] count at the end
   unsigned long long* d_flops = nullptr;
+  double* d_gws = nullptr;  // global workspace of the large-problem tier, grown on demand
+  size_t gws_bytes = 0;
   // adaptive stage
   double* d_twiddle = nullptr;
   float* d_gk = nullptr;
@@ -255,16 +257,33 @@ int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
       if (P.adapt_mode == 0 || P.adapt_mode == 1) P.adapt_mode = 2;  // the estimate already exists
     }
     size_t smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap, shape, P.adapt_mode >= 0);
-    if (smem > 227 * 1024) {
-      g_err = "cmpc_batch_solve: instance too large for shared memory (n=" + std::to_string(P.nmax) + ")";
-      return CMPC_E_ARG;
+    if (smem > 200 * 1024 && shape == CMPC_SHAPE_MEM) {
+      // the matrix no longer fits shared memory: keep K and P in a per-CTA global workspace (L2 resident)
+      shape = CMPC_SHAPE_GMEM;
+      smem = cmpc_smem_bytes(P.horizon, P.nmax, P.qcap, shape, P.adapt_mode >= 0);
     }
     int per_sm = cmpc_max_ctas_per_sm(shape, smem, P.adapt_mode >= 0);
     if (per_sm < 1) {
       g_err = "cmpc_batch_solve: kernel not launchable on this device (no sm_100a image?)";
       return CMPC_E_NODEVICE;
     }
+    if (shape == CMPC_SHAPE_GMEM) per_sm = std::min(per_sm, 2);
     int grid = std::min(count, b->sm_count * per_sm);
+    if (shape == CMPC_SHAPE_GMEM) {
+      const size_t stride = (size_t)P.nmax * P.nmax + (size_t)(P.nmax + 1) * (P.nmax + 2) / 2;
+      const size_t need = sizeof(double) * stride * (size_t)b->sm_count * 2 * 2;  // two streams' worth
+      if (need > b->gws_bytes) {
+        for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+        if (b->d_gws) CK(cudaFree(b->d_gws));
+        b->d_gws = nullptr;
+        CK(cudaMalloc(&b->d_gws, need));
+        b->gws_bytes = need;
+      }
+      P.gws = b->d_gws + (size_t)si * stride * (size_t)b->sm_count * 2;
+      P.gws_stride = stride;
+    } else {
+      P.gws = nullptr;
+    }
     int rc = cmpc_launch_solve(P, shape, grid, st);
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_solve_kernel launch");
     b->launches++;
@@ -341,7 +360,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   for (int i = 0; i < 2; i++) cudaStreamSynchronize(b->stream[i]);
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
   cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops);
-  cudaFree(b->d_overflow[0]); cudaFree(b->d_overflow[1]);
+  cudaFree(b->d_overflow[0]); cudaFree(b->d_overflow[1]); cudaFree(b->d_gws);
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFreeHost(b->h_forces); cudaFreeHost(b->h_obj); cudaFreeHost(b->h_status); cudaFreeHost(b->h_iters);

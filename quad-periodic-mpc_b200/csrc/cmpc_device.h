@@ -82,6 +82,9 @@ struct CmpcParams {
   const float* sim_time;      // [count]
   double* est;                // [count][4] stat, amp, freq, phase
   float* f_est;               // [count][6]
+  // global-memory workspace tier (reduced problems too large for shared memory): K and P per CTA
+  double* gws;                // NULL unless shape == CMPC_SHAPE_GMEM
+  size_t gws_stride;          // doubles per CTA
 };
 
 // kernel shapes (cmpc_kernels.cu): register-tile tiers by reduced problem size, shared-memory tier beyond
@@ -89,6 +92,7 @@ struct CmpcParams {
 #define CMPC_SHAPE_64W 1   /* n <= 64, 128 threads, 8x4 register tiles */
 #define CMPC_SHAPE_128 2   /* n <= 128, 256 threads, 8x8 register tiles */
 #define CMPC_SHAPE_MEM 3   /* matrix in shared memory, 128 threads */
+#define CMPC_SHAPE_GMEM 4  /* matrix and working-set inverse in an L2-resident global workspace, 128 threads */
 
 size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape, bool adapt);
 int cmpc_shape_threads(int shape);

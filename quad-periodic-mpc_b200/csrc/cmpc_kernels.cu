@@ -52,7 +52,7 @@ struct Carve {
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_stride, int npad, bool adapt) {
+__host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_stride, int npad, bool adapt, bool gmem) {
   Carve c;
   int o = 0;
   int nc = nmax / 3, m = 5 * nc;
@@ -67,7 +67,7 @@ __host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_s
   c.rowinfo = o; o += align16(4 * (npad > nmax ? npad : nmax));
   c.cbuf = o; o += align16(8 * (2 * (npad + 2) + 2 * npad));  // pivot rows (x2) + diagonal copies (x2)
   {
-    int kb = 8 * nmax * nmax;  // the estimator stage borrows this region for 3 x 400 doubles of work space
+    int kb = gmem ? 0 : 8 * nmax * nmax;  // the estimator stage borrows this region for 3 x 400 doubles of work space
     if (adapt && kb < 8 * 3 * CMPC_ADAPT_WINDOW) kb = 8 * 3 * CMPC_ADAPT_WINDOW;
     c.K = o; o += align16(kb);
   }
@@ -84,7 +84,7 @@ __host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_s
   c.d = o; o += align16(8 * (qcap + 1));
   c.r = o; o += align16(8 * (qcap + 1));
   c.col = o; o += align16(8 * (qcap + 1));
-  c.Pp = o; o += align16(8 * ((qcap + 1) * (qcap + 2) / 2));
+  c.Pp = o; o += gmem ? 0 : align16(8 * ((qcap + 1) * (qcap + 2) / 2));
   c.red = o; o += 512;
   c.total = o;
   return c;
@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const int h = P.horizon;
-  const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride, S::NPAD, ADAPT);
+  const bool gmem = P.gws != nullptr;
+  const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride, S::NPAD, ADAPT, gmem);
   unsigned char* recbuf[2] = {smem + cv.rec0, smem + cv.rec1};
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.bars);
   double* sW = reinterpret_cast<double*>(smem + cv.small);  // W[4][3][3]
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
   int* fsinv = reinterpret_cast<int*>(smem + cv.fsinv);     // global foot-step -> reduced or -1
   int* rowinfo = reinterpret_cast<int*>(smem + cv.rowinfo); // reduced variable -> step | foot<<8 | comp<<16
   double* cbuf = reinterpret_cast<double*>(smem + cv.cbuf);
-  double* K = reinterpret_cast<double*>(smem + cv.K);
+  double* K = gmem ? P.gws + (size_t)blockIdx.x * P.gws_stride : reinterpret_cast<double*>(smem + cv.K);
   double* g = reinterpret_cast<double*>(smem + cv.g);
   double* x = reinterpret_cast<double*>(smem + cv.x);
   double* kn = reinterpret_cast<double*>(smem + cv.kn);
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
   double* dvec = reinterpret_cast<double*>(smem + cv.d);
   double* rvec = reinterpret_cast<double*>(smem + cv.r);
   double* col = reinterpret_cast<double*>(smem + cv.col);
-  double* Pp = reinterpret_cast<double*>(smem + cv.Pp);
+  double* Pp = gmem ? K + (size_t)P.nmax * P.nmax : reinterpret_cast<double*>(smem + cv.Pp);
   double* red = reinterpret_cast<double*>(smem + cv.red);
   int* redi = reinterpret_cast<int*>(red + 32);  // shared ints: [0]=nc
 
@@ -822,7 +823,8 @@ int npad_of(int shape) {
 }  // namespace
 
 size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape, bool adapt) {
-  return (size_t)make_carve(horizon, nmax, qcap, cmpc_rec_stride(horizon), npad_of(shape), adapt).total;
+  return (size_t)make_carve(horizon, nmax, qcap, cmpc_rec_stride(horizon), npad_of(shape), adapt,
+                            shape == CMPC_SHAPE_GMEM).total;
 }
 
 int cmpc_shape_threads(int shape) {

@@ -52,12 +52,14 @@ def test_golden_parity(built_lib, golden, case):
 
 
 @pytest.mark.skipif(not O.available(), reason="oracle/_ref did not travel")
-@pytest.mark.parametrize("h,gaits,spread,seed,nseg", [
-    (10, ("trot",), 1.0, 101, None), (10, ("trot",), 3.0, 102, None),
-    (16, ("trot", "bound", "pace", "gallop"), 1.5, 103, 10), (10, ("stand",), 2.0, 104, None),
-    (5, ("trot",), 1.0, 105, 10), (1, ("stand",), 1.0, 106, None), (12, ("walk2", "trotrun"), 2.0, 107, 10)])
-def test_live_oracle_parity(built_lib, h, gaits, spread, seed, nseg):
-    B = 96
+@pytest.mark.parametrize("h,gaits,spread,seed,nseg,B", [
+    (10, ("trot",), 1.0, 101, None, 96), (10, ("trot",), 3.0, 102, None, 96),
+    (16, ("trot", "bound", "pace", "gallop"), 1.5, 103, 10, 96), (10, ("stand",), 2.0, 104, None, 96),
+    (5, ("trot",), 1.0, 105, 10, 96), (1, ("stand",), 1.0, 106, None, 96),
+    (12, ("walk2", "trotrun"), 2.0, 107, 10, 96),
+    # maximum sizes: every foot down over the longest horizons (n = 192, 228): global-workspace tier
+    (16, ("stand",), 1.5, 108, None, 12), (19, ("stand",), 1.5, 109, None, 8), (13, ("stand",), 1.0, 110, None, 12)])
+def test_live_oracle_parity(built_lib, h, gaits, spread, seed, nseg, B):
     inst = synth.make_batch(B, horizon=h, seed=seed, gaits=gaits, spread=spread, n_segment=nseg)
     res = solve(inst)
     st = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"])
