@@ -162,6 +162,12 @@ int cmpc_batch_reset_counters(cmpc_batch* b);
 /* Algorithmic FP64 flop count since the last reset, accumulated by the kernel from its own loop counters. */
 int cmpc_batch_last_flops(cmpc_batch* b, double* flops);
 
+/* Phase clocks (profiling aid): when enabled, thread 0 of every CTA charges SM cycles to the kernel's
+ * phases (record wait, estimator, condensation, H assembly, tile load, sweep, K store, active set,
+ * outputs); cycles[i] is the sum over CTAs since enabling.  Off by default. */
+int cmpc_batch_enable_phase_clocks(cmpc_batch* b, int on);
+int cmpc_batch_phase_cycles(cmpc_batch* b, unsigned long long* cycles, int n);
+
 /* Measured FP64 FMA throughput of the device (dependent-free DFMA chains on every SM), the
  * denominator of the solve kernel's roofline; TFLOP/s. */
 int cmpc_measure_fp64_peak(int device, double* tflops);

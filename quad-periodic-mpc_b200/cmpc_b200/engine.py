@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libcmpc_b200.so")
+LIB_PATH = os.environ.get("CMPC_LIB") or os.path.join(_PKG, "libcmpc_b200.so")  # CMPC_LIB: experiment builds
 
 ST_SOLVED, ST_EMPTY, ST_MAXITER, ST_INFEASIBLE, ST_WSOVERFLOW, ST_CAPACITY = range(6)
 
@@ -52,6 +52,8 @@ def lib():
         L.cmpc_batch_mark.argtypes = [C.c_void_p, C.c_int]
         L.cmpc_batch_marked_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.cmpc_batch_reset_counters.argtypes = [C.c_void_p]
+        L.cmpc_batch_enable_phase_clocks.argtypes = [C.c_void_p, C.c_int]
+        L.cmpc_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
         L.cmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.cmpc_batch_device_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.cmpc_batch_device_forces.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -208,6 +210,16 @@ class Batch:
         f = C.c_double()
         _check(lib().cmpc_batch_last_flops(self._h, C.byref(f)), "cmpc_batch_last_flops")
         return f.value
+
+    PHASES = ("wait", "adapt", "prep", "hess", "load", "sweep", "store", "qp", "out")
+
+    def enable_phase_clocks(self, on=True):
+        _check(lib().cmpc_batch_enable_phase_clocks(self._h, int(on)), "cmpc_batch_enable_phase_clocks")
+
+    def phase_cycles(self):
+        arr = (C.c_ulonglong * len(self.PHASES))()
+        _check(lib().cmpc_batch_phase_cycles(self._h, arr, len(self.PHASES)), "cmpc_batch_phase_cycles")
+        return dict(zip(self.PHASES, [int(x) for x in arr]))
 
     def upload_disturbance(self, win_t, win_d, sim_time, mode):
         """mode 0 estimate, 1 estimate+apply, 2 apply the stored estimate (windows may be None), <0 off."""

@@ -117,6 +117,7 @@ struct cmpc_batch {
   signed char* d_active = nullptr;
   int* d_overflow[2] = {nullptr, nullptr};  // per stream: [capacity] list + [1] count at the end
   unsigned long long* d_flops = nullptr;
+  unsigned long long* d_phase = nullptr;  // CMPC_PH_COUNT phase clocks, allocated by cmpc_batch_enable_phase_clocks
   double* d_gws = nullptr;  // global workspace of the large-problem tier, grown on demand
   size_t gws_bytes = 0;
   // adaptive stage
@@ -221,6 +222,7 @@ int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
   P.iterations = b->d_iters + first;
   P.active = b->d_active + (size_t)first * 20 * b->h;
   P.flops = b->d_flops;
+  P.phase_cycles = b->d_phase;
   if (b->adapt_mode >= 0) {
     P.twiddle = b->d_twiddle;
     P.gk = b->d_gk;
@@ -359,7 +361,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaSetDevice(b->device);
   for (int i = 0; i < 2; i++) cudaStreamSynchronize(b->stream[i]);
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
-  cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops);
+  cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops); cudaFree(b->d_phase);
   cudaFree(b->d_overflow[0]); cudaFree(b->d_overflow[1]); cudaFree(b->d_gws);
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
@@ -634,6 +636,30 @@ int cmpc_batch_last_flops(cmpc_batch* b, double* flops) {
   CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream[0]));
   CK(cudaStreamSynchronize(b->stream[0]));
   *flops = (double)*b->h_flops;
+  return CMPC_OK;
+}
+
+int cmpc_batch_enable_phase_clocks(cmpc_batch* b, int on) {
+  if (!b) return fail_arg("cmpc_batch_enable_phase_clocks: null batch");
+  CK(cudaSetDevice(b->device));
+  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+  if (on && !b->d_phase) CK(cudaMalloc(&b->d_phase, sizeof(unsigned long long) * CMPC_PH_COUNT));
+  if (!on && b->d_phase) {
+    CK(cudaFree(b->d_phase));
+    b->d_phase = nullptr;
+  }
+  if (b->d_phase) CK(cudaMemset(b->d_phase, 0, sizeof(unsigned long long) * CMPC_PH_COUNT));
+  return CMPC_OK;
+}
+
+int cmpc_batch_phase_cycles(cmpc_batch* b, unsigned long long* cycles, int n) {
+  if (!b || !cycles || n < 1) return fail_arg("cmpc_batch_phase_cycles: bad arguments");
+  if (!b->d_phase) { g_err = "cmpc_batch_phase_cycles: phase clocks are not enabled"; return CMPC_E_STATE; }
+  CK(cudaSetDevice(b->device));
+  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+  unsigned long long tmp[CMPC_PH_COUNT];
+  CK(cudaMemcpy(tmp, b->d_phase, sizeof(tmp), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) cycles[i] = i < CMPC_PH_COUNT ? tmp[i] : 0ull;
   return CMPC_OK;
 }
 

@@ -85,7 +85,20 @@ struct CmpcParams {
   // global-memory workspace tier (reduced problems too large for shared memory): K and P per CTA
   double* gws;                // NULL unless shape == CMPC_SHAPE_GMEM
   size_t gws_stride;          // doubles per CTA
+  // optional phase clocks (profiling aid): CMPC_PH_COUNT counters of SM cycles summed over CTAs, thread 0 only
+  unsigned long long* phase_cycles;
 };
+
+#define CMPC_PH_WAIT 0    /* record wait (mbarrier) */
+#define CMPC_PH_ADAPT 1   /* disturbance estimator */
+#define CMPC_PH_PREP 2    /* state, W, tracking error, aggregates, g */
+#define CMPC_PH_HESS 3    /* H assembly */
+#define CMPC_PH_LOAD 4    /* tile load, scaling, diagonal copy */
+#define CMPC_PH_SWEEP 5   /* pivot loop */
+#define CMPC_PH_STORE 6   /* K store, x0 = -K g, slacks */
+#define CMPC_PH_QP 7      /* active-set iterations */
+#define CMPC_PH_OUT 8     /* objective, outputs */
+#define CMPC_PH_COUNT 9
 
 // kernel shapes (cmpc_kernels.cu): register-tile tiers by reduced problem size, shared-memory tier beyond
 #define CMPC_SHAPE_64 0    /* n <= 64, 64 threads, 8x8 register tiles */

@@ -30,10 +30,11 @@ namespace {
 // NPAD x NPAD (padded) Hessian; REG = false keeps the matrix in shared memory
 // (any n that fits), used beyond the register tiers.
 // ---------------------------------------------------------------------------
-template <int TY_, int TX_, int TM_, int TN_, bool REG_, int MINB_>
+template <int TY_, int TX_, int TM_, int TN_, bool REG_, int MINB_, bool GMEM_ = false>
 struct Shape {
   static constexpr int TY = TY_, TX = TX_, TM = TM_, TN = TN_, NT = TY_ * TX_, NPAD = TY_ * TM_, MINB = MINB_;
   static constexpr bool REG = REG_;
+  static constexpr bool GMEM = GMEM_;  // K and the working-set inverse live in a per-CTA global workspace
   static_assert(TY_ * TM_ == TX_ * TN_, "square padded matrix");
   static_assert(TX_ % TY_ == 0, "column owner derivable from the row block");
 };
@@ -41,6 +42,7 @@ using Shape64 = Shape<8, 8, 8, 8, true, 4>;       // n <= 64, 64 threads, 8x8 ti
 using Shape64w = Shape<8, 16, 8, 4, true, 4>;     // n <= 64, 128 threads, 8x4 tiles
 using Shape128 = Shape<16, 16, 8, 8, true, 1>;    // n <= 128, 256 threads, 8x8 tiles
 using ShapeMem = Shape<8, 16, 8, 4, false, 1>;    // any n that fits shared memory, 128 threads
+using ShapeGmem = Shape<8, 16, 8, 4, false, 1, true>;  // beyond shared memory: L2-resident workspace
 
 // ---------------------------------------------------------------------------
 // shared memory carve-up (same arithmetic on host and device)
@@ -177,6 +179,25 @@ __device__ __forceinline__ double& psym(double* Pp, int k, int l) {
   return (k >= l) ? Pp[k * (k + 1) / 2 + l] : Pp[l * (l + 1) / 2 + k];
 }
 
+// phase clocks (profiling aid, off unless CmpcParams::phase_cycles is set): thread 0 of a CTA charges the
+// cycles since its previous tick to a phase.  State lives in shared memory so the feature costs no registers.
+struct PhaseClock {
+  unsigned long long* out;  // global counters or nullptr
+  long long* last;          // shared
+  __device__ __forceinline__ void init(unsigned long long* o, long long* smem_slot, int tid) {
+    out = (tid == 0) ? o : nullptr;
+    last = smem_slot;
+    if (out) *last = clock64();
+  }
+  __device__ __forceinline__ void tick(int phase) const {
+    if (out) {
+      const long long now = clock64();
+      atomicAdd(out + phase, (unsigned long long)(now - *last));
+      *last = now;
+    }
+  }
+};
+
 // per-instance constants the Hessian entries are assembled from
 struct HessCtx {
   const double* sig;   // global, 5 tables of h*h
@@ -312,6 +333,7 @@ __device__ __forceinline__ void build_invert_smem(const HessCtx& C, const int* r
 
 #include "cmpc_sweep.cuh"
 #include "cmpc_adapt.cuh"
+#include "cmpc_qp.cuh"
 
 template <class S, bool ADAPT>
 __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid_constant__ CmpcParams P) {
@@ -319,7 +341,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const int h = P.horizon;
-  const bool gmem = P.gws != nullptr;
+  constexpr bool gmem = S::GMEM;  // compile-time, so that K stays a shared-window pointer (LDS, not generic LD) otherwise
   const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride, S::NPAD, ADAPT, gmem);
   unsigned char* recbuf[2] = {smem + cv.rec0, smem + cv.rec1};
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.bars);
@@ -334,7 +356,9 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
   int* fsinv = reinterpret_cast<int*>(smem + cv.fsinv);     // global foot-step -> reduced or -1
   int* rowinfo = reinterpret_cast<int*>(smem + cv.rowinfo); // reduced variable -> step | foot<<8 | comp<<16
   double* cbuf = reinterpret_cast<double*>(smem + cv.cbuf);
-  double* K = gmem ? P.gws + (size_t)blockIdx.x * P.gws_stride : reinterpret_cast<double*>(smem + cv.K);
+  double* K;
+  if constexpr (gmem) K = P.gws + (size_t)blockIdx.x * P.gws_stride;
+  else K = reinterpret_cast<double*>(smem + cv.K);
   double* g = reinterpret_cast<double*>(smem + cv.g);
   double* x = reinterpret_cast<double*>(smem + cv.x);
   double* kn = reinterpret_cast<double*>(smem + cv.kn);
@@ -348,7 +372,9 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
   double* dvec = reinterpret_cast<double*>(smem + cv.d);
   double* rvec = reinterpret_cast<double*>(smem + cv.r);
   double* col = reinterpret_cast<double*>(smem + cv.col);
-  double* Pp = gmem ? K + (size_t)P.nmax * P.nmax : reinterpret_cast<double*>(smem + cv.Pp);
+  double* Pp;
+  if constexpr (gmem) Pp = K + (size_t)P.nmax * P.nmax;
+  else Pp = reinterpret_cast<double*>(smem + cv.Pp);
   double* red = reinterpret_cast<double*>(smem + cv.red);
   int* redi = reinterpret_cast<int*>(red + 32);  // shared ints: [0]=nc
 
@@ -370,6 +396,8 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
 
   const double dt = P.dt, mu_inv = P.mu_inv, minv = P.mass_inv;
   double flops_acc = 0.0;
+  PhaseClock pc;
+  pc.init(P.phase_cycles, reinterpret_cast<long long*>(red + 48), tid);
 
   for (int buf = 0; slot < count; slot += gridDim.x, buf ^= 1) {
     const int inst = P.worklist ? P.worklist[slot] : slot;
@@ -385,6 +413,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
     }
     mbar_wait(&bars[buf], phase[buf]);
     phase[buf] ^= 1u;
+    pc.tick(CMPC_PH_WAIT);
     const float* rec = reinterpret_cast<const float*>(recbuf[buf]);
     const unsigned char* gait = recbuf[buf] + 4 * (CMPC_REC_TRAJ + 12 * h);
 
@@ -411,6 +440,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
         }
       }
       __syncthreads();
+      pc.tick(CMPC_PH_ADAPT);
     }
 
     // ---- A1. contact foot-steps (the reference keeps a foot-step unless its fz bound is ~0) ----
@@ -582,8 +612,9 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
       C.xd = rec[CMPC_REC_XDRAG];
       C.m2 = minv * minv;
       C.alpha2 = 2.0 * (double)rec[CMPC_REC_ALPHA];
+      pc.tick(CMPC_PH_PREP);
       // ---- D. K <- H^-1 (H is SPD: 2aI + 2B'SB, a > 0) ----
-      if (S::REG) build_invert_regtile2<S>(C, rowinfo, n, tid, cbuf, K, red);
+      if (S::REG) build_invert_regtile2<S>(C, rowinfo, n, tid, cbuf, K, red, pc);
       else build_invert_smem<NT>(C, rowinfo, n, tid, kn, K);
       __syncthreads();
       // x = -H^-1 g, slacks of every candidate row
@@ -604,139 +635,24 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
       }
       __syncthreads();
       flops_acc += 2.0 * (double)n * n * n * 0.5 + 12.0 * (double)n * n + 2.0 * (double)n * n;
+      pc.tick(CMPC_PH_STORE);
 
-      // ---- E. Goldfarb-Idnani dual active set on K ----
-      int q = 0;
-      bool done = false;
-      while (!done) {
-        double best = 1e300; int bidx = -1;
-        for (int c = tid; c < m; c += NT)
-          if (!isact[c]) { double sv = s[c]; if (sv < best) { best = sv; bidx = c; } }
-        block_argmin<NT>(best, bidx, red, tid);
-        if (!(best < -P.tol_violation)) break;
-        const int p = bidx;
-        int pia, piz; double pva, pvz;
-        cons_of(p, mu_inv, pia, pva, piz, pvz);
-        double up = 0.0;
-        while (true) {
-          iters++;
-          if (iters > P.max_iter) { status = CMPC_ST_MAXITER; done = true; break; }
-          for (int i = tid; i < n; i += NT) kn[i] = pva * K[pia * n + i] + pvz * K[piz * n + i];
-          __syncthreads();
-          const double scale = pva * kn[pia] + pvz * kn[piz];
-          for (int k = tid; k < q; k += NT) {
-            int ia, iz; double va, vz;
-            cons_of(act[k], mu_inv, ia, va, iz, vz);
-            dvec[k] = va * kn[ia] + vz * kn[iz];
-          }
-          __syncthreads();
-          double dr = 0.0, ratio = 1e300; int kd = -1;
-          for (int k = tid; k < q; k += NT) {
-            double acc = 0.0;
-            for (int l = 0; l < q; l++) acc = fma(psym(Pp, k, l), dvec[l], acc);
-            rvec[k] = acc;
-            rc[act[k]] = acc;
-            dr = fma(dvec[k], acc, dr);
-            if (acc > 0.0) { double t = u[k] / acc; if (t < ratio) { ratio = t; kd = k; } }
-          }
-          dr = block_sum<NT>(dr, red, tid);
-          block_argmin<NT>(ratio, kd, red, tid);
-          __syncthreads();
-          const double rho2 = scale - dr;
-          const bool dependent = !(rho2 > 1e-12 * scale);
-          if (!dependent) {
-            // v = N r gathered per variable from the (at most five) rows of its foot-step
-            for (int i = tid; i < n; i += NT) {
-              int j = i / 3, comp = i - 3 * j;
-              const double* rj = rc + 5 * j;
-              double val;
-              if (comp == 0) val = mu_inv * (rj[0] - rj[1]);
-              else if (comp == 1) val = mu_inv * (rj[2] - rj[3]);
-              else val = rj[0] + rj[1] + rj[2] + rj[3] - rj[4];
-              vv[i] = val;
-            }
-            __syncthreads();
-            for (int i = tid; i < n; i += NT) {
-              double acc = kn[i];
-              for (int l = 0; l < n; l++) {
-                double vl = vv[l];
-                if (vl != 0.0) acc = fma(-K[l * n + i], vl, acc);
-              }
-              z[i] = acc;
-            }
-            __syncthreads();
-          }
-          const double rho2_inv = dependent ? 0.0 : fast_rcp(rho2);
-          const double t2 = dependent ? 1e300 : -s[p] * rho2_inv;
-          const double t1 = ratio;
-          const double t = fmin(t1, t2);
-          if (t >= 1e299) { status = CMPC_ST_INFEASIBLE; done = true; break; }
-          const bool full = (t2 <= t1);
-          __syncthreads();  // everyone has read s[p], u[], rvec[] decisions
-          if (!dependent) {
-            for (int i = tid; i < n; i += NT) x[i] = fma(t, z[i], x[i]);
-            for (int c = tid; c < m; c += NT) {
-              int ia, iz; double va, vz;
-              cons_of(c, mu_inv, ia, va, iz, vz);
-              s[c] = fma(t, va * z[ia] + vz * z[iz], s[c]);
-            }
-          }
-          for (int k = tid; k < q; k += NT) {
-            u[k] = fma(-t, rvec[k], u[k]);
-            rc[act[k]] = 0.0;
-          }
-          up += t;
-          flops_acc += 2.0 * (4.0 * n + 4.0 * q + (double)q * q + 3.0 * n * (2.0 * q < n ? 2.0 * q : (double)n) + 4.0 * m + n);
-          if (full) {
-            if (q >= P.qcap) { status = CMPC_ST_WSOVERFLOW; done = true; break; }
-            const double inv = rho2_inv;
-            for (int k = tid; k < q; k += NT) {
-              double rk = rvec[k] * inv;
-              for (int l = 0; l <= k; l++) Pp[k * (k + 1) / 2 + l] = fma(rk, rvec[l], Pp[k * (k + 1) / 2 + l]);
-              Pp[q * (q + 1) / 2 + k] = -rk;
-            }
-            if (tid == 0) {
-              Pp[q * (q + 1) / 2 + q] = inv;
-              act[q] = (short)p;
-              u[q] = up;
-              isact[p] = 1;
-            }
-            q++;
-            flops_acc += 2.0 * (double)q * q;
-            __syncthreads();
-            break;
-          }
-          // partial step: constraint kd leaves the working set, p stays the candidate
-          for (int k = tid; k < q; k += NT) col[k] = psym(Pp, k, kd);
-          __syncthreads();
-          {
-            const double inv = 1.0 / col[kd];
-            for (int k = tid; k < q; k += NT) {
-              if (k == kd) continue;
-              double ck = col[k] * inv;
-              for (int l = 0; l <= k; l++)
-                if (l != kd) Pp[k * (k + 1) / 2 + l] = fma(-ck, col[l], Pp[k * (k + 1) / 2 + l]);
-            }
-          }
-          __syncthreads();
-          const int last = q - 1;
-          if (kd != last) {
-            for (int l = tid; l < last; l += NT)
-              if (l != kd) psym(Pp, kd, l) = psym(Pp, last, l);
-            if (tid == 0) {
-              Pp[kd * (kd + 1) / 2 + kd] = Pp[last * (last + 1) / 2 + last];
-              isact[act[kd]] = 0;
-              act[kd] = act[last];
-              u[kd] = u[last];
-            }
-          } else if (tid == 0) {
-            isact[act[kd]] = 0;
-          }
-          q--;
-          flops_acc += 2.0 * (double)q * q;
-          __syncthreads();
-        }
+      // ---- E. Goldfarb-Idnani dual active set on K (cmpc_qp.cuh), run by the first GT threads ----
+#ifdef CMPC_QP_FULL
+      constexpr int GT = NT;
+#else
+      constexpr int GT = (S::NPAD < NT) ? S::NPAD : NT;
+#endif
+      if (tid < GT) {
+        QpState qs = qp_dual_active_set<GT>(tid, n, m, mu_inv, P.tol_violation, P.max_iter, P.qcap, K, x, s, rc, isact,
+                                            act, u, dvec, rvec, col, Pp, kn, z, vv, red, flops_acc);
+        if (tid == 0) { redi[1] = qs.status; redi[2] = qs.iters; redi[3] = qs.q; }
       }
+      __syncthreads();
+      pc.tick(CMPC_PH_QP);
+      status = redi[1];
+      iters = redi[2];
+      const int q = redi[3];
       // ---- objective 0.5 x'Hx + g'x = 0.5 g'x + 0.5 lambda'b at a KKT point ----
       double part = 0.0;
       for (int i = tid; i < n; i += NT) part = fma(0.5 * g[i], x[i], part);
@@ -786,6 +702,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
       }
     }
     __syncthreads();  // record buffer and work arrays are reused by the next instance
+    pc.tick(CMPC_PH_OUT);
   }
   if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops, (unsigned long long)flops_acc);
 }
@@ -817,6 +734,7 @@ int npad_of(int shape) {
     case CMPC_SHAPE_64: return Shape64::NPAD;
     case CMPC_SHAPE_64W: return Shape64w::NPAD;
     case CMPC_SHAPE_128: return Shape128::NPAD;
+    case CMPC_SHAPE_GMEM: return ShapeGmem::NPAD;
     default: return ShapeMem::NPAD;
   }
 }
@@ -841,6 +759,7 @@ int cmpc_shape_threads(int shape) {
     case CMPC_SHAPE_64: return adapt ? FN<Shape64, true>(__VA_ARGS__) : FN<Shape64, false>(__VA_ARGS__);     \
     case CMPC_SHAPE_64W: return adapt ? FN<Shape64w, true>(__VA_ARGS__) : FN<Shape64w, false>(__VA_ARGS__);  \
     case CMPC_SHAPE_128: return adapt ? FN<Shape128, true>(__VA_ARGS__) : FN<Shape128, false>(__VA_ARGS__);  \
+    case CMPC_SHAPE_GMEM: return adapt ? FN<ShapeGmem, true>(__VA_ARGS__) : FN<ShapeGmem, false>(__VA_ARGS__); \
     default: return adapt ? FN<ShapeMem, true>(__VA_ARGS__) : FN<ShapeMem, false>(__VA_ARGS__);              \
   }
 

@@ -37,7 +37,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 
 template <class S>
 __device__ __forceinline__ void build_invert_regtile2(const HessCtx& C, const int* rowinfo, int n, int tid, double* cbuf,
-                                                      double* K, double* red) {
+                                                      double* K, double* red, PhaseClock& pc) {
   constexpr int TY = S::TY, TX = S::TX, TM = S::TM, TN = S::TN, NPAD = S::NPAD, NT = S::NT;
   const int ty = tid / TX, tx = tid - ty * TX;
   // H into shared memory, one 3x3 foot-step pair block (j1 >= j2) per thread and mirrored: the horizon
@@ -85,6 +85,7 @@ __device__ __forceinline__ void build_invert_regtile2(const HessCtx& C, const in
     dmax = -neg;
   }
   if (NT <= 32) __syncthreads();
+  pc.tick(CMPC_PH_HESS);
   int e2;
   frexp(dmax, &e2);                          // dmax = m * 2^e2, m in [0.5, 1)
   const double scale = ldexp(1.0, -e2);      // exact; scaled diagonal < 1
@@ -102,6 +103,7 @@ __device__ __forceinline__ void build_invert_regtile2(const HessCtx& C, const in
   double* dg = cbuf + 2 * (NPAD + 2);  // two diagonal buffers of NPAD
   for (int i = tid; i < NPAD; i += NT) dg[i] = (i < n) ? K[i * n + i] * scale : 0.5;
   __syncthreads();
+  pc.tick(CMPC_PH_LOAD);
   double dinv = fast_rcp(dg[0]);
   int par = 0;
 #pragma unroll 1
@@ -146,6 +148,7 @@ __device__ __forceinline__ void build_invert_regtile2(const HessCtx& C, const in
     dinv = dinv_next;
     par ^= 1;
   }
+  pc.tick(CMPC_PH_SWEEP);
   // -swept = (scaled H)^-1; undo the scaling and the +2 carried by every diagonal element
 #pragma unroll
   for (int a = 0; a < TM; a++)
