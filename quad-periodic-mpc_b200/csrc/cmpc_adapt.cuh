@@ -15,9 +15,13 @@
 
 namespace {
 
-template <int NT>
-__device__ __forceinline__ void estimate_disturbance(const CmpcParams& P, int inst, int tid, double* work, double* red,
-                                                     double* est_out /* shared, 4 doubles */) {
+// NT threads cooperate on one instance: a whole CTA (WARP = false, barriers are __syncthreads) or one warp of
+// a CTA whose warps work on different instances (WARP = true, NT = 32, barriers are __syncwarp).
+template <int NT, bool WARP>
+__device__ __forceinline__ void estimate_disturbance_impl(const CmpcParams& P, int inst, int tid, double* work,
+                                                          double* red, double* est_out /* shared, 4 doubles */) {
+  static_assert(!WARP || NT == 32, "the warp variant is warp-synchronous");
+  auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
   constexpr int N = CMPC_ADAPT_WINDOW;
   double* y = work;            // band-passed window
   double* tre = work + N;      // first-pass DFT / staged raw window
@@ -25,7 +29,7 @@ __device__ __forceinline__ void estimate_disturbance(const CmpcParams& P, int in
   const float* wd = P.win_d + (size_t)inst * N;
   const float* wt = P.win_t + (size_t)inst * N;
   for (int i = tid; i < N; i += NT) tre[i] = (double)wd[i];
-  __syncthreads();
+  sync();
   // band-pass: difference of the two blurs, edge samples repeated (SolverMPC.cpp:425-434)
   const float* g1 = P.gk;
   const float* g2 = P.gk + 2 * CMPC_GK_R1 + 1;
@@ -41,7 +45,7 @@ __device__ __forceinline__ void estimate_disturbance(const CmpcParams& P, int in
     }
     y[i] = a1 - a2;
   }
-  __syncthreads();
+  sync();
   // mean and (population) standard deviation
   double part = 0.0;
   for (int i = tid; i < N; i += NT) part += y[i];
@@ -49,7 +53,7 @@ __device__ __forceinline__ void estimate_disturbance(const CmpcParams& P, int in
   part = 0.0;
   for (int i = tid; i < N; i += NT) { double dlt = y[i] - mean; part = fma(dlt, dlt, part); }
   const double var = block_sum<NT>(part, red, tid) / (double)N;
-  __syncthreads();
+  sync();
   // pass 1: T[n2][k1] = W400^(n2 k1) * sum_n1 y[20 n1 + n2] W20^(n1 k1)
   for (int idx = tid; idx < N; idx += NT) {
     const int n2 = idx / 20, k1 = idx - 20 * n2;
@@ -67,7 +71,7 @@ __device__ __forceinline__ void estimate_disturbance(const CmpcParams& P, int in
     tre[idx] = re * c - im * s;
     tim[idx] = re * s + im * c;
   }
-  __syncthreads();
+  sync();
   // pass 2: X[k1 + 20 k2] = sum_n2 T[n2][k1] W20^(n2 k2); only bins 1..200 are searched
   double best = 1e300;
   int bidx = 1 << 30;
@@ -94,7 +98,18 @@ __device__ __forceinline__ void estimate_disturbance(const CmpcParams& P, int in
     est_out[2] = fabs((double)bidx / ((double)N * dts));
     est_out[3] = 0.0;
   }
-  __syncthreads();
+  sync();
+}
+
+template <int NT>
+__device__ __forceinline__ void estimate_disturbance(const CmpcParams& P, int inst, int tid, double* work, double* red,
+                                                     double* est_out) {
+  estimate_disturbance_impl<NT, false>(P, inst, tid, work, red, est_out);
+}
+
+__device__ __forceinline__ void estimate_disturbance_warp(const CmpcParams& P, int inst, int lane, double* work,
+                                                          double* est_out) {
+  estimate_disturbance_impl<32, true>(P, inst, lane, work, nullptr, est_out);
 }
 
 }  // namespace

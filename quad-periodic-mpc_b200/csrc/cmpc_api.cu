@@ -120,6 +120,11 @@ struct cmpc_batch {
   unsigned long long* d_phase = nullptr;  // CMPC_PH_COUNT phase clocks, allocated by cmpc_batch_enable_phase_clocks
   double* d_gws = nullptr;  // global workspace of the large-problem tier, grown on demand
   size_t gws_bytes = 0;
+  // two-kernel pipeline: per-stream workspace slots (K, g, x0 per instance of a chunk) and work counters
+  double* d_qws[2] = {nullptr, nullptr};
+  size_t qws_bytes[2] = {0, 0};
+  int* d_sched[2] = {nullptr, nullptr};
+  int sched_ints[2] = {0, 0};
   // adaptive stage
   double* d_twiddle = nullptr;
   float* d_gk = nullptr;
@@ -191,6 +196,121 @@ int check_inputs(const cmpc_batch* b, int count, const cmpc_inputs* in, const ch
   return CMPC_OK;
 }
 
+// Two-kernel pipeline (cmpc_pipeline.cu) over the instances P describes, in chunks whose workspace stays
+// L2-sized: condensation + K = H^-1 (one CTA per instance), then the dual active set (one warp per
+// instance) with a small working-set capacity, then the few instances that outgrew it at full capacity.
+int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
+  cudaStream_t st = b->stream[si];
+  const bool adapt = P.adapt_mode >= 0;
+  const int nmax = P.nmax;
+  int cshape = nmax <= 64 ? CMPC_CSHAPE_MMA64 : (nmax <= 96 ? CMPC_CSHAPE_96 : CMPC_CSHAPE_128);
+  if (const char* e = std::getenv("CMPC_CSHAPE")) {  // experiments: force a shape that still fits
+    const int sh = std::atoi(e);
+    if ((sh == CMPC_CSHAPE_64 && nmax <= 64) || (sh == CMPC_CSHAPE_96 && nmax <= 96) || sh == CMPC_CSHAPE_128) cshape = sh;
+  }
+  const size_t slot = cmpc_qws_slot_doubles(nmax);
+  size_t budget = 160;
+  if (const char* e = std::getenv("CMPC_WS_MB")) budget = (size_t)std::max(1, std::atoi(e));
+  budget <<= 20;
+  int chunk = (int)std::min<size_t>((size_t)count, std::max<size_t>(1, budget / (slot * sizeof(double))));
+  const int nchunks = (count + chunk - 1) / chunk;
+  const size_t need = (size_t)chunk * slot * sizeof(double);
+  if (need > b->qws_bytes[si] || 3 * nchunks > b->sched_ints[si]) {
+    for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+    if (need > b->qws_bytes[si]) {
+      if (b->d_qws[si]) CK(cudaFree(b->d_qws[si]));
+      b->d_qws[si] = nullptr;
+      b->qws_bytes[si] = 0;
+      CK(cudaMalloc(&b->d_qws[si], need));
+      b->qws_bytes[si] = need;
+    }
+    if (3 * nchunks > b->sched_ints[si]) {
+      if (b->d_sched[si]) CK(cudaFree(b->d_sched[si]));
+      b->d_sched[si] = nullptr;
+      b->sched_ints[si] = 0;
+      const int ints = std::max(3 * nchunks, 768);
+      CK(cudaMalloc(&b->d_sched[si], sizeof(int) * ints));
+      b->sched_ints[si] = ints;
+    }
+  }
+  CK(cudaMemsetAsync(b->d_sched[si], 0, sizeof(int) * 3 * nchunks, st));
+  // kernel 1
+  const size_t smem1 = cmpc_condense_smem_bytes(P.horizon, nmax, cshape, adapt);
+  const int per_sm1 = cmpc_condense_max_ctas_per_sm(cshape, smem1, adapt);
+  if (per_sm1 < 1) {
+    g_err = "cmpc_batch_solve: condensation kernel not launchable on this device (no sm_100a image?)";
+    return CMPC_E_NODEVICE;
+  }
+  // kernel 2, two working-set capacity tiers
+  int qcap1 = 16;
+  if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
+  if (qcap1 < 1 || qcap1 > nmax) qcap1 = nmax;
+  int wpc1 = 4;
+  if (const char* e = std::getenv("CMPC_WPC")) wpc1 = std::atoi(e);
+  if (wpc1 != 1 && wpc1 != 2 && wpc1 != 4 && wpc1 != 8) wpc1 = 4;
+  const size_t smax = 227 * 1024;
+  while (wpc1 > 1 && cmpc_dual_smem_bytes_per_warp(nmax, qcap1) * wpc1 > smax) wpc1 >>= 1;
+  const int per_sm2 = cmpc_dual_max_ctas_per_sm(wpc1, cmpc_dual_smem_bytes_per_warp(nmax, qcap1) * wpc1);
+  int wpc2 = 4;
+  while (wpc2 > 1 && cmpc_dual_smem_bytes_per_warp(nmax, nmax) * wpc2 > 100 * 1024) wpc2 >>= 1;
+  const int per_sm3 = cmpc_dual_max_ctas_per_sm(wpc2, cmpc_dual_smem_bytes_per_warp(nmax, nmax) * wpc2);
+  if (per_sm2 < 1 || per_sm3 < 1) {
+    g_err = "cmpc_batch_solve: active-set kernel not launchable on this device (no sm_100a image?)";
+    return CMPC_E_NODEVICE;
+  }
+  const CmpcParams base = P;
+  for (int c = 0; c < nchunks; c++) {
+    const int off = c * chunk, cnt = std::min(chunk, count - off);
+    CmpcParams Q = base;
+    Q.count = cnt;
+    Q.records = base.records + (size_t)off * base.rec_stride;
+    Q.forces = base.forces + (size_t)off * 12 * base.horizon;
+    Q.objective = base.objective + off;
+    Q.status = base.status + off;
+    Q.iterations = base.iterations + off;
+    Q.active = base.active + (size_t)off * 20 * base.horizon;
+    if (adapt) {
+      Q.win_t = base.win_t + (size_t)off * CMPC_ADAPT_WINDOW;
+      Q.win_d = base.win_d + (size_t)off * CMPC_ADAPT_WINDOW;
+      Q.sim_time = base.sim_time + off;
+      Q.est = base.est + (size_t)off * 4;
+      Q.f_est = base.f_est + (size_t)off * 6;
+    }
+    Q.qws = b->d_qws[si];
+    Q.qws_stride = slot;
+    Q.worklist = nullptr;
+    Q.count_ptr = nullptr;
+    Q.sched = b->d_sched[si] + 3 * c;
+    const int ipc = cmpc_condense_instances_per_cta(cshape);
+    int rc = cmpc_launch_condense(Q, cshape, std::min((cnt + ipc - 1) / ipc, b->sm_count * per_sm1), st);
+    if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_condense_kernel launch");
+    b->launches++;
+    Q.sched = b->d_sched[si] + 3 * c + 1;
+    Q.qcap = qcap1;
+    if (qcap1 < nmax) {
+      Q.overflow_list = b->d_overflow[si];
+      Q.overflow_count = b->d_overflow[si] + b->capacity;
+      CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
+    } else {
+      Q.overflow_list = nullptr;
+    }
+    rc = cmpc_launch_dual(Q, wpc1, std::min((cnt + wpc1 - 1) / wpc1, b->sm_count * per_sm2), st);
+    if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel launch");
+    b->launches++;
+    if (qcap1 < nmax) {
+      Q.sched = b->d_sched[si] + 3 * c + 2;
+      Q.qcap = nmax;
+      Q.worklist = b->d_overflow[si];
+      Q.count_ptr = b->d_overflow[si] + b->capacity;
+      Q.overflow_list = nullptr;
+      rc = cmpc_launch_dual(Q, wpc2, std::min((cnt + wpc2 - 1) / wpc2, b->sm_count * per_sm3), st);
+      if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel (full capacity) launch");
+      b->launches++;
+    }
+  }
+  return CMPC_OK;
+}
+
 // enqueue the solve of the uploaded instances [first, first+count) on stream si
 int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
   if (count <= 0) return CMPC_OK;
@@ -231,6 +351,13 @@ int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
     P.sim_time = b->d_simtime + first;
     P.est = b->d_est + (size_t)first * 4;
     P.f_est = b->d_fest + (size_t)first * 6;
+  }
+  // reduced problems of up to 128 variables take the two-kernel pipeline; CMPC_PATH=fused forces the
+  // single-kernel path below (kept for larger problems and for A/B measurements)
+  {
+    const char* e = std::getenv("CMPC_PATH");
+    const bool fused = e && std::strcmp(e, "fused") == 0;
+    if (P.nmax <= CMPC_PIPELINE_NMAX && !fused) return launch_pipeline(b, P, count, si);
   }
   // kernel shape by reduced problem size; CMPC_SHAPE overrides (0..3) for experiments
   int shape = P.nmax <= 64 ? CMPC_SHAPE_64W : (P.nmax <= 128 ? CMPC_SHAPE_128 : CMPC_SHAPE_MEM);
@@ -363,6 +490,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
   cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops); cudaFree(b->d_phase);
   cudaFree(b->d_overflow[0]); cudaFree(b->d_overflow[1]); cudaFree(b->d_gws);
+  for (int i = 0; i < 2; i++) { cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); }
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFreeHost(b->h_forces); cudaFreeHost(b->h_obj); cudaFreeHost(b->h_status); cudaFreeHost(b->h_iters);

@@ -85,6 +85,11 @@ struct CmpcParams {
   // global-memory workspace tier (reduced problems too large for shared memory): K and P per CTA
   double* gws;                // NULL unless shape == CMPC_SHAPE_GMEM
   size_t gws_stride;          // doubles per CTA
+  // two-kernel pipeline (cmpc_pipeline.cu): per-instance workspace slots written by the condensation kernel
+  // and read by the dual active-set kernel, and the device-side work counter of the launch
+  double* qws;                // [count][qws_stride]: K (nmax x nmax, row stride n), g, x0, header
+  size_t qws_stride;          // doubles per slot, >= cmpc_qws_slot_doubles(nmax)
+  int* sched;                 // work counter of THIS launch (zeroed by the host)
   // optional phase clocks (profiling aid): CMPC_PH_COUNT counters of SM cycles summed over CTAs, thread 0 only
   unsigned long long* phase_cycles;
 };
@@ -106,6 +111,27 @@ struct CmpcParams {
 #define CMPC_SHAPE_128 2   /* n <= 128, 256 threads, 8x8 register tiles */
 #define CMPC_SHAPE_MEM 3   /* matrix in shared memory, 128 threads */
 #define CMPC_SHAPE_GMEM 4  /* matrix and working-set inverse in an L2-resident global workspace, 128 threads */
+
+// two-kernel pipeline shapes (cmpc_condense.cuh)
+#define CMPC_CSHAPE_64 0   /* n <= 64, 128 threads */
+#define CMPC_CSHAPE_96 1   /* n <= 96, 256 threads */
+#define CMPC_CSHAPE_128 2  /* n <= 128, 256 threads */
+#define CMPC_CSHAPE_MMA64 3 /* n <= 64, one warp per instance, DMMA rank-8 updates, 4 instances per CTA */
+#define CMPC_PIPELINE_NMAX 128
+
+static inline size_t cmpc_qws_slot_doubles(int nmax) {
+  // K, g, x0, header {int nc, int status, uchar fs[CMPC_MAX_FS], uchar gait[CMPC_MAX_FS]}
+  size_t d = (size_t)nmax * nmax + 2 * (size_t)nmax + (8 + 2 * CMPC_MAX_FS + 7) / 8;
+  return (d + 1) & ~(size_t)1;
+}
+
+size_t cmpc_condense_smem_bytes(int horizon, int nmax, int cshape, bool adapt);
+int cmpc_condense_max_ctas_per_sm(int cshape, size_t smem, bool adapt);
+int cmpc_launch_condense(const CmpcParams& P, int cshape, int grid, void* stream);
+int cmpc_condense_instances_per_cta(int cshape);
+size_t cmpc_dual_smem_bytes_per_warp(int nmax, int qcap);
+int cmpc_dual_max_ctas_per_sm(int warps_per_cta, size_t smem);
+int cmpc_launch_dual(const CmpcParams& P, int warps_per_cta, int grid, void* stream);
 
 size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape, bool adapt);
 int cmpc_shape_threads(int shape);

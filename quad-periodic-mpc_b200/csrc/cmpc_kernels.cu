@@ -92,216 +92,11 @@ __host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_s
   return c;
 }
 
-// ---------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+}  // namespace
 
-__device__ __forceinline__ void mbar_init(void* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#include "cmpc_common.cuh"
 
-// ---------------------------------------------------------------------------
-// block reductions
-// ---------------------------------------------------------------------------
-template <int NT>
-__device__ __forceinline__ void block_argmin(double& val, int& idx, double* red, int tid) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_xor_sync(0xffffffffu, val, o);
-    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
-  }
-  if (NT > 32) {
-    int* redi = reinterpret_cast<int*>(red + 8);
-    __syncthreads();
-    if ((tid & 31) == 0) { red[tid >> 5] = val; redi[tid >> 5] = idx; }
-    __syncthreads();
-    val = red[0]; idx = redi[0];
-#pragma unroll
-    for (int w = 1; w < NT / 32; w++) {
-      double ov = red[w]; int oi = redi[w];
-      if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
-    }
-  }
-}
-
-template <int NT>
-__device__ __forceinline__ double block_sum(double val, double* red, int tid) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-  if (NT > 32) {
-    __syncthreads();
-    if ((tid & 31) == 0) red[16 + (tid >> 5)] = val;
-    __syncthreads();
-    val = red[16];
-#pragma unroll
-    for (int w = 1; w < NT / 32; w++) val += red[16 + w];
-  }
-  return val;
-}
-
-// constraint c = 5j+t of the reduced problem as  s(x) = va*x[ia] + vz*x[iz] - b >= 0
-//   t=0:  x/mu + z >= 0   t=1: -x/mu + z >= 0   t=2:  y/mu + z >= 0   t=3: -y/mu + z >= 0
-//   t=4:  -z + ub >= 0    (fmat rows, SolverMPC.cpp:660; the row-4 lower side z >= 0 is implied by t=0,1)
-__device__ __forceinline__ void cons_of(int c, double mu_inv, int& ia, double& va, int& iz, double& vz) {
-  int j = c / 5, t = c - 5 * j;
-  iz = 3 * j + 2;
-  if (t == 4) { ia = iz; va = 0.0; vz = -1.0; }
-  else { ia = 3 * j + (t >> 1); va = (t & 1) ? -mu_inv : mu_inv; vz = 1.0; }
-}
-
-__device__ __forceinline__ double& psym(double* Pp, int k, int l) {
-  return (k >= l) ? Pp[k * (k + 1) / 2 + l] : Pp[l * (l + 1) / 2 + k];
-}
-
-// phase clocks (profiling aid, off unless CmpcParams::phase_cycles is set): thread 0 of a CTA charges the
-// cycles since its previous tick to a phase.  State lives in shared memory so the feature costs no registers.
-struct PhaseClock {
-  unsigned long long* out;  // global counters or nullptr
-  long long* last;          // shared
-  __device__ __forceinline__ void init(unsigned long long* o, long long* smem_slot, int tid) {
-    out = (tid == 0) ? o : nullptr;
-    last = smem_slot;
-    if (out) *last = clock64();
-  }
-  __device__ __forceinline__ void tick(int phase) const {
-    if (out) {
-      const long long now = clock64();
-      atomicAdd(out + phase, (unsigned long long)(now - *last));
-      *last = now;
-    }
-  }
-};
-
-// per-instance constants the Hessian entries are assembled from
-struct HessCtx {
-  const double* sig;   // global, 5 tables of h*h
-  const double* sPT;   // shared, [4][4][3][3]
-  const double* sPO;
-  int h;
-  const double* wp;    // shared, position weights [3] then velocity weights [3]
-  const int* fs;       // shared, reduced foot-step -> global foot-step
-  double xd, m2, alpha2;
-};
-
-// H[(step a, foot fi, comp c1), (step b, foot fj, comp c2)], DESIGN.md §3
-__device__ __forceinline__ double hess_entry(const HessCtx& C, int ri, int rj, bool diag) {
-  const int a = ri & 0xff, fi = (ri >> 8) & 3, c1 = ri >> 16;
-  const int b = rj & 0xff, fj = (rj >> 8) & 3, c2 = rj >> 16;
-  const int hh = C.h * C.h, ab = a * C.h + b, ba = b * C.h + a;
-  const double s11 = __ldg(C.sig + CMPC_SIG_11 * hh + ab), s22 = __ldg(C.sig + CMPC_SIG_22 * hh + ab);
-  const int pidx = (fi * 4 + fj) * 9 + c1 * 3 + c2;
-  double val = s22 * C.sPT[pidx] + s11 * C.sPO[pidx];
-  double pv = 0.0;
-  if (c1 == c2) pv = s22 * C.wp[c1] + s11 * C.wp[3 + c1];
-  if (C.xd != 0.0) {
-    if (c1 == 2 && c2 == 0) pv += C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_23 * hh + ab) + C.wp[5] * __ldg(C.sig + CMPC_SIG_12 * hh + ab));
-    if (c1 == 0 && c2 == 2) pv += C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_23 * hh + ba) + C.wp[5] * __ldg(C.sig + CMPC_SIG_12 * hh + ba));
-    if (c1 == 0 && c2 == 0) pv += C.xd * C.xd * (C.wp[2] * __ldg(C.sig + CMPC_SIG_33 * hh + ab) + C.wp[5] * s22);
-  }
-  val = 2.0 * (val + pv * C.m2);
-  if (diag) val += C.alpha2;
-  return val;
-}
-
-// D (register tiers): build H into the thread's tile, sweep every pivot k < n, store -swept = H^-1.
-// Row i = ty + TY*a (a < TM), column j = tx + TX*b (b < TN).  Pivot k lives in row block a = k / TY of
-// threads ty = k % TY and in column block b = k / TX of threads tx = k % TX; the pivot loop is unrolled
-// over a so every register index is a compile-time constant.
-template <class S>
-__device__ __forceinline__ void build_invert_regtile(const HessCtx& C, const int* rowinfo, int n, int tid, double* cbuf,
-                                                     double* K) {
-  constexpr int TY = S::TY, TX = S::TX, TM = S::TM, TN = S::TN, NPAD = S::NPAD;
-  const int ty = tid / TX, tx = tid - ty * TX;
-  double A[TM][TN];
-  {
-    int ri[TM], rj[TN];
-#pragma unroll
-    for (int a = 0; a < TM; a++) ri[a] = rowinfo[ty + TY * a];
-#pragma unroll
-    for (int b = 0; b < TN; b++) rj[b] = rowinfo[tx + TX * b];
-#pragma unroll
-    for (int a = 0; a < TM; a++)
-#pragma unroll
-      for (int b = 0; b < TN; b++) {
-        const int i = ty + TY * a, j = tx + TX * b;
-        double v = (i == j) ? 1.0 : 0.0;  // identity padding beyond n
-        if (ri[a] >= 0 && rj[b] >= 0) v = hess_entry(C, ri[a], rj[b], i == j);
-        A[a][b] = v;
-      }
-  }
-  int par = 0;
-#pragma unroll
-  for (int a = 0; a < TM; a++) {
-    const int b = (a * TY) / TX;          // column block of the pivots of this row block
-    const int txo = (a * TY) % TX;        // column-owner tx = kk + txo
-    if (TY * a < n) {
-      for (int kk = 0; kk < TY; kk++) {
-        const int k = kk + TY * a;
-        if (k >= n) break;
-        double* cb = cbuf + par * (NPAD + 2);
-        if (tx == kk + txo) {
-#pragma unroll
-          for (int aa = 0; aa < TM; aa++) cb[ty + TY * aa] = A[aa][b];
-          if (ty == kk) cb[NPAD] = 1.0 / A[a][b];
-        }
-        __syncthreads();
-        const double dinv = cb[NPAD];
-        double ci[TM], cjd[TN];
-#pragma unroll
-        for (int aa = 0; aa < TM; aa++) ci[aa] = cb[ty + TY * aa];
-#pragma unroll
-        for (int bb = 0; bb < TN; bb++) cjd[bb] = cb[tx + TX * bb] * dinv;
-#pragma unroll
-        for (int aa = 0; aa < TM; aa++)
-#pragma unroll
-          for (int bb = 0; bb < TN; bb++) A[aa][bb] = fma(-ci[aa], cjd[bb], A[aa][bb]);
-        if (ty == kk) {
-#pragma unroll
-          for (int bb = 0; bb < TN; bb++) A[a][bb] = cjd[bb];
-        }
-        if (tx == kk + txo) {
-#pragma unroll
-          for (int aa = 0; aa < TM; aa++) A[aa][b] = ci[aa] * dinv;
-          if (ty == kk) A[a][b] = -dinv;
-        }
-        par ^= 1;
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < TM; a++)
-#pragma unroll
-    for (int b = 0; b < TN; b++) {
-      const int i = ty + TY * a, j = tx + TX * b;
-      if (i < n && j < n) K[i * n + j] = -A[a][b];
-    }
-}
+namespace {
 
 // D (shared-memory tier): same sweep with the matrix in shared memory
 template <int NT>

@@ -1,0 +1,140 @@
+// Two-kernel pipeline of the batched convex-MPC engine for reduced problems of up to 128 variables
+// (every A1 gait at the reference's horizons except long all-feet-down stances):
+//
+//   cmpc_condense_kernel  one CTA per instance: condensation, H in register tiles, K = H^-1 by blocked
+//                         symmetric sweeps (FP64-pipe bound), x0 = -K g            cmpc_condense.cuh
+//   cmpc_dual_kernel      one warp per instance: Goldfarb-Idnani dual active set on K (latency bound,
+//                         many warps per SM), outputs                                cmpc_dual.cuh
+//
+// K travels between the two through a per-instance workspace slot that the host sizes to stay L2
+// resident.  Larger problems take the fused single-kernel path in cmpc_kernels.cu.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "cmpc_device.h"
+
+namespace {
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+}  // namespace
+
+#include "cmpc_common.cuh"
+#include "cmpc_adapt.cuh"
+#include "cmpc_condense.cuh"
+#include "cmpc_condense_mma.cuh"
+#include "cmpc_dual.cuh"
+
+namespace {
+
+template <class S, bool ADAPT>
+int launch_condense_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e =
+      cudaFuncSetAttribute(cmpc_condense_kernel<S, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cmpc_condense_kernel<S, ADAPT><<<grid, S::NT, smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+template <class S, bool ADAPT>
+int occ_condense_t(size_t smem) {
+  int nb = 0;
+  if (cudaFuncSetAttribute(cmpc_condense_kernel<S, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_condense_kernel<S, ADAPT>, S::NT, smem) != cudaSuccess)
+    return -1;
+  return nb;
+}
+template <bool ADAPT, int MINB>
+int launch_mma_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(cmpc_condense_mma_kernel<ADAPT, MINB>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cmpc_condense_mma_kernel<ADAPT, MINB><<<grid, 32 * MMA_WPC, smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+template <bool ADAPT, int MINB>
+int occ_mma_t(size_t smem) {
+  int nb = 0;
+  if (cudaFuncSetAttribute(cmpc_condense_mma_kernel<ADAPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem) != cudaSuccess)
+    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_condense_mma_kernel<ADAPT, MINB>, 32 * MMA_WPC, smem) !=
+      cudaSuccess)
+    return -1;
+  return nb;
+}
+int cnpad_of(int cshape) {
+  switch (cshape) {
+    case CMPC_CSHAPE_64: return CShape64::NPAD;
+    case CMPC_CSHAPE_96: return CShape96::NPAD;
+    default: return CShape128::NPAD;
+  }
+}
+
+template <int WPC>
+int launch_dual_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(cmpc_dual_kernel<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cmpc_dual_kernel<WPC><<<grid, 32 * WPC, smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+template <int WPC>
+int occ_dual_t(size_t smem) {
+  int nb = 0;
+  if (cudaFuncSetAttribute(cmpc_dual_kernel<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_dual_kernel<WPC>, 32 * WPC, smem) != cudaSuccess) return -1;
+  return nb;
+}
+
+}  // namespace
+
+#define CMPC_CDISPATCH(FN, ...)                                                                              \
+  switch (cshape) {                                                                                          \
+    case CMPC_CSHAPE_64: return adapt ? FN<CShape64, true>(__VA_ARGS__) : FN<CShape64, false>(__VA_ARGS__);   \
+    case CMPC_CSHAPE_96: return adapt ? FN<CShape96, true>(__VA_ARGS__) : FN<CShape96, false>(__VA_ARGS__);   \
+    default: return adapt ? FN<CShape128, true>(__VA_ARGS__) : FN<CShape128, false>(__VA_ARGS__);             \
+  }
+
+size_t cmpc_condense_smem_bytes(int horizon, int nmax, int cshape, bool adapt) {
+  if (cshape == CMPC_CSHAPE_MMA64) return (size_t)make_mcarve(horizon, cmpc_rec_stride(horizon), adapt).total;
+  return (size_t)make_ccarve(horizon, nmax, cmpc_rec_stride(horizon), cnpad_of(cshape), adapt).total;
+}
+
+int cmpc_condense_max_ctas_per_sm(int cshape, size_t smem, bool adapt) {
+  if (cshape == CMPC_CSHAPE_MMA64) return adapt ? occ_mma_t<true, 2>(smem) : occ_mma_t<false, 2>(smem);
+  CMPC_CDISPATCH(occ_condense_t, smem)
+}
+
+int cmpc_condense_instances_per_cta(int cshape) { return cshape == CMPC_CSHAPE_MMA64 ? MMA_WPC : 1; }
+
+int cmpc_launch_condense(const CmpcParams& P, int cshape, int grid, void* stream) {
+  const bool adapt = P.adapt_mode >= 0;
+  const size_t smem = cmpc_condense_smem_bytes(P.horizon, P.nmax, cshape, adapt);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cshape == CMPC_CSHAPE_MMA64)
+    return adapt ? launch_mma_t<true, 2>(P, grid, smem, st) : launch_mma_t<false, 2>(P, grid, smem, st);
+  CMPC_CDISPATCH(launch_condense_t, P, grid, smem, st)
+}
+
+size_t cmpc_dual_smem_bytes_per_warp(int nmax, int qcap) { return (size_t)make_dcarve(nmax, qcap).total; }
+
+int cmpc_dual_max_ctas_per_sm(int wpc, size_t smem) {
+  switch (wpc) {
+    case 1: return occ_dual_t<1>(smem);
+    case 2: return occ_dual_t<2>(smem);
+    case 4: return occ_dual_t<4>(smem);
+    default: return occ_dual_t<8>(smem);
+  }
+}
+
+int cmpc_launch_dual(const CmpcParams& P, int wpc, int grid, void* stream) {
+  const size_t smem = cmpc_dual_smem_bytes_per_warp(P.nmax, P.qcap) * (size_t)wpc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (wpc) {
+    case 1: return launch_dual_t<1>(P, grid, smem, st);
+    case 2: return launch_dual_t<2>(P, grid, smem, st);
+    case 4: return launch_dual_t<4>(P, grid, smem, st);
+    default: return launch_dual_t<8>(P, grid, smem, st);
+  }
+}

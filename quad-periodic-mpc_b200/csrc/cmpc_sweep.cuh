@@ -24,17 +24,6 @@
 
 namespace {
 
-__device__ __forceinline__ double fast_rcp(double d) {
-  // MUFU.RCP64H seed + two Newton steps: relative error ~1e-16 for the normal, positive pivots seen here
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
-
 template <class S>
 __device__ __forceinline__ void build_invert_regtile2(const HessCtx& C, const int* rowinfo, int n, int tid, double* cbuf,
                                                       double* K, double* red, PhaseClock& pc) {
