@@ -203,12 +203,13 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
   cudaStream_t st = b->stream[si];
   const bool adapt = P.adapt_mode >= 0;
   const int nmax = P.nmax;
-  int cshape = nmax <= 64 ? CMPC_CSHAPE_MMA64 : (nmax <= 96 ? CMPC_CSHAPE_96 : CMPC_CSHAPE_128);
+  int cshape = nmax < 64 ? CMPC_CSHAPE_MMA64 : (nmax <= 96 ? CMPC_CSHAPE_96 : CMPC_CSHAPE_128);
   if (const char* e = std::getenv("CMPC_CSHAPE")) {  // experiments: force a shape that still fits
     const int sh = std::atoi(e);
     if ((sh == CMPC_CSHAPE_64 && nmax <= 64) || (sh == CMPC_CSHAPE_96 && nmax <= 96) || sh == CMPC_CSHAPE_128) cshape = sh;
   }
-  const size_t slot = cmpc_qws_slot_doubles(nmax);
+  const int tiled = (cshape == CMPC_CSHAPE_MMA64) ? 1 : 0;
+  const size_t slot = cmpc_qws_slot_doubles(nmax, tiled);
   size_t budget = 160;
   if (const char* e = std::getenv("CMPC_WS_MB")) budget = (size_t)std::max(1, std::atoi(e));
   budget <<= 20;
@@ -278,6 +279,8 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     }
     Q.qws = b->d_qws[si];
     Q.qws_stride = slot;
+    Q.k_tiled = tiled;
+    Q.qws_goff = cmpc_qws_goff(nmax, tiled);
     Q.worklist = nullptr;
     Q.count_ptr = nullptr;
     Q.sched = b->d_sched[si] + 3 * c;

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
     const float* rec = reinterpret_cast<const float*>(recbuf[buf]);
     const unsigned char* gait = recbuf[buf] + 4 * (CMPC_REC_TRAJ + 12 * h);
     double* slot = P.qws + (size_t)inst * P.qws_stride;
-    int* hdr = reinterpret_cast<int*>(slot + (size_t)P.nmax * P.nmax + 2 * P.nmax);
+    int* hdr = reinterpret_cast<int*>(slot + P.qws_goff + 2 * P.nmax);
 
     // ---- 0. periodic-disturbance estimator (Adaptive MPC): xi for this instance, SolverMPC.cpp:688-798 ----
     if (ADAPT) {
@@ -509,8 +509,8 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
 #pragma unroll
         for (int t = 0; t < 8; t++) acc += pan[t * S::PS + j];
         const double gj = g[j];
-        slot[(size_t)P.nmax * P.nmax + j] = gj;
-        slot[(size_t)P.nmax * P.nmax + P.nmax + j] = scale * (acc - 2.0 * gj);
+        slot[P.qws_goff + j] = gj;
+        slot[P.qws_goff + P.nmax + j] = scale * (acc - 2.0 * gj);
       }
       flops_acc += 2.0 * (double)n * n * n * 0.5 + 12.0 * (double)n * n + 2.0 * (double)n * n;
     }

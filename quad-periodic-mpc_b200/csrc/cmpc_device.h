@@ -90,6 +90,8 @@ struct CmpcParams {
   double* qws;                // [count][qws_stride]: K (nmax x nmax, row stride n), g, x0, header
   size_t qws_stride;          // doubles per slot, >= cmpc_qws_slot_doubles(nmax)
   int* sched;                 // work counter of THIS launch (zeroed by the host)
+  int k_tiled;                // K is stored as 36 lower-triangular 8x8 tiles (cmpc_condense_mma.cuh), else row-major n x n
+  int qws_goff;               // offset (doubles) of g in a slot; x0 follows at +nmax, the header at +2 nmax
   // optional phase clocks (profiling aid): CMPC_PH_COUNT counters of SM cycles summed over CTAs, thread 0 only
   unsigned long long* phase_cycles;
 };
@@ -119,9 +121,14 @@ struct CmpcParams {
 #define CMPC_CSHAPE_MMA64 3 /* n <= 64, one warp per instance, DMMA rank-8 updates, 4 instances per CTA */
 #define CMPC_PIPELINE_NMAX 128
 
-static inline size_t cmpc_qws_slot_doubles(int nmax) {
+#define CMPC_KTILE_DOUBLES (36 * 64)
+static inline int cmpc_qws_goff(int nmax, int tiled) {
+  int k = tiled ? CMPC_KTILE_DOUBLES : nmax * nmax;
+  return (k + 1) & ~1;
+}
+static inline size_t cmpc_qws_slot_doubles(int nmax, int tiled) {
   // K, g, x0, header {int nc, int status, uchar fs[CMPC_MAX_FS], uchar gait[CMPC_MAX_FS]}
-  size_t d = (size_t)nmax * nmax + 2 * (size_t)nmax + (8 + 2 * CMPC_MAX_FS + 7) / 8;
+  size_t d = (size_t)cmpc_qws_goff(nmax, tiled) + 2 * (size_t)nmax + (8 + 2 * CMPC_MAX_FS + 7) / 8;
   return (d + 1) & ~(size_t)1;
 }
 

@@ -55,6 +55,14 @@ __device__ __forceinline__ void warp_argmin(double& val, int& idx) {
   }
 }
 
+// K[i][j] from a workspace slot: row-major n x n, or the lower-triangular 8x8 tiles of cmpc_condense_mma.cuh
+__device__ __forceinline__ double k_entry(const double* slot, int n, bool tiled, int i, int j) {
+  if (!tiled) return __ldg(slot + (size_t)i * n + j);
+  const int It = i >> 3, ri = i & 7, Jt = j >> 3, cj = j & 7;
+  const int off = (Jt <= It) ? (It * (It + 1) / 2 + Jt) * 64 + ri * 8 + cj : (Jt * (Jt + 1) / 2 + It) * 64 + cj * 8 + ri;
+  return __ldg(slot + off);
+}
+
 __device__ __forceinline__ double warp_sum(double val) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
@@ -97,7 +105,8 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
     if (slot_i >= count) break;
     const int inst = P.worklist ? P.worklist[slot_i] : slot_i;
     const double* slot = P.qws + (size_t)inst * P.qws_stride;
-    const double* gg = slot + (size_t)nmax * nmax;
+    const double* gg = slot + P.qws_goff;
+    const bool tiled = P.k_tiled != 0;
     const double* x0 = gg + nmax;
     const int* hdr = reinterpret_cast<const int*>(x0 + nmax);
     const int nc = hdr[0];
@@ -143,11 +152,8 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
         int pia, piz;
         double pva, pvz;
         cons_of(p, mu_inv, pia, pva, piz, pvz);
-        {
-          const double* ka = slot + (size_t)pia * n;
-          const double* kz = slot + (size_t)piz * n;
-          for (int i = lane; i < n; i += 32) kn[i] = pva * __ldg(ka + i) + pvz * __ldg(kz + i);
-        }
+        for (int i = lane; i < n; i += 32)
+          kn[i] = pva * k_entry(slot, n, tiled, pia, i) + pvz * k_entry(slot, n, tiled, piz, i);
         __syncwarp();
         const double scale = pva * kn[pia] + pvz * kn[piz];
         double up = 0.0;

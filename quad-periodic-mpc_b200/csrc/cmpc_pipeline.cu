@@ -49,7 +49,7 @@ int launch_mma_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(cmpc_condense_mma_kernel<ADAPT, MINB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  cmpc_condense_mma_kernel<ADAPT, MINB><<<grid, 32 * MMA_WPC, smem, st>>>(P);
+  cmpc_condense_mma_kernel<ADAPT, MINB><<<grid, MMA_NT, smem, st>>>(P);
   return (int)cudaGetLastError();
 }
 template <bool ADAPT, int MINB>
@@ -58,7 +58,7 @@ int occ_mma_t(size_t smem) {
   if (cudaFuncSetAttribute(cmpc_condense_mma_kernel<ADAPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)smem) != cudaSuccess)
     return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_condense_mma_kernel<ADAPT, MINB>, 32 * MMA_WPC, smem) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_condense_mma_kernel<ADAPT, MINB>, MMA_NT, smem) !=
       cudaSuccess)
     return -1;
   return nb;
@@ -102,18 +102,18 @@ size_t cmpc_condense_smem_bytes(int horizon, int nmax, int cshape, bool adapt) {
 }
 
 int cmpc_condense_max_ctas_per_sm(int cshape, size_t smem, bool adapt) {
-  if (cshape == CMPC_CSHAPE_MMA64) return adapt ? occ_mma_t<true, 2>(smem) : occ_mma_t<false, 2>(smem);
+  if (cshape == CMPC_CSHAPE_MMA64) return adapt ? occ_mma_t<true, 5>(smem) : occ_mma_t<false, 5>(smem);
   CMPC_CDISPATCH(occ_condense_t, smem)
 }
 
-int cmpc_condense_instances_per_cta(int cshape) { return cshape == CMPC_CSHAPE_MMA64 ? MMA_WPC : 1; }
+int cmpc_condense_instances_per_cta(int cshape) { (void)cshape; return 1; }
 
 int cmpc_launch_condense(const CmpcParams& P, int cshape, int grid, void* stream) {
   const bool adapt = P.adapt_mode >= 0;
   const size_t smem = cmpc_condense_smem_bytes(P.horizon, P.nmax, cshape, adapt);
   cudaStream_t st = (cudaStream_t)stream;
   if (cshape == CMPC_CSHAPE_MMA64)
-    return adapt ? launch_mma_t<true, 2>(P, grid, smem, st) : launch_mma_t<false, 2>(P, grid, smem, st);
+    return adapt ? launch_mma_t<true, 5>(P, grid, smem, st) : launch_mma_t<false, 5>(P, grid, smem, st);
   CMPC_CDISPATCH(launch_condense_t, P, grid, smem, st)
 }
 
