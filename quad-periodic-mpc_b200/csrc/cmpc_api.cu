@@ -216,7 +216,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
   int chunk = (int)std::min<size_t>((size_t)count, std::max<size_t>(1, budget / (slot * sizeof(double))));
   const int nchunks = (count + chunk - 1) / chunk;
   const size_t need = (size_t)chunk * slot * sizeof(double);
-  if (need > b->qws_bytes[si] || 3 * nchunks > b->sched_ints[si]) {
+  if (need > b->qws_bytes[si] || 4 * nchunks > b->sched_ints[si]) {
     for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
     if (need > b->qws_bytes[si]) {
       if (b->d_qws[si]) CK(cudaFree(b->d_qws[si]));
@@ -225,16 +225,16 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       CK(cudaMalloc(&b->d_qws[si], need));
       b->qws_bytes[si] = need;
     }
-    if (3 * nchunks > b->sched_ints[si]) {
+    if (4 * nchunks > b->sched_ints[si]) {
       if (b->d_sched[si]) CK(cudaFree(b->d_sched[si]));
       b->d_sched[si] = nullptr;
       b->sched_ints[si] = 0;
-      const int ints = std::max(3 * nchunks, 768);
+      const int ints = std::max(4 * nchunks, 1024);
       CK(cudaMalloc(&b->d_sched[si], sizeof(int) * ints));
       b->sched_ints[si] = ints;
     }
   }
-  CK(cudaMemsetAsync(b->d_sched[si], 0, sizeof(int) * 3 * nchunks, st));
+  CK(cudaMemsetAsync(b->d_sched[si], 0, sizeof(int) * 4 * nchunks, st));
   // kernel 1
   const size_t smem1 = cmpc_condense_smem_bytes(P.horizon, nmax, cshape, adapt);
   const int per_sm1 = cmpc_condense_max_ctas_per_sm(cshape, smem1, adapt);
@@ -242,10 +242,22 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     g_err = "cmpc_batch_solve: condensation kernel not launchable on this device (no sm_100a image?)";
     return CMPC_E_NODEVICE;
   }
+  const int per_sm_inv = tiled ? cmpc_invert_max_ctas_per_sm() : 1;
+  if (per_sm_inv < 1) {
+    g_err = "cmpc_batch_solve: inversion kernel not launchable on this device (no sm_100a image?)";
+    return CMPC_E_NODEVICE;
+  }
   // kernel 2, two working-set capacity tiers
-  int qcap1 = 16;
+  int qcap1 = 32;
   if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
   if (qcap1 < 1 || qcap1 > nmax) qcap1 = nmax;
+  bool fast = qcap1 <= 32;  // tier 1 on the register-resident kernel (cmpc_dual_fast.cuh)
+  if (const char* e = std::getenv("CMPC_DUAL")) fast = fast && std::strcmp(e, "generic") != 0;
+  int per_sm_fast = 0;
+  if (fast) {
+    per_sm_fast = cmpc_dual_fast_max_ctas_per_sm(nmax, cmpc_dual_fast_smem_bytes(nmax, qcap1));
+    if (per_sm_fast < 1) fast = false;
+  }
   int wpc1 = 4;
   if (const char* e = std::getenv("CMPC_WPC")) wpc1 = std::atoi(e);
   if (wpc1 != 1 && wpc1 != 2 && wpc1 != 4 && wpc1 != 8) wpc1 = 4;
@@ -283,12 +295,19 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.qws_goff = cmpc_qws_goff(nmax, tiled);
     Q.worklist = nullptr;
     Q.count_ptr = nullptr;
-    Q.sched = b->d_sched[si] + 3 * c;
+    Q.sched = b->d_sched[si] + 4 * c;
     const int ipc = cmpc_condense_instances_per_cta(cshape);
     int rc = cmpc_launch_condense(Q, cshape, std::min((cnt + ipc - 1) / ipc, b->sm_count * per_sm1), st);
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_condense_kernel launch");
     b->launches++;
-    Q.sched = b->d_sched[si] + 3 * c + 1;
+    if (tiled) {  // the assembly kernel left H tiles: invert them in place on the FP64 tensor cores
+      Q.sched = b->d_sched[si] + 4 * c + 3;
+      const int ipc2 = cmpc_invert_instances_per_cta();
+      rc = cmpc_launch_invert(Q, std::min((cnt + ipc2 - 1) / ipc2, b->sm_count * per_sm_inv), st);
+      if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_invert_mma_kernel launch");
+      b->launches++;
+    }
+    Q.sched = b->d_sched[si] + 4 * c + 1;
     Q.qcap = qcap1;
     if (qcap1 < nmax) {
       Q.overflow_list = b->d_overflow[si];
@@ -297,11 +316,12 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     } else {
       Q.overflow_list = nullptr;
     }
-    rc = cmpc_launch_dual(Q, wpc1, std::min((cnt + wpc1 - 1) / wpc1, b->sm_count * per_sm2), st);
+    if (fast) rc = cmpc_launch_dual_fast(Q, std::min((cnt + 3) / 4, b->sm_count * per_sm_fast), st);
+    else rc = cmpc_launch_dual(Q, wpc1, std::min((cnt + wpc1 - 1) / wpc1, b->sm_count * per_sm2), st);
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel launch");
     b->launches++;
     if (qcap1 < nmax) {
-      Q.sched = b->d_sched[si] + 3 * c + 2;
+      Q.sched = b->d_sched[si] + 4 * c + 2;
       Q.qcap = nmax;
       Q.worklist = b->d_overflow[si];
       Q.count_ptr = b->d_overflow[si] + b->capacity;

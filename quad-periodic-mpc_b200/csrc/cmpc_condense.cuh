@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
     const float* rec = reinterpret_cast<const float*>(recbuf[buf]);
     const unsigned char* gait = recbuf[buf] + 4 * (CMPC_REC_TRAJ + 12 * h);
     double* slot = P.qws + (size_t)inst * P.qws_stride;
-    int* hdr = reinterpret_cast<int*>(slot + P.qws_goff + 2 * P.nmax);
+    int* hdr = reinterpret_cast<int*>(slot + P.qws_goff + 2 * P.nmax + 2);
 
     // ---- 0. periodic-disturbance estimator (Adaptive MPC): xi for this instance, SolverMPC.cpp:688-798 ----
     if (ADAPT) {

@@ -152,7 +152,7 @@ __device__ __forceinline__ double tracking_error(const float* rec, const double*
 }  // namespace
 
 template <bool ADAPT, int MINB>
-__global__ void __launch_bounds__(MMA_NT, MINB) cmpc_condense_mma_kernel(const __grid_constant__ CmpcParams P) {
+__global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const __grid_constant__ CmpcParams P) {
   constexpr int NT = MMA_NT, PS = MMA_PS;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_condense_mma_kernel(const _
     const float* rec = reinterpret_cast<const float*>(recbuf[buf]);
     const unsigned char* gait = recbuf[buf] + 4 * (CMPC_REC_TRAJ + 12 * h);
     double* slot = P.qws + (size_t)inst * P.qws_stride;
-    int* hdr = reinterpret_cast<int*>(slot + P.qws_goff + 2 * P.nmax);
+    int* hdr = reinterpret_cast<int*>(slot + P.qws_goff + 2 * P.nmax + 2);
 
     // ---- 0. periodic-disturbance estimator (Adaptive MPC), SolverMPC.cpp:688-798 ----
     if (ADAPT) {
@@ -492,113 +492,7 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_condense_mma_kernel(const _
           }
         }
       }
-      pc.tick(CMPC_PH_HESS);
-
-      // ---- blocked symmetric sweep ----
-      const int fo = q * PS + r;  // fragment offset: element (k = q, row/col = r)
-#pragma unroll 1
-      for (int s = 0; s < nblk; s++) {
-        // 1. -D^-1 from the diagonal tile (s, s) by its owner; publish the panel with D - I in the diagonal block
-        const bool excl = (s == 7);  // block 7 holds the border row 63: it is not a pivot
-        if (ILO == s || IHI == s) {
-          double d0 = 0.0, d1 = 0.0;
-          if (ILO == s) {
-#pragma unroll
-            for (int J = 0; J < 4; J++)
-              if (J == s) { d0 = tl[J][0]; d1 = tl[J][1]; }
-          } else {
-#pragma unroll
-            for (int J = 4; J < 8; J++)
-              if (J == s) { d0 = th[J][0]; d1 = th[J][1]; }
-          }
-          if (excl) {
-            if (r == 7) { d0 = 0.0; d1 = (q == 3) ? 1.0 : 0.0; }
-            else if (q == 3) d1 = 0.0;
-          }
-          warp_inv8_acc(d0, d1, r, q);
-          *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
-        }
-        // row part: tiles (s, J <= s)
-        if (ILO == s) {
-#pragma unroll
-          for (int J = 0; J < 4; J++)
-            if (J <= s) {
-              double v0 = tl[J][0], v1 = tl[J][1];
-              if (J == s) {
-                if (r == 2 * q) v0 -= 1.0;
-                if (r == 2 * q + 1) v1 -= 1.0;
-              }
-              *reinterpret_cast<double2*>(pan + r * PS + 8 * J + 2 * q) = make_double2(v0, v1);
-            }
-        }
-        if (IHI == s) {
-#pragma unroll
-          for (int J = 0; J < 8; J++)
-            if (J <= s) {
-              double v0 = th[J][0], v1 = th[J][1];
-              if (J == s) {
-                if (r == 2 * q) v0 -= 1.0;
-                if (r == 2 * q + 1) v1 -= 1.0;
-              }
-              if (excl && r == 7) { v0 = 0.0; v1 = 0.0; }
-              *reinterpret_cast<double2*>(pan + r * PS + 8 * J + 2 * q) = make_double2(v0, v1);
-            }
-        }
-        // column part: tiles (I > s, s), transposed
-        if (ILO > s) {
-#pragma unroll
-          for (int J = 0; J < 3; J++)
-            if (J == s) {
-              pan[(2 * q) * PS + 8 * ILO + r] = tl[J][0];
-              pan[(2 * q + 1) * PS + 8 * ILO + r] = tl[J][1];
-            }
-        }
-        if (IHI > s) {
-#pragma unroll
-          for (int J = 0; J < 7; J++)
-            if (J == s) {
-              pan[(2 * q) * PS + 8 * IHI + r] = th[J][0];
-              pan[(2 * q + 1) * PS + 8 * IHI + r] = th[J][1];
-            }
-        }
-        __syncthreads();
-        // 2. M = -D^-1 C, tile columns 2w and 2w+1
-        {
-          const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
-#pragma unroll
-          for (int jj = 0; jj < 2; jj++) {
-            const int J = 2 * w + jj;
-            double m0 = 0.0, m1 = 0.0;
-            dmma884(m0, m1, a0, pan[fo + 8 * J]);
-            dmma884(m0, m1, a1, pan[fo + 4 * PS + 8 * J]);
-            *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(m0, m1);
-          }
-        }
-        __syncthreads();
-        // 3. tiles (I, J) += C_I' M_J
-        {
-          const bool dolo = ILO < nblk, dohi = (IHI < nblk) || IHI == 7;
-          const double pl0 = pan[fo + 8 * ILO], pl1 = pan[fo + 4 * PS + 8 * ILO];
-          const double ph0 = pan[fo + 8 * IHI], ph1 = pan[fo + 4 * PS + 8 * IHI];
-#pragma unroll
-          for (int J = 0; J < 8; J++) {
-            if (J <= IHI) {
-              const double m0 = mm[fo + 8 * J], m1 = mm[fo + 4 * PS + 8 * J];
-              if (J < 4 && J <= ILO && dolo) {
-                dmma884(tl[J < 4 ? J : 0][0], tl[J < 4 ? J : 0][1], pl0, m0);
-                dmma884(tl[J < 4 ? J : 0][0], tl[J < 4 ? J : 0][1], pl1, m1);
-              }
-              if (dohi) {
-                dmma884(th[J][0], th[J][1], ph0, m0);
-                dmma884(th[J][0], th[J][1], ph1, m1);
-              }
-            }
-          }
-        }
-        __syncthreads();  // the next publish overwrites pan and dv
-      }
-      pc.tick(CMPC_PH_SWEEP);
-      // ---- K_ij = -(A_ij - 2 d_ij) scale, tile-major, to the workspace slot; x0 = -scale A[63][:]; g ----
+      // ---- tiles (accumulator layout, scaled) and the scale to the workspace slot for the sweep kernel ----
       {
 #pragma unroll
         for (int t = 0; t < 2; t++) {
@@ -608,21 +502,14 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_condense_mma_kernel(const _
             if (t == 0 && J >= 4) continue;
             if (J <= I) {
               const double a0 = t ? th[J][0] : tl[J < 4 ? J : 0][0], a1 = t ? th[J][1] : tl[J < 4 ? J : 0][1];
-              const int i = 8 * I + r, j = 8 * J + 2 * q;
-              double2 kv;
-              kv.x = -(a0 - ((I == J && i == j) ? 2.0 : 0.0)) * scale;
-              kv.y = -(a1 - ((I == J && i == j + 1) ? 2.0 : 0.0)) * scale;
-              *reinterpret_cast<double2*>(slot + tix(I, J) * 64 + r * 8 + 2 * q) = kv;
-              if (t == 1 && w == 0 && r == 7) {
-                double* xo = slot + P.qws_goff + P.nmax;
-                if (j < n) xo[j] = -scale * a0;
-                if (j + 1 < n) xo[j + 1] = -scale * a1;
-              }
+              *reinterpret_cast<double2*>(slot + tix(I, J) * 64 + lane * 2) = make_double2(a0, a1);
             }
           }
         }
         for (int j = tid; j < n; j += NT) slot[P.qws_goff + j] = g[j];
+        if (tid == 0) slot[P.qws_goff + 2 * P.nmax] = scale;
       }
+      pc.tick(CMPC_PH_HESS);
       flops_acc += 2.0 * (double)n * n * n * 0.5 + 12.0 * (double)n * n + 2.0 * (double)n * n;
     }
     // contact list for kernel 2

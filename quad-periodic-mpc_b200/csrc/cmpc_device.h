@@ -118,7 +118,7 @@ struct CmpcParams {
 #define CMPC_CSHAPE_64 0   /* n <= 64, 128 threads */
 #define CMPC_CSHAPE_96 1   /* n <= 96, 256 threads */
 #define CMPC_CSHAPE_128 2  /* n <= 128, 256 threads */
-#define CMPC_CSHAPE_MMA64 3 /* n <= 64, one warp per instance, DMMA rank-8 updates, 4 instances per CTA */
+#define CMPC_CSHAPE_MMA64 3 /* n <= 63: assembly kernel (CTA per instance) + DMMA inversion kernel (warp per instance) */
 #define CMPC_PIPELINE_NMAX 128
 
 #define CMPC_KTILE_DOUBLES (36 * 64)
@@ -127,8 +127,8 @@ static inline int cmpc_qws_goff(int nmax, int tiled) {
   return (k + 1) & ~1;
 }
 static inline size_t cmpc_qws_slot_doubles(int nmax, int tiled) {
-  // K, g, x0, header {int nc, int status, uchar fs[CMPC_MAX_FS], uchar gait[CMPC_MAX_FS]}
-  size_t d = (size_t)cmpc_qws_goff(nmax, tiled) + 2 * (size_t)nmax + (8 + 2 * CMPC_MAX_FS + 7) / 8;
+  // K, g, x0, scale (+ pad), header {int nc, int status, uchar fs[CMPC_MAX_FS], uchar gait[CMPC_MAX_FS]}
+  size_t d = (size_t)cmpc_qws_goff(nmax, tiled) + 2 * (size_t)nmax + 2 + (8 + 2 * CMPC_MAX_FS + 7) / 8;
   return (d + 1) & ~(size_t)1;
 }
 
@@ -136,6 +136,12 @@ size_t cmpc_condense_smem_bytes(int horizon, int nmax, int cshape, bool adapt);
 int cmpc_condense_max_ctas_per_sm(int cshape, size_t smem, bool adapt);
 int cmpc_launch_condense(const CmpcParams& P, int cshape, int grid, void* stream);
 int cmpc_condense_instances_per_cta(int cshape);
+int cmpc_invert_max_ctas_per_sm(void);
+int cmpc_invert_instances_per_cta(void);
+int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream);
+size_t cmpc_dual_fast_smem_bytes(int nmax, int qcap);  /* per CTA of 4 warps; qcap <= 32, nmax <= 128 */
+int cmpc_dual_fast_max_ctas_per_sm(int nmax, size_t smem);
+int cmpc_launch_dual_fast(const CmpcParams& P, int grid, void* stream);
 size_t cmpc_dual_smem_bytes_per_warp(int nmax, int qcap);
 int cmpc_dual_max_ctas_per_sm(int warps_per_cta, size_t smem);
 int cmpc_launch_dual(const CmpcParams& P, int warps_per_cta, int grid, void* stream);

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
     const double* gg = slot + P.qws_goff;
     const bool tiled = P.k_tiled != 0;
     const double* x0 = gg + nmax;
-    const int* hdr = reinterpret_cast<const int*>(x0 + nmax);
+    const int* hdr = reinterpret_cast<const int*>(x0 + nmax + 2);
     const int nc = hdr[0];
     const int st0 = hdr[1];
     const unsigned char* hb = reinterpret_cast<const unsigned char*>(hdr + 2);

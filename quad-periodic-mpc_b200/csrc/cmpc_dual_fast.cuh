@@ -1,0 +1,353 @@
+// Kernel 2 of the pipeline, fast tier: Goldfarb-Idnani dual active set on K = H^-1, one warp per instance,
+// working sets of up to 32 rows (lane k owns working-set slot k).  Same method as cmpc_dual.cuh (which stays
+// as the any-capacity tier for the few instances that outgrow 32 rows); this variant keeps the iterate in
+// registers and trims the dependent chain of an iteration:
+//   * x, the slacks s and the per-row constants (which two variables a row touches, with what sign) live in
+//     registers: lane l owns variables l, l+32, ... and rows l, l+32, ...;
+//   * argmin over the violated rows / the ratio test: two REDUX.MIN on an order-preserving 64-bit key plus a
+//     ballot instead of five shuffle levels;
+//   * the multipliers u and the slot's row constants live in the slot's lane; P = (N'KN)^-1 is a full
+//     (not packed) matrix in shared memory, one row per lane; KN = K N is cached row by row.
+#pragma once
+
+namespace {
+
+struct FCarve {
+  int kn, z, d, r, P, KN, misc, total;
+};
+
+__host__ __device__ inline FCarve make_fcarve(int npl, int qcap) {
+  FCarve c;
+  int o = 0;
+  c.kn = o; o += 8 * 32 * npl;
+  c.z = o; o += 8 * 32 * npl;
+  c.d = o; o += 8 * 32;
+  c.r = o; o += 8 * 32;
+  c.P = o; o += align16(8 * qcap * (qcap + 1));
+  c.KN = o; o += 8 * qcap * 32 * npl;
+  c.misc = o; o += 3 * CMPC_MAX_FS + 16;  // fs, gv, fsinv bytes
+  c.total = align16(o);
+  return c;
+}
+
+// order-preserving map double -> uint64 (smaller double <=> smaller key)
+__device__ __forceinline__ unsigned long long dkey(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// warp argmin of (val, idx): returns the smallest val and, among equal values, the smallest idx
+__device__ __forceinline__ void warp_argmin_redux(double& val, int& idx) {
+  const unsigned long long k = dkey(val);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  const bool win = (hi == mhi) && (lo == mlo);
+  const unsigned midx = __reduce_min_sync(0xffffffffu, win ? (unsigned)idx : 0xffffffffu);
+  const unsigned src = __ffs(__ballot_sync(0xffffffffu, win && (unsigned)idx == midx)) - 1;
+  val = __shfl_sync(0xffffffffu, val, src);
+  idx = (int)midx;
+}
+
+// row c = 5j + t of the reduced problem as s(x) = va x[ia] + vz x[iz] - b >= 0, packed: ia | iz << 8 | t << 16
+__device__ __forceinline__ int cons_pack(int c) {
+  const int j = c / 5, t = c - 5 * j;
+  const int iz = 3 * j + 2, ia = (t == 4) ? iz : 3 * j + (t >> 1);
+  return ia | (iz << 8) | (t << 16);
+}
+__device__ __forceinline__ double cons_va(int pk, double mu_inv) {
+  const int t = pk >> 16;
+  return (t == 4) ? 0.0 : ((t & 1) ? -mu_inv : mu_inv);
+}
+__device__ __forceinline__ double cons_vz(int pk) { return ((pk >> 16) == 4) ? -1.0 : 1.0; }
+
+}  // namespace
+
+template <int WPC, int NPL, int MPL>
+__global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_constant__ CmpcParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = P.horizon, nmax = P.nmax, qcap = P.qcap;  // qcap <= 32
+  const FCarve cv = make_fcarve(NPL, qcap);
+  unsigned char* base = smem + (size_t)warp * cv.total;
+  double* kns = reinterpret_cast<double*>(base + cv.kn);
+  double* zs = reinterpret_cast<double*>(base + cv.z);
+  double* dvec = reinterpret_cast<double*>(base + cv.d);
+  double* rvec = reinterpret_cast<double*>(base + cv.r);
+  double* Pm = reinterpret_cast<double*>(base + cv.P);
+  double* KN = reinterpret_cast<double*>(base + cv.KN);
+  unsigned char* fs = base + cv.misc;
+  unsigned char* gv = fs + CMPC_MAX_FS;
+  signed char* fsinv = reinterpret_cast<signed char*>(gv + CMPC_MAX_FS);
+  constexpr int NS = 32 * NPL;  // KN row stride
+  const int PSQ = qcap + 1;     // P row stride (odd for qcap = 32: conflict-free row-per-lane access)
+
+  const int count = P.count_ptr ? min(*P.count_ptr, P.count) : P.count;
+  const double mu_inv = P.mu_inv;
+  double flops_acc = 0.0;
+
+  while (true) {
+    int slot_i = 0;
+    if (lane == 0) slot_i = atomicAdd(P.sched, 1);
+    slot_i = __shfl_sync(0xffffffffu, slot_i, 0);
+    if (slot_i >= count) break;
+    const int inst = P.worklist ? P.worklist[slot_i] : slot_i;
+    const double* slot = P.qws + (size_t)inst * P.qws_stride;
+    const double* gg = slot + P.qws_goff;
+    const double* x0 = gg + nmax;
+    const int* hdr = reinterpret_cast<const int*>(x0 + nmax + 2);
+    const bool tiled = P.k_tiled != 0;
+    const int nc = hdr[0];
+    const int st0 = hdr[1];
+    const unsigned char* hb = reinterpret_cast<const unsigned char*>(hdr + 2);
+    const int n = 3 * nc, m = 5 * nc;
+    const bool have = (st0 == CMPC_ST_SOLVED) && n <= NS && m <= 32 * MPL;
+
+    for (int k = lane; k < 4 * h; k += 32) fsinv[k] = -1;
+    __syncwarp();
+    double x[NPL], s[MPL];
+    int cpk[MPL];
+    unsigned amask = 0;  // bit j: row lane + 32 j is in the working set
+#pragma unroll
+    for (int e = 0; e < NPL; e++) x[e] = 0.0;
+    if (have) {
+      for (int j = lane; j < nc; j += 32) {
+        const unsigned char k = hb[j];
+        fs[j] = k;
+        gv[j] = hb[CMPC_MAX_FS + j];
+        fsinv[k] = (signed char)j;
+      }
+#pragma unroll
+      for (int e = 0; e < NPL; e++) {
+        const int i = lane + 32 * e;
+        x[e] = (i < n) ? x0[i] : 0.0;
+        kns[i] = x[e];  // staged for the slack gather below
+      }
+    }
+    __syncwarp();
+    int status = (st0 == CMPC_ST_SOLVED && !have) ? CMPC_ST_CAPACITY : st0, iters = 0, q = 0;
+    // working-set slot state of this lane (slot = lane)
+    int spk = 0, sact = -1;
+    double u = 0.0;
+    if (have) {
+#pragma unroll
+      for (int j = 0; j < MPL; j++) {
+        const int c = lane + 32 * j;
+        cpk[j] = 0;
+        s[j] = 1e300;  // rows beyond m never violate
+        if (c < m) {
+          const int pk = cons_pack(c);
+          cpk[j] = pk;
+          const double b = ((pk >> 16) == 4) ? -(double)gv[c / 5] * P.f_max : 0.0;
+          s[j] = cons_va(pk, mu_inv) * kns[pk & 0xff] + cons_vz(pk) * kns[(pk >> 8) & 0xff] - b;
+        }
+      }
+      __syncwarp();
+      bool done = false;
+      while (!done) {
+        // most violated row outside the working set
+        double best = 1e300;
+        int bidx = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < MPL; j++)
+          if (!((amask >> j) & 1u) && s[j] < best) { best = s[j]; bidx = lane + 32 * j; }
+        warp_argmin_redux(best, bidx);
+        if (!(best < -P.tol_violation)) break;
+        const int p = bidx;
+        const int ppk = cons_pack(p);
+        const int pia = ppk & 0xff, piz = (ppk >> 8) & 0xff;
+        const double pva = cons_va(ppk, mu_inv), pvz = cons_vz(ppk);
+        double kn[NPL];
+#pragma unroll
+        for (int e = 0; e < NPL; e++) {
+          const int i = lane + 32 * e;
+          kn[e] = (i < n) ? pva * k_entry(slot, n, tiled, pia, i) + pvz * k_entry(slot, n, tiled, piz, i) : 0.0;
+          kns[i] = kn[e];
+        }
+        __syncwarp();
+        const double scale = pva * kns[pia] + pvz * kns[piz];
+        double up = 0.0;
+        while (true) {
+          iters++;
+          if (iters > P.max_iter) { status = CMPC_ST_MAXITER; done = true; break; }
+          // d = N' kn (slot per lane), r = P d
+          const double d = (lane < q) ? cons_va(spk, mu_inv) * kns[spk & 0xff] + cons_vz(spk) * kns[(spk >> 8) & 0xff] : 0.0;
+          dvec[lane] = d;
+          __syncwarp();
+          double rr = 0.0;
+          if (lane < q) {
+            const double* prow = Pm + lane * PSQ;
+            for (int l = 0; l < q; l++) rr = fma(prow[l], dvec[l], rr);
+          }
+          rvec[lane] = rr;
+          const double dr = warp_sum(d * rr);
+          double ratio = (lane < q && rr > 0.0) ? u / rr : 1e300;
+          int kd = lane;
+          warp_argmin_redux(ratio, kd);
+          __syncwarp();
+          const double rho2 = scale - dr;
+          const bool dependent = !(rho2 > 1e-12 * scale);
+          double z[NPL];
+          if (!dependent) {
+#pragma unroll
+            for (int e = 0; e < NPL; e++) z[e] = kn[e];
+            for (int k = 0; k < q; k++) {
+              const double rk = rvec[k];
+#pragma unroll
+              for (int e = 0; e < NPL; e++) z[e] = fma(-rk, KN[k * NS + lane + 32 * e], z[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < NPL; e++) zs[lane + 32 * e] = z[e];
+            __syncwarp();
+          }
+          // slack of the candidate row (held by lane p & 31, register p >> 5)
+          double sp = 0.0;
+#pragma unroll
+          for (int j = 0; j < MPL; j++)
+            if (j == (p >> 5)) sp = s[j];
+          sp = __shfl_sync(0xffffffffu, sp, p & 31);
+          const double rho2_inv = dependent ? 0.0 : fast_rcp(rho2);
+          const double t2 = dependent ? 1e300 : -sp * rho2_inv;
+          const double t1 = ratio;
+          const double t = fmin(t1, t2);
+          if (t >= 1e299) { status = CMPC_ST_INFEASIBLE; done = true; break; }
+          const bool full = (t2 <= t1);
+          if (!dependent) {
+#pragma unroll
+            for (int e = 0; e < NPL; e++) x[e] = fma(t, z[e], x[e]);
+#pragma unroll
+            for (int j = 0; j < MPL; j++) {
+              const int pk = cpk[j];
+              if (lane + 32 * j < m)
+                s[j] = fma(t, cons_va(pk, mu_inv) * zs[pk & 0xff] + cons_vz(pk) * zs[(pk >> 8) & 0xff], s[j]);
+            }
+          }
+          if (lane < q) u = fma(-t, rr, u);
+          up += t;
+          flops_acc += 2.0 * (4.0 * n + 4.0 * q + (double)q * q + (double)n * q + 4.0 * m + n);
+          if (full) {
+            if (q >= qcap) { status = CMPC_ST_WSOVERFLOW; done = true; break; }
+            // border P with the new row: [P + r r'/rho2, -r/rho2; -r'/rho2, 1/rho2]; cache K n_p; slot q <- row p
+            if (lane < q) {
+              const double rk = rr * rho2_inv;
+              double* prow = Pm + lane * PSQ;
+              for (int l = 0; l < q; l++) prow[l] = fma(rk, rvec[l], prow[l]);
+              prow[q] = -rk;
+              Pm[q * PSQ + lane] = -rk;
+            }
+            if (lane == q) {
+              Pm[q * PSQ + q] = rho2_inv;
+              spk = ppk;
+              sact = p;
+              u = up;
+            }
+#pragma unroll
+            for (int e = 0; e < NPL; e++) KN[q * NS + lane + 32 * e] = kn[e];
+            if (lane == (p & 31)) amask |= 1u << (p >> 5);
+            q++;
+            flops_acc += 2.0 * (double)q * q;
+            __syncwarp();
+            break;
+          }
+          // partial step: slot kd leaves the working set (P deflated by its row/column), p stays the candidate
+          {
+            const double ckd = Pm[kd * PSQ + kd];
+            const double inv = 1.0 / ckd;
+            if (lane < q && lane != kd) {
+              double* prow = Pm + lane * PSQ;
+              const double* krow = Pm + kd * PSQ;
+              const double ck = prow[kd] * inv;
+              for (int l = 0; l < q; l++)
+                if (l != kd) prow[l] = fma(-ck, krow[l], prow[l]);
+            }
+          }
+          __syncwarp();
+          const int last = q - 1;
+          const int dropped = __shfl_sync(0xffffffffu, sact, kd);
+          if (lane == (dropped & 31)) amask &= ~(1u << (dropped >> 5));
+          {
+            // slot kd <- slot last (row, column, cached K n, multiplier, row constants)
+            const int lspk = __shfl_sync(0xffffffffu, spk, last), lsact = __shfl_sync(0xffffffffu, sact, last);
+            const double lu = __shfl_sync(0xffffffffu, u, last);
+            if (kd != last) {
+              if (lane < last && lane != kd) {
+                const double v = Pm[last * PSQ + lane];
+                Pm[kd * PSQ + lane] = v;
+                Pm[lane * PSQ + kd] = v;
+              }
+              if (lane == kd) {
+                Pm[kd * PSQ + kd] = Pm[last * PSQ + last];
+                spk = lspk;
+                sact = lsact;
+                u = lu;
+              }
+#pragma unroll
+              for (int e = 0; e < NPL; e++) KN[kd * NS + lane + 32 * e] = KN[last * NS + lane + 32 * e];
+            }
+            if (lane == last) { sact = -1; u = 0.0; }
+          }
+          q--;
+          flops_acc += 2.0 * (double)q * q;
+          __syncwarp();
+        }
+      }
+    }
+    if (status == CMPC_ST_WSOVERFLOW && P.overflow_list) {
+      if (lane == 0) {  // left for the any-capacity launch
+        const int pos = atomicAdd(P.overflow_count, 1);
+        P.overflow_list[pos] = inst;
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- outputs: q_soln scatter (zeros for swing feet), objective, primal activity mask ----
+    const bool have_x = have;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) kns[lane + 32 * e] = x[e];
+    __syncwarp();
+    if (P.forces) {
+      double* out = P.forces + (size_t)inst * 12 * h;
+      for (int idx = lane; idx < 12 * h; idx += 32) {
+        const int k = idx / 3, comp = idx - 3 * k;
+        const int j = fsinv[k];
+        out[idx] = (j >= 0 && have_x) ? kns[3 * j + comp] : 0.0;
+      }
+    }
+    if (P.active) {
+      signed char* out = P.active + (size_t)inst * 20 * h;
+      for (int idx = lane; idx < 20 * h; idx += 32) {
+        const int k = idx / 5, t = idx - 5 * k;
+        const int j = fsinv[k];
+        signed char a = 0;
+        if (j >= 0 && have_x) {
+          const double fx = kns[3 * j], fy = kns[3 * j + 1], fz = kns[3 * j + 2];
+          const double row = (t == 0) ? fx * mu_inv + fz : (t == 1) ? -fx * mu_inv + fz : (t == 2) ? fy * mu_inv + fz
+                           : (t == 3) ? -fy * mu_inv + fz : fz;
+          if (row <= P.tol_active) a = -1;
+          if (t == 4 && row >= (double)gv[j] * P.f_max - P.tol_active) a = 1;
+        }
+        out[idx] = a;
+      }
+    }
+    {
+      // objective 0.5 x'Hx + g'x = 0.5 g'x + 0.5 lambda'b at a KKT point
+      double part = 0.0;
+      if (have_x) {
+#pragma unroll
+        for (int e = 0; e < NPL; e++) {
+          const int i = lane + 32 * e;
+          if (i < n) part = fma(0.5 * __ldg(gg + i), x[e], part);
+        }
+        if (lane < q && (spk >> 16) == 4) part -= 0.5 * u * (double)gv[sact / 5] * P.f_max;
+      }
+      part = warp_sum(part);
+      if (lane == 0) {
+        if (P.objective) P.objective[inst] = have_x ? part : 0.0;
+        if (P.status) P.status[inst] = status;
+        if (P.iterations) P.iterations[inst] = iters;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops, (unsigned long long)flops_acc);
+}

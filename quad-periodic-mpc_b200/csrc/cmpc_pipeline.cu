@@ -22,7 +22,9 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 #include "cmpc_adapt.cuh"
 #include "cmpc_condense.cuh"
 #include "cmpc_condense_mma.cuh"
+#include "cmpc_invert_mma.cuh"
 #include "cmpc_dual.cuh"
+#include "cmpc_dual_fast.cuh"
 
 namespace {
 
@@ -46,19 +48,19 @@ int occ_condense_t(size_t smem) {
 }
 template <bool ADAPT, int MINB>
 int launch_mma_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cmpc_condense_mma_kernel<ADAPT, MINB>,
+  cudaError_t e = cudaFuncSetAttribute(cmpc_assemble_mma_kernel<ADAPT, MINB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  cmpc_condense_mma_kernel<ADAPT, MINB><<<grid, MMA_NT, smem, st>>>(P);
+  cmpc_assemble_mma_kernel<ADAPT, MINB><<<grid, MMA_NT, smem, st>>>(P);
   return (int)cudaGetLastError();
 }
 template <bool ADAPT, int MINB>
 int occ_mma_t(size_t smem) {
   int nb = 0;
-  if (cudaFuncSetAttribute(cmpc_condense_mma_kernel<ADAPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(cmpc_assemble_mma_kernel<ADAPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)smem) != cudaSuccess)
     return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_condense_mma_kernel<ADAPT, MINB>, MMA_NT, smem) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_assemble_mma_kernel<ADAPT, MINB>, MMA_NT, smem) !=
       cudaSuccess)
     return -1;
   return nb;
@@ -102,7 +104,7 @@ size_t cmpc_condense_smem_bytes(int horizon, int nmax, int cshape, bool adapt) {
 }
 
 int cmpc_condense_max_ctas_per_sm(int cshape, size_t smem, bool adapt) {
-  if (cshape == CMPC_CSHAPE_MMA64) return adapt ? occ_mma_t<true, 5>(smem) : occ_mma_t<false, 5>(smem);
+  if (cshape == CMPC_CSHAPE_MMA64) return adapt ? occ_mma_t<true, 6>(smem) : occ_mma_t<false, 6>(smem);
   CMPC_CDISPATCH(occ_condense_t, smem)
 }
 
@@ -113,7 +115,7 @@ int cmpc_launch_condense(const CmpcParams& P, int cshape, int grid, void* stream
   const size_t smem = cmpc_condense_smem_bytes(P.horizon, P.nmax, cshape, adapt);
   cudaStream_t st = (cudaStream_t)stream;
   if (cshape == CMPC_CSHAPE_MMA64)
-    return adapt ? launch_mma_t<true, 5>(P, grid, smem, st) : launch_mma_t<false, 5>(P, grid, smem, st);
+    return adapt ? launch_mma_t<true, 6>(P, grid, smem, st) : launch_mma_t<false, 6>(P, grid, smem, st);
   CMPC_CDISPATCH(launch_condense_t, P, grid, smem, st)
 }
 
@@ -137,4 +139,48 @@ int cmpc_launch_dual(const CmpcParams& P, int wpc, int grid, void* stream) {
     case 4: return launch_dual_t<4>(P, grid, smem, st);
     default: return launch_dual_t<8>(P, grid, smem, st);
   }
+}
+
+// ---- inversion kernel of the n <= 63 path (cmpc_invert_mma.cuh) ----
+int cmpc_invert_max_ctas_per_sm(void) {
+  int nb = 0;
+  const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
+  if (cudaFuncSetAttribute(cmpc_invert_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_invert_mma_kernel<2>, 32 * INV_WPC, smem) != cudaSuccess) return -1;
+  return nb;
+}
+int cmpc_invert_instances_per_cta(void) { return INV_WPC; }
+int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
+  const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
+  cudaError_t e = cudaFuncSetAttribute(cmpc_invert_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cmpc_invert_mma_kernel<2><<<grid, 32 * INV_WPC, smem, (cudaStream_t)stream>>>(P);
+  return (int)cudaGetLastError();
+}
+
+// ---- fast tier of the dual active-set kernel (cmpc_dual_fast.cuh): working sets of up to 32 rows ----
+namespace {
+template <int NPL, int MPL>
+int launch_fast_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(cmpc_dual_fast_kernel<4, NPL, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cmpc_dual_fast_kernel<4, NPL, MPL><<<grid, 128, smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+template <int NPL, int MPL>
+int occ_fast_t(size_t smem) {
+  int nb = 0;
+  if (cudaFuncSetAttribute(cmpc_dual_fast_kernel<4, NPL, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_dual_fast_kernel<4, NPL, MPL>, 128, smem) != cudaSuccess) return -1;
+  return nb;
+}
+}  // namespace
+
+size_t cmpc_dual_fast_smem_bytes(int nmax, int qcap) { return 4 * (size_t)make_fcarve(nmax <= 64 ? 2 : 4, qcap).total; }
+int cmpc_dual_fast_max_ctas_per_sm(int nmax, size_t smem) { return nmax <= 64 ? occ_fast_t<2, 4>(smem) : occ_fast_t<4, 7>(smem); }
+int cmpc_launch_dual_fast(const CmpcParams& P, int grid, void* stream) {
+  const size_t smem = cmpc_dual_fast_smem_bytes(P.nmax, P.qcap);
+  return P.nmax <= 64 ? launch_fast_t<2, 4>(P, grid, smem, (cudaStream_t)stream) : launch_fast_t<4, 7>(P, grid, smem, (cudaStream_t)stream);
 }
