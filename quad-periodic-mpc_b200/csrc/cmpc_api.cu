@@ -316,7 +316,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     } else {
       Q.overflow_list = nullptr;
     }
-    if (fast) rc = cmpc_launch_dual_fast(Q, std::min((cnt + 3) / 4, b->sm_count * per_sm_fast), st);
+    if (fast) rc = cmpc_launch_dual_fast(Q, std::min(cnt, b->sm_count * per_sm_fast), st);
     else rc = cmpc_launch_dual(Q, wpc1, std::min((cnt + wpc1 - 1) / wpc1, b->sm_count * per_sm2), st);
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel launch");
     b->launches++;

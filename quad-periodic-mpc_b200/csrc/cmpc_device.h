@@ -139,7 +139,7 @@ int cmpc_condense_instances_per_cta(int cshape);
 int cmpc_invert_max_ctas_per_sm(void);
 int cmpc_invert_instances_per_cta(void);
 int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream);
-size_t cmpc_dual_fast_smem_bytes(int nmax, int qcap);  /* per CTA of 4 warps; qcap <= 32, nmax <= 128 */
+size_t cmpc_dual_fast_smem_bytes(int nmax, int qcap);  /* per CTA of one warp; qcap <= 32, nmax <= 128 */
 int cmpc_dual_fast_max_ctas_per_sm(int nmax, size_t smem);
 int cmpc_launch_dual_fast(const CmpcParams& P, int grid, void* stream);
 size_t cmpc_dual_smem_bytes_per_warp(int nmax, int qcap);

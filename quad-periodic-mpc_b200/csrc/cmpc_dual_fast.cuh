@@ -7,7 +7,10 @@
 //   * argmin over the violated rows / the ratio test: two REDUX.MIN on an order-preserving 64-bit key plus a
 //     ballot instead of five shuffle levels;
 //   * the multipliers u and the slot's row constants live in the slot's lane; P = (N'KN)^-1 is a full
-//     (not packed) matrix in shared memory, one row per lane; KN = K N is cached row by row.
+//     (not packed) matrix in shared memory, one row per lane; KN = K N is cached row by row;
+//   * every O(q) loop is unrolled by four over zero-padded data so that its shared-memory loads overlap;
+//   * the two rows of K of the NEXT candidate are requested from L2 as soon as the slacks have moved,
+//     before the working-set matrices are bordered, so most of that latency is off the chain.
 #pragma once
 
 namespace {
@@ -21,10 +24,10 @@ __host__ __device__ inline FCarve make_fcarve(int npl, int qcap) {
   int o = 0;
   c.kn = o; o += 8 * 32 * npl;
   c.z = o; o += 8 * 32 * npl;
-  c.d = o; o += 8 * 32;
-  c.r = o; o += 8 * 32;
-  c.P = o; o += align16(8 * qcap * (qcap + 1));
-  c.KN = o; o += 8 * qcap * 32 * npl;
+  c.d = o; o += 8 * 40;
+  c.r = o; o += 8 * 40;
+  c.P = o; o += align16(8 * (qcap * ((qcap + 4) | 1) + 8));
+  c.KN = o; o += 8 * (qcap + 4) * 32 * npl;
   c.misc = o; o += 3 * CMPC_MAX_FS + 16;  // fs, gv, fsinv bytes
   c.total = align16(o);
   return c;
@@ -80,12 +83,18 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
   unsigned char* gv = fs + CMPC_MAX_FS;
   signed char* fsinv = reinterpret_cast<signed char*>(gv + CMPC_MAX_FS);
   constexpr int NS = 32 * NPL;  // KN row stride
-  const int PSQ = qcap + 1;     // P row stride (odd for qcap = 32: conflict-free row-per-lane access)
+  const int PSQ = (qcap + 4) | 1;  // P row stride: room for the 4-wide padded loops, odd (conflict-free row-per-lane access)
 
   const int count = P.count_ptr ? min(*P.count_ptr, P.count) : P.count;
   const double mu_inv = P.mu_inv;
   double flops_acc = 0.0;
+  for (int i = lane; i < qcap * PSQ + 8; i += 32) Pm[i] = 0.0;  // the unrolled loops read (finite, zero-weighted) padding
+  for (int i = lane; i < (qcap + 4) * NS; i += 32) KN[i] = 0.0;
+  for (int i = lane; i < 40; i += 32) { dvec[i] = 0.0; rvec[i] = 0.0; }
+  __syncwarp();
 
+  long long tclk = 0;
+  if (P.phase_cycles && lane == 0) tclk = clock64();
   while (true) {
     int slot_i = 0;
     if (lane == 0) slot_i = atomicAdd(P.sched, 1);
@@ -143,26 +152,38 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
         }
       }
       __syncwarp();
-      bool done = false;
-      while (!done) {
-        // most violated row outside the working set
-        double best = 1e300;
-        int bidx = 0x7fffffff;
+      if (P.phase_cycles && lane == 0) {
+        const long long now = clock64();
+        atomicAdd(P.phase_cycles + CMPC_PH_STORE, (unsigned long long)(now - tclk));  // instance setup
+        tclk = now;
+      }
+      // most violated row outside the working set; its two rows of K
+      double best = 1e300;
+      int p = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < MPL; j++)
-          if (!((amask >> j) & 1u) && s[j] < best) { best = s[j]; bidx = lane + 32 * j; }
-        warp_argmin_redux(best, bidx);
-        if (!(best < -P.tol_violation)) break;
-        const int p = bidx;
-        const int ppk = cons_pack(p);
+      for (int j = 0; j < MPL; j++)
+        if (s[j] < best) { best = s[j]; p = lane + 32 * j; }
+      warp_argmin_redux(best, p);
+      bool done = !(best < -P.tol_violation);
+      double ka[NPL], kz[NPL];  // raw rows of K of the candidate
+      int ppk = 0;
+      if (!done) {
+        ppk = cons_pack(p);
+#pragma unroll
+        for (int e = 0; e < NPL; e++) {
+          const int i = lane + 32 * e;
+          ka[e] = (i < n) ? k_entry(slot, n, tiled, ppk & 0xff, i) : 0.0;
+          kz[e] = (i < n) ? k_entry(slot, n, tiled, (ppk >> 8) & 0xff, i) : 0.0;
+        }
+      }
+      while (!done) {
         const int pia = ppk & 0xff, piz = (ppk >> 8) & 0xff;
         const double pva = cons_va(ppk, mu_inv), pvz = cons_vz(ppk);
         double kn[NPL];
 #pragma unroll
         for (int e = 0; e < NPL; e++) {
-          const int i = lane + 32 * e;
-          kn[e] = (i < n) ? pva * k_entry(slot, n, tiled, pia, i) + pvz * k_entry(slot, n, tiled, piz, i) : 0.0;
-          kns[i] = kn[e];
+          kn[e] = pva * ka[e] + pvz * kz[e];
+          kns[lane + 32 * e] = kn[e];
         }
         __syncwarp();
         const double scale = pva * kns[pia] + pvz * kns[piz];
@@ -170,6 +191,7 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
         while (true) {
           iters++;
           if (iters > P.max_iter) { status = CMPC_ST_MAXITER; done = true; break; }
+          const int q4 = (q + 3) & ~3;
           // d = N' kn (slot per lane), r = P d
           const double d = (lane < q) ? cons_va(spk, mu_inv) * kns[spk & 0xff] + cons_vz(spk) * kns[(spk >> 8) & 0xff] : 0.0;
           dvec[lane] = d;
@@ -177,11 +199,18 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
           double rr = 0.0;
           if (lane < q) {
             const double* prow = Pm + lane * PSQ;
-            for (int l = 0; l < q; l++) rr = fma(prow[l], dvec[l], rr);
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+            for (int l = 0; l < q4; l += 4) {
+              r0 = fma(prow[l], dvec[l], r0);
+              r1 = fma(prow[l + 1], dvec[l + 1], r1);
+              r2 = fma(prow[l + 2], dvec[l + 2], r2);
+              r3 = fma(prow[l + 3], dvec[l + 3], r3);
+            }
+            rr = (r0 + r1) + (r2 + r3);
           }
           rvec[lane] = rr;
           const double dr = warp_sum(d * rr);
-          double ratio = (lane < q && rr > 0.0) ? u / rr : 1e300;
+          double ratio = (lane < q && rr > 0.0) ? u * fast_rcp(rr) : 1e300;
           int kd = lane;
           warp_argmin_redux(ratio, kd);
           __syncwarp();
@@ -191,10 +220,13 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
           if (!dependent) {
 #pragma unroll
             for (int e = 0; e < NPL; e++) z[e] = kn[e];
-            for (int k = 0; k < q; k++) {
-              const double rk = rvec[k];
+            for (int k = 0; k < q4; k += 4) {  // rvec is zero beyond q, the KN padding rows are finite
 #pragma unroll
-              for (int e = 0; e < NPL; e++) z[e] = fma(-rk, KN[k * NS + lane + 32 * e], z[e]);
+              for (int kk = 0; kk < 4; kk++) {
+                const double rk = rvec[k + kk];
+#pragma unroll
+                for (int e = 0; e < NPL; e++) z[e] = fma(-rk, KN[(k + kk) * NS + lane + 32 * e], z[e]);
+              }
             }
 #pragma unroll
             for (int e = 0; e < NPL; e++) zs[lane + 32 * e] = z[e];
@@ -227,12 +259,40 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
           flops_acc += 2.0 * (4.0 * n + 4.0 * q + (double)q * q + (double)n * q + 4.0 * m + n);
           if (full) {
             if (q >= qcap) { status = CMPC_ST_WSOVERFLOW; done = true; break; }
+            if (lane == (p & 31)) amask |= 1u << (p >> 5);
+            // next candidate: request its rows of K now, border the working-set matrices while they travel
+            double nbest = 1e300;
+            int pn = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < MPL; j++)
+              if (!((amask >> j) & 1u) && s[j] < nbest) { nbest = s[j]; pn = lane + 32 * j; }
+            warp_argmin_redux(nbest, pn);
+            const bool more = nbest < -P.tol_violation;
+            double na[NPL], nz[NPL];
+            int npk = 0;
+            if (more) {
+              npk = cons_pack(pn);
+#pragma unroll
+              for (int e = 0; e < NPL; e++) {
+                const int i = lane + 32 * e;
+                na[e] = (i < n) ? k_entry(slot, n, tiled, npk & 0xff, i) : 0.0;
+                nz[e] = (i < n) ? k_entry(slot, n, tiled, (npk >> 8) & 0xff, i) : 0.0;
+              }
+            }
             // border P with the new row: [P + r r'/rho2, -r/rho2; -r'/rho2, 1/rho2]; cache K n_p; slot q <- row p
             if (lane < q) {
               const double rk = rr * rho2_inv;
               double* prow = Pm + lane * PSQ;
-              for (int l = 0; l < q; l++) prow[l] = fma(rk, rvec[l], prow[l]);
-              prow[q] = -rk;
+              for (int l = 0; l < q4; l += 4) {
+                const double v0 = fma(rk, rvec[l], prow[l]), v1 = fma(rk, rvec[l + 1], prow[l + 1]);
+                const double v2 = fma(rk, rvec[l + 2], prow[l + 2]), v3 = fma(rk, rvec[l + 3], prow[l + 3]);
+                prow[l] = v0; prow[l + 1] = v1; prow[l + 2] = v2; prow[l + 3] = v3;
+              }
+            }
+            __syncwarp();  // the padded writes above touch columns q..q4-1: order them before the new column
+            if (lane < q) {
+              const double rk = rr * rho2_inv;
+              Pm[lane * PSQ + q] = -rk;
               Pm[q * PSQ + lane] = -rk;
             }
             if (lane == q) {
@@ -243,22 +303,28 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
             }
 #pragma unroll
             for (int e = 0; e < NPL; e++) KN[q * NS + lane + 32 * e] = kn[e];
-            if (lane == (p & 31)) amask |= 1u << (p >> 5);
             q++;
             flops_acc += 2.0 * (double)q * q;
             __syncwarp();
+            if (!more) done = true;
+            p = pn;
+            ppk = npk;
+#pragma unroll
+            for (int e = 0; e < NPL; e++) { ka[e] = na[e]; kz[e] = nz[e]; }
             break;
           }
           // partial step: slot kd leaves the working set (P deflated by its row/column), p stays the candidate
           {
-            const double ckd = Pm[kd * PSQ + kd];
-            const double inv = 1.0 / ckd;
+            const double inv = fast_rcp(Pm[kd * PSQ + kd]);
             if (lane < q && lane != kd) {
               double* prow = Pm + lane * PSQ;
               const double* krow = Pm + kd * PSQ;
               const double ck = prow[kd] * inv;
-              for (int l = 0; l < q; l++)
-                if (l != kd) prow[l] = fma(-ck, krow[l], prow[l]);
+              for (int l = 0; l < q4; l += 4) {
+                const double v0 = fma(-ck, krow[l], prow[l]), v1 = fma(-ck, krow[l + 1], prow[l + 1]);
+                const double v2 = fma(-ck, krow[l + 2], prow[l + 2]), v3 = fma(-ck, krow[l + 3], prow[l + 3]);
+                prow[l] = v0; prow[l + 1] = v1; prow[l + 2] = v2; prow[l + 3] = v3;
+              }
             }
           }
           __syncwarp();
@@ -266,17 +332,20 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
           const int dropped = __shfl_sync(0xffffffffu, sact, kd);
           if (lane == (dropped & 31)) amask &= ~(1u << (dropped >> 5));
           {
-            // slot kd <- slot last (row, column, cached K n, multiplier, row constants)
+            // slot kd <- slot last (row, column, cached K n, multiplier, row constants); slot last is cleared
             const int lspk = __shfl_sync(0xffffffffu, spk, last), lsact = __shfl_sync(0xffffffffu, sact, last);
             const double lu = __shfl_sync(0xffffffffu, u, last);
+            double vrow = 0.0;
+            if (lane < last && lane != kd) vrow = Pm[last * PSQ + lane];
+            const double vdiag = Pm[last * PSQ + last];
+            __syncwarp();
             if (kd != last) {
               if (lane < last && lane != kd) {
-                const double v = Pm[last * PSQ + lane];
-                Pm[kd * PSQ + lane] = v;
-                Pm[lane * PSQ + kd] = v;
+                Pm[kd * PSQ + lane] = vrow;
+                Pm[lane * PSQ + kd] = vrow;
               }
               if (lane == kd) {
-                Pm[kd * PSQ + kd] = Pm[last * PSQ + last];
+                Pm[kd * PSQ + kd] = vdiag;
                 spk = lspk;
                 sact = lsact;
                 u = lu;
@@ -284,6 +353,9 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
 #pragma unroll
               for (int e = 0; e < NPL; e++) KN[kd * NS + lane + 32 * e] = KN[last * NS + lane + 32 * e];
             }
+            // row and column `last` leave the matrix: zero them so that the padded loops keep reading zeros
+            Pm[last * PSQ + lane] = 0.0;
+            if (lane < qcap) Pm[lane * PSQ + last] = 0.0;
             if (lane == last) { sact = -1; u = 0.0; }
           }
           q--;
@@ -291,6 +363,11 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
           __syncwarp();
         }
       }
+    }
+    if (P.phase_cycles && lane == 0) {
+      const long long now = clock64();
+      atomicAdd(P.phase_cycles + CMPC_PH_QP, (unsigned long long)(now - tclk));  // active-set iterations
+      tclk = now;
     }
     if (status == CMPC_ST_WSOVERFLOW && P.overflow_list) {
       if (lane == 0) {  // left for the any-capacity launch
@@ -305,28 +382,28 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
 #pragma unroll
     for (int e = 0; e < NPL; e++) kns[lane + 32 * e] = x[e];
     __syncwarp();
-    if (P.forces) {
-      double* out = P.forces + (size_t)inst * 12 * h;
-      for (int idx = lane; idx < 12 * h; idx += 32) {
-        const int k = idx / 3, comp = idx - 3 * k;
-        const int j = fsinv[k];
-        out[idx] = (j >= 0 && have_x) ? kns[3 * j + comp] : 0.0;
+    for (int k = lane; k < 4 * h; k += 32) {  // one foot-step per lane
+      const int j = fsinv[k];
+      double fx = 0.0, fy = 0.0, fz = 0.0;
+      if (j >= 0 && have_x) { fx = kns[3 * j]; fy = kns[3 * j + 1]; fz = kns[3 * j + 2]; }
+      if (P.forces) {
+        double* out = P.forces + (size_t)inst * 12 * h + 3 * k;
+        out[0] = fx; out[1] = fy; out[2] = fz;
       }
-    }
-    if (P.active) {
-      signed char* out = P.active + (size_t)inst * 20 * h;
-      for (int idx = lane; idx < 20 * h; idx += 32) {
-        const int k = idx / 5, t = idx - 5 * k;
-        const int j = fsinv[k];
-        signed char a = 0;
+      if (P.active) {
+        signed char* out = P.active + (size_t)inst * 20 * h + 5 * k;
+        signed char a[5] = {0, 0, 0, 0, 0};
         if (j >= 0 && have_x) {
-          const double fx = kns[3 * j], fy = kns[3 * j + 1], fz = kns[3 * j + 2];
-          const double row = (t == 0) ? fx * mu_inv + fz : (t == 1) ? -fx * mu_inv + fz : (t == 2) ? fy * mu_inv + fz
-                           : (t == 3) ? -fy * mu_inv + fz : fz;
-          if (row <= P.tol_active) a = -1;
-          if (t == 4 && row >= (double)gv[j] * P.f_max - P.tol_active) a = 1;
+          const double ub = (double)gv[j] * P.f_max;
+          a[0] = (fx * mu_inv + fz <= P.tol_active) ? -1 : 0;
+          a[1] = (-fx * mu_inv + fz <= P.tol_active) ? -1 : 0;
+          a[2] = (fy * mu_inv + fz <= P.tol_active) ? -1 : 0;
+          a[3] = (-fy * mu_inv + fz <= P.tol_active) ? -1 : 0;
+          a[4] = (fz <= P.tol_active) ? -1 : 0;
+          if (fz >= ub - P.tol_active) a[4] = 1;
         }
-        out[idx] = a;
+#pragma unroll
+        for (int t = 0; t < 5; t++) out[t] = a[t];
       }
     }
     {
@@ -348,6 +425,11 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
       }
     }
     __syncwarp();
+    if (P.phase_cycles && lane == 0) {
+      const long long now = clock64();
+      atomicAdd(P.phase_cycles + CMPC_PH_OUT, (unsigned long long)(now - tclk));  // outputs
+      tclk = now;
+    }
   }
   if (lane == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops, (unsigned long long)flops_acc);
 }

@@ -15,6 +15,28 @@
 #pragma once
 
 namespace {
+// Panel of block step S from the register tiles: rows 8S..8S+7 of the symmetric matrix, tiles (S, J <= S) as
+// they are and tiles (I > S, S) transposed, D - I in the diagonal block; row 63 (the border) is published as 0.
+template <int S>
+__device__ __forceinline__ void publish_panel(const double (&t)[36][2], double* pan, int r, int q) {
+  constexpr int PS = MMA_PS;
+#pragma unroll
+  for (int J = 0; J <= S; J++) {
+    double v0 = t[tix(S, J)][0], v1 = t[tix(S, J)][1];
+    if (J == S) {
+      if (r == 2 * q) v0 -= 1.0;
+      if (r == 2 * q + 1) v1 -= 1.0;
+    }
+    if (S == 7 && r == 7) { v0 = 0.0; v1 = 0.0; }
+    *reinterpret_cast<double2*>(pan + r * PS + 8 * J + 2 * q) = make_double2(v0, v1);
+  }
+#pragma unroll
+  for (int I = S + 1; I < 8; I++) {
+    pan[(2 * q) * PS + 8 * I + r] = t[tix(I, S)][0];
+    pan[(2 * q + 1) * PS + 8 * I + r] = t[tix(I, S)][1];
+  }
+}
+
 constexpr int INV_WPC = 4;  // independent warps (instances in flight) per CTA
 constexpr int INV_WARP_SMEM = 8 * (2 * 8 * MMA_PS + 64);
 }  // namespace
@@ -31,6 +53,15 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
   const int count = P.count;
   const int fo = q * PS + r;  // fragment offset: element (k = q, row/col = r)
 
+  long long tclk = 0;
+  const bool clk = P.phase_cycles != nullptr;
+  if (clk) tclk = clock64();
+#define INV_TICK(PH)                                                                    \
+  if (clk) {                                                                            \
+    const long long now_ = clock64();                                                   \
+    if (lane == 0) atomicAdd(P.phase_cycles + (PH), (unsigned long long)(now_ - tclk)); \
+    tclk = now_;                                                                        \
+  }
   while (true) {
     int inst = 0;
     if (lane == 0) inst = atomicAdd(P.sched, 1);
@@ -49,73 +80,85 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
       t[k][0] = v.x;
       t[k][1] = v.y;
     }
+    INV_TICK(CMPC_PH_LOAD)
+    // -D^-1 of the first diagonal tile; later ones are formed one step ahead, interleaved with the update DMMAs
+    {
+      double d0 = t[0][0], d1 = t[0][1];
+      warp_inv8_acc(d0, d1, r, q);
+      *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
+    }
 #pragma unroll 1
     for (int s = 0; s < nblk; s++) {
-      const bool excl = (s == 7);  // block 7 holds the border row 63: it is not a pivot
-      // 1. -D^-1 from the diagonal tile; publish the panel with D - I in the diagonal block
+      // 1. publish the panel (static tile indices per block step)
+      switch (s) {
+        case 0: publish_panel<0>(t, pan, r, q); break;
+        case 1: publish_panel<1>(t, pan, r, q); break;
+        case 2: publish_panel<2>(t, pan, r, q); break;
+        case 3: publish_panel<3>(t, pan, r, q); break;
+        case 4: publish_panel<4>(t, pan, r, q); break;
+        case 5: publish_panel<5>(t, pan, r, q); break;
+        case 6: publish_panel<6>(t, pan, r, q); break;
+        default: publish_panel<7>(t, pan, r, q); break;
+      }
+      __syncwarp();
+      INV_TICK(CMPC_PH_WAIT)
+      // 2. M = -D^-1 C: the two k-steps of a tile are issued eight DMMAs apart
       {
+        const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
+        double mt[8][2];
+#pragma unroll
+        for (int J = 0; J < 8; J++) {
+          mt[J][0] = 0.0;
+          mt[J][1] = 0.0;
+          dmma884(mt[J][0], mt[J][1], a0, pan[fo + 8 * J]);
+        }
+#pragma unroll
+        for (int J = 0; J < 8; J++) {
+          dmma884(mt[J][0], mt[J][1], a1, pan[fo + 4 * PS + 8 * J]);
+          *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(mt[J][0], mt[J][1]);
+        }
+      }
+      __syncwarp();
+      INV_TICK(CMPC_PH_ADAPT)
+      // 3. every tile (I, J) += C_I' M_J.  First the next diagonal tile on its own, so that its inversion (a serial
+      //    chain of shuffles and reciprocals) can be scheduled between the 72 independent DMMAs that follow.
+      {
+        const int sn = (s + 1 < 8) ? s + 1 : 7;
         double d0 = 0.0, d1 = 0.0;
 #pragma unroll
         for (int I = 0; I < 8; I++)
-          if (I == s) { d0 = t[tix(I, I)][0]; d1 = t[tix(I, I)][1]; }
-        if (excl) {
+          if (I == sn) { d0 = t[tix(I, I)][0]; d1 = t[tix(I, I)][1]; }
+        {
+          const double pn0 = pan[fo + 8 * sn], pn1 = pan[fo + 4 * PS + 8 * sn];
+          const double mn0 = mm[fo + 8 * sn], mn1 = mm[fo + 4 * PS + 8 * sn];
+          dmma884(d0, d1, pn0, mn0);
+          dmma884(d0, d1, pn1, mn1);
+        }
+        if (sn == 7) {  // the border row / column of block 7 is excluded from the pivot block
           if (r == 7) { d0 = 0.0; d1 = (q == 3) ? 1.0 : 0.0; }
           else if (q == 3) d1 = 0.0;
         }
-        warp_inv8_acc(d0, d1, r, q);
-        *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
-      }
-#pragma unroll
-      for (int I = 0; I < 8; I++)
-#pragma unroll
-        for (int J = 0; J <= I; J++) {
-          if (I == s) {
-            double v0 = t[tix(I, J)][0], v1 = t[tix(I, J)][1];
-            if (J == I) {
-              if (r == 2 * q) v0 -= 1.0;
-              if (r == 2 * q + 1) v1 -= 1.0;
-            }
-            if (I == 7 && r == 7) { v0 = 0.0; v1 = 0.0; }
-            *reinterpret_cast<double2*>(pan + r * PS + 8 * J + 2 * q) = make_double2(v0, v1);
-          } else if (J == s) {
-            pan[(2 * q) * PS + 8 * I + r] = t[tix(I, J)][0];
-            pan[(2 * q + 1) * PS + 8 * I + r] = t[tix(I, J)][1];
-          }
-        }
-      __syncwarp();
-      // 2. M = -D^-1 C
-      {
-        const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
-#pragma unroll
-        for (int J = 0; J < 8; J++) {
-          double m0 = 0.0, m1 = 0.0;
-          dmma884(m0, m1, a0, pan[fo + 8 * J]);
-          dmma884(m0, m1, a1, pan[fo + 4 * PS + 8 * J]);
-          *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(m0, m1);
-        }
-      }
-      __syncwarp();
-      // 3. every tile (I, J) += C_I' M_J
-      {
-        double mf[8][2];
+        double mf[8][2], pf[8][2];
 #pragma unroll
         for (int J = 0; J < 8; J++) {
           mf[J][0] = mm[fo + 8 * J];
           mf[J][1] = mm[fo + 4 * PS + 8 * J];
+          pf[J][0] = pan[fo + 8 * J];
+          pf[J][1] = pan[fo + 4 * PS + 8 * J];
         }
 #pragma unroll
-        for (int I = 0; I < 8; I++) {
-          if (I < nblk || I == 7) {
-            const double p0 = pan[fo + 8 * I], p1 = pan[fo + 4 * PS + 8 * I];
+        for (int I = 0; I < 8; I++)
 #pragma unroll
-            for (int J = 0; J <= I; J++) {
-              dmma884(t[tix(I, J)][0], t[tix(I, J)][1], p0, mf[J][0]);
-              dmma884(t[tix(I, J)][0], t[tix(I, J)][1], p1, mf[J][1]);
-            }
-          }
-        }
+          for (int J = 0; J <= I; J++) dmma884(t[tix(I, J)][0], t[tix(I, J)][1], pf[I][0], mf[J][0]);
+        warp_inv8_acc(d0, d1, r, q);
+#pragma unroll
+        for (int I = 0; I < 8; I++)
+#pragma unroll
+          for (int J = 0; J <= I; J++) dmma884(t[tix(I, J)][0], t[tix(I, J)][1], pf[I][1], mf[J][1]);
+        __syncwarp();  // every lane is done with dv, pan and mm of this step
+        *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
       }
-      __syncwarp();  // the next publish overwrites pan and dv
+      INV_TICK(CMPC_PH_SWEEP)
     }
     // K_ij = -(A_ij - 2 d_ij) scale in place; x0 = -scale A[63][:]
 #pragma unroll
@@ -134,5 +177,7 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
           if (j + 1 < n) xo[j + 1] = -scale * a1;
         }
       }
+    INV_TICK(CMPC_PH_LOAD)
   }
+#undef INV_TICK
 }

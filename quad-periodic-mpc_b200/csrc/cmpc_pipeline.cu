@@ -163,24 +163,25 @@ int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
 namespace {
 template <int NPL, int MPL>
 int launch_fast_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cmpc_dual_fast_kernel<4, NPL, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(cmpc_dual_fast_kernel<1, NPL, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  cmpc_dual_fast_kernel<4, NPL, MPL><<<grid, 128, smem, st>>>(P);
+  cmpc_dual_fast_kernel<1, NPL, MPL><<<grid, 32, smem, st>>>(P);
   return (int)cudaGetLastError();
 }
 template <int NPL, int MPL>
 int occ_fast_t(size_t smem) {
   int nb = 0;
-  if (cudaFuncSetAttribute(cmpc_dual_fast_kernel<4, NPL, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (cudaFuncSetAttribute(cmpc_dual_fast_kernel<1, NPL, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_dual_fast_kernel<4, NPL, MPL>, 128, smem) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_dual_fast_kernel<1, NPL, MPL>, 32, smem) != cudaSuccess) return -1;
   return nb;
 }
 }  // namespace
 
-size_t cmpc_dual_fast_smem_bytes(int nmax, int qcap) { return 4 * (size_t)make_fcarve(nmax <= 64 ? 2 : 4, qcap).total; }
+size_t cmpc_dual_fast_smem_bytes(int nmax, int qcap) { return (size_t)make_fcarve(nmax <= 64 ? 2 : 4, qcap).total; }
 int cmpc_dual_fast_max_ctas_per_sm(int nmax, size_t smem) { return nmax <= 64 ? occ_fast_t<2, 4>(smem) : occ_fast_t<4, 7>(smem); }
 int cmpc_launch_dual_fast(const CmpcParams& P, int grid, void* stream) {
   const size_t smem = cmpc_dual_fast_smem_bytes(P.nmax, P.qcap);
   return P.nmax <= 64 ? launch_fast_t<2, 4>(P, grid, smem, (cudaStream_t)stream) : launch_fast_t<4, 7>(P, grid, smem, (cudaStream_t)stream);
 }
+

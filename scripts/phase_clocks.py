@@ -20,6 +20,7 @@ def run(B, h=10, gaits=("trot",), spread=1.0, nseg=None, launches=4, tag=""):
         b.solve(); b.sync(); ms.append(b.last_solve_ms())
     cyc = b.phase_cycles()
     res = b.download()
+    print("   iterations histogram:", np.bincount(np.minimum(res["iterations"], 40)).tolist())
     tot = sum(cyc.values())
     print("%s B=%d h=%d: kernel %.3f ms plain, %.3f ms with clocks; iters mean %.1f max %d; cycles/instance %.0f"
           % (tag, B, h, min(plain), min(ms), res["iterations"].mean(), res["iterations"].max(), tot / (B * launches)))
