@@ -99,6 +99,13 @@ struct cmpc_batch {
   cudaStream_t stream[2] = {nullptr, nullptr};  // [0] is "the batch stream"; [1] only carries pipelined chunks
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, mark0 = nullptr, mark1 = nullptr;
   cudaEvent_t chunk_done[kMaxChunks] = {};
+  // successive solve_range calls alternate between the two streams so that the latency-bound tail of one
+  // batch overlaps the next batch's kernels; these events carry the cross-stream ordering
+  cudaEvent_t join_ev = nullptr;      // scratch: "stream 1 has reached this point"
+  cudaEvent_t fork_ev = nullptr;      // scratch: "stream 0 has reached this point"
+  unsigned rr = 0;                    // round-robin counter of solve_range
+  bool serial = false;                // CMPC_SERIAL=1: keep every solve on the batch stream
+  bool s1_dirty = false;              // stream 1 carries work that stream 0 has not waited for yet
   // problem setup
   bool is_setup = false;
   int h = 0;
@@ -193,6 +200,21 @@ int check_inputs(const cmpc_batch* b, int count, const cmpc_inputs* in, const ch
   if (!in->p || !in->v || !in->q || !in->w || !in->r || !in->weights || !in->traj || !in->alpha || !in->gait ||
       !in->x_drag)
     return fail_arg("null input array");
+  return CMPC_OK;
+}
+
+// stream 0 ("the batch stream") waits for everything enqueued on stream 1 so far
+int join_streams(cmpc_batch* b) {
+  if (!b->s1_dirty) return CMPC_OK;
+  CK(cudaEventRecord(b->join_ev, b->stream[1]));
+  CK(cudaStreamWaitEvent(b->stream[0], b->join_ev, 0));
+  b->s1_dirty = false;
+  return CMPC_OK;
+}
+// stream 1 waits for everything enqueued on stream 0 so far (uploads, marks)
+int fork_streams(cmpc_batch* b) {
+  CK(cudaEventRecord(b->fork_ev, b->stream[0]));
+  CK(cudaStreamWaitEvent(b->stream[1], b->fork_ev, 0));
   return CMPC_OK;
 }
 
@@ -481,6 +503,8 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaEventCreate(&b->mark0));
   CK(cudaEventCreate(&b->mark1));
   for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->chunk_done[i], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&b->join_ev, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming));
   const size_t cap = (size_t)capacity;
   const int hm = CMPC_MAX_HORIZON;
   const size_t rec_max = (size_t)cmpc_rec_stride(hm);
@@ -502,6 +526,7 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMallocHost(&b->h_active, cap * 20 * hm));
   CK(cudaMallocHost(&b->h_flops, sizeof(unsigned long long)));
   *b->h_flops = 0;
+  if (const char* e = std::getenv("CMPC_SERIAL")) b->serial = std::atoi(e) != 0;
   *out = b;
   return CMPC_OK;
 }
@@ -520,6 +545,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFreeHost(b->h_active); cudaFreeHost(b->h_flops);
   cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->mark0); cudaEventDestroy(b->mark1);
   for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->chunk_done[i]);
+  cudaEventDestroy(b->join_ev); cudaEventDestroy(b->fork_ev);
   for (int i = 0; i < 2; i++) cudaStreamDestroy(b->stream[i]);
   delete b;
 }
@@ -562,6 +588,7 @@ int cmpc_batch_upload(cmpc_batch* b, int count, const cmpc_inputs* in) {
   CK(cudaSetDevice(b->device));
   b->max_contact = pack_records(b, in, 0, count);
   b->count = count;
+  { int rcj = join_streams(b); if (rcj) return rcj; }  // solves in flight on stream 1 still read the records
   if (count > 0)
     CK(cudaMemcpyAsync(b->d_rec, b->h_rec, (size_t)count * b->rec_stride, cudaMemcpyHostToDevice, b->stream[0]));
   return CMPC_OK;
@@ -586,10 +613,17 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
   if (!b->is_setup) { g_err = "cmpc_batch_solve: call cmpc_batch_setup first"; return CMPC_E_STATE; }
   if (first < 0 || count < 0 || first + count > b->count) return fail_arg("cmpc_batch_solve_range: range outside the uploaded instances");
   CK(cudaSetDevice(b->device));
-  CK(cudaEventRecord(b->ev0, b->stream[0]));
-  int rc = launch_range(b, first, count, b->max_contact, 0);
+  int si = 0;
+  if (!b->serial) si = (int)(b->rr++ & 1u);
+  if (si == 1) {
+    int rcf = fork_streams(b);  // after the uploads / marks already enqueued on the batch stream
+    if (rcf) return rcf;
+    b->s1_dirty = true;
+  }
+  CK(cudaEventRecord(b->ev0, b->stream[si]));
+  int rc = launch_range(b, first, count, b->max_contact, si);
   if (rc) return rc;
-  CK(cudaEventRecord(b->ev1, b->stream[0]));
+  CK(cudaEventRecord(b->ev1, b->stream[si]));
   b->timed = true;
   return CMPC_OK;
 }
@@ -598,6 +632,7 @@ int cmpc_batch_sync(cmpc_batch* b) {
   if (!b) return fail_arg("cmpc_batch_sync: null batch");
   CK(cudaSetDevice(b->device));
   for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+  b->s1_dirty = false;
   return CMPC_OK;
 }
 
@@ -628,6 +663,7 @@ int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out) {
   if (!b || !out) return fail_arg("cmpc_batch_download: null argument");
   CK(cudaSetDevice(b->device));
   CK(cudaStreamSynchronize(b->stream[1]));
+  b->s1_dirty = false;
   int rc = enqueue_d2h(b, out, 0, b->count, b->stream[0]);
   if (rc) return rc;
   CK(cudaStreamSynchronize(b->stream[0]));
@@ -649,6 +685,7 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
   nchunks = std::max(1, std::min(nchunks, kMaxChunks));
   const int per = (count + nchunks - 1) / nchunks;
   CK(cudaStreamSynchronize(b->stream[1]));
+  b->s1_dirty = false;
   CK(cudaEventRecord(b->ev0, b->stream[0]));
   b->count = count;
   int maxc_all = 0, used = 0;
@@ -684,6 +721,8 @@ int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows
                                   const float* sim_time, int mode) {
   if (!b) return fail_arg("cmpc_batch_upload_disturbance: null batch");
   CK(cudaSetDevice(b->device));
+  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));  // solves in flight read the old windows
+  b->s1_dirty = false;
   if (mode < 0 || (!windows_t && mode != 2)) {
     b->adapt_mode = -1;
     return CMPC_OK;
@@ -754,7 +793,9 @@ int cmpc_batch_last_solve_ms(cmpc_batch* b, float* ms) {
 int cmpc_batch_mark(cmpc_batch* b, int which) {
   if (!b || (which != 0 && which != 1)) return fail_arg("cmpc_batch_mark: bad arguments");
   CK(cudaSetDevice(b->device));
+  { int rcj = join_streams(b); if (rcj) return rcj; }
   CK(cudaEventRecord(which ? b->mark1 : b->mark0, b->stream[0]));
+  { int rcf = fork_streams(b); if (rcf) return rcf; }  // stream 1 starts nothing before the mark
   return CMPC_OK;
 }
 
@@ -769,6 +810,7 @@ int cmpc_batch_marked_ms(cmpc_batch* b, float* ms) {
 int cmpc_batch_reset_counters(cmpc_batch* b) {
   if (!b) return fail_arg("cmpc_batch_reset_counters: null batch");
   CK(cudaSetDevice(b->device));
+  { int rcj = join_streams(b); if (rcj) return rcj; }
   CK(cudaMemsetAsync(b->d_flops, 0, sizeof(unsigned long long), b->stream[0]));
   b->launches = 0;
   return CMPC_OK;
