@@ -13,8 +13,10 @@ path shards with no collective (weak scaling: every rank solves its own 4096-ins
              records.  CUDA events on the engine's stream, max over ranks.
   e2e        the same metric through cmpc_batch_solve_host() with HOST buffers: pack into pinned
              records, H2D, kernel, D2H of forces/status, every step inside the timed region.
-  roofline   the solve kernel against the measured FP64 FMA peak (it is FP64-pipe / latency
-             bound, not HBM bound; the HBM fraction is reported beside it).
+  roofline   the FP64 tensor-core inversion kernel (K = H^-1 by blocked sweeps of DMMA m8n8k4, ~90 % of the
+             step's flops) against the measured FP64 peak of the device; every kernel class of the step
+             (assembly, inversion, dual active set) is listed beside it with its own time, flops and
+             fraction, and so is the whole step.  The path is not HBM bound; the HBM fraction is reported.
   cpu_baseline / --impl reference
              the reference's CPU path: restated fp32 condensation + the reference's real
              qpOASES 3.2.0 (oracle/_ref), one solve per thread on all host cores.
@@ -37,6 +39,8 @@ import numpy as np  # noqa: E402
 HORIZON, DT, BATCH = 10, 0.03, 4096
 METRIC = "cmpc_qp_solves_per_sec_h10_batched"
 L2_BYTES = 126 * 1024 * 1024
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures (profiles/)
+NCU_TRAFFIC = {"assemble": None, "invert": None, "dual": None, "fused": None}
 
 
 def shard_bounds(total, rank, world):
@@ -204,23 +208,45 @@ def run_b200(args, rank, world, local_rank):
     h2d = BATCH * rec_bytes
     d2h = BATCH * (12 * h * 8 + 8 + 4 + 4) + 8
 
+    # ---- per-kernel-class device time: serial solves (CUDA events between the classes) on cold ring batches ----
+    kflops = b.kernel_flops()                     # algorithmic flops of the timed region, per kernel class
+    prof_n = min(8, ring)
+    kms = {k: 0.0 for k in engine.Batch.KERNELS}
+    for i in range(prof_n):
+        t = b.profile_range(((i + 3) % ring) * BATCH, BATCH)
+        for k in kms:
+            kms[k] += t[k] / prof_n
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         fp64 = engine.measure_fp64_peak(local_rank)
-        kms = region_ms / args.steps
-        fl = flops_total / args.steps
-        achieved = fl / (kms * 1e-3) / 1e12
+        step_ms = region_ms / args.steps
+        names = {"assemble": "cmpc_assemble_mma_kernel", "invert": "cmpc_invert_mma_kernel",
+                 "dual": "cmpc_dual_fast_kernel (+ cmpc_dual_kernel for overflowed working sets)", "fused": "cmpc_solve_kernel"}
+        bounds = {"assemble": "latency / issue (FP64 FMA + shared memory)", "invert": "tensor (FP64 DMMA)",
+                  "dual": "latency (dependent chain per active-set iteration)", "fused": "latency"}
+        kernels = []
+        for k in engine.Batch.KERNELS:
+            if kms[k] <= 0.0:
+                continue
+            fl = kflops[k] / args.steps
+            ach = fl / (kms[k] * 1e-3) / 1e12
+            kernels.append({"kernel": names[k], "ms": kms[k], "flops_per_launch": fl, "achieved_tflops": ach,
+                            "frac_of_fp64_peak": ach / fp64 if fp64 else None, "bound": bounds[k]})
+        fl_step = sum(kflops.values()) / args.steps
+        dom = "invert" if kms["invert"] > 0 else max(kms, key=kms.get)
+        fl_dom = kflops[dom] / args.steps
+        achieved = fl_dom / (kms[dom] * 1e-3) / 1e12
         hbm_bytes = BATCH * (rec_bytes + out_bytes)
-        hbm_ach = hbm_bytes / (kms * 1e-3) / 1e9
+        hbm_ach = hbm_bytes / (step_ms * 1e-3) / 1e9
         cpu = None
-        if world == 1 or True:
-            try:
-                c = cpu_reference_run(3, 1, 512)
-                cpu = {"value": c["value"], "unit": "solves/s", "cores": c["threads"], "kind": "reference",
-                       "sample": "3 x 512 instances of the bench workload, qpOASES 3.2.0 built from the reference's "
-                                 "sources + restated fp32 condensation, one solve per thread on all host cores"}
-            except Exception as e:  # the checker library did not travel
-                cpu = {"value": None, "unit": "solves/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        try:
+            c = cpu_reference_run(3, 1, 512)
+            cpu = {"value": c["value"], "unit": "solves/s", "cores": c["threads"], "kind": "reference",
+                   "sample": "3 x 512 instances of the bench workload, qpOASES 3.2.0 built from the reference's "
+                             "sources + restated fp32 condensation, one solve per thread on all host cores"}
+        except Exception as e:  # the checker library did not travel
+            cpu = {"value": None, "unit": "solves/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
         line = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True,
@@ -230,12 +256,26 @@ def run_b200(args, rank, world, local_rank):
                        "batch_per_gpu": BATCH, "horizon": h, "ring_batches": ring,
                        "l2": "inputs rotate through a ring of %d distinct resident batches (%.0f MB > L2)"
                              % (ring, total * (rec_bytes + out_bytes) / 1e6),
-                       "sharding": "independent instances, no data-path collective"},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64, "unit": "TFLOP/s",
-                         "frac": achieved / fp64 if fp64 else None, "traffic": None,
-                         "kernel": "cmpc_solve_kernel", "kernel_ms": kms,
-                         "peak_source": "DFMA microbenchmark run in this process (cmpc_measure_fp64_peak)",
-                         "flops_per_launch": fl,
+                       "sharding": "independent instances, no data-path collective",
+                       "pipelining": "successive steps alternate between two CUDA streams of the engine (a step is "
+                                     "three kernels: assembly, FP64-tensor inversion, dual active set)"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64, "unit": "TFLOP/s",
+                         "frac": achieved / fp64 if fp64 else None,
+                         "traffic": NCU_TRAFFIC.get(dom),
+                         "kernel": names[dom], "kernel_ms": kms[dom],
+                         "peak_source": "FP64 FMA microbenchmark run in this process (cmpc_measure_fp64_peak); FP64 DMMA "
+                                        "m8n8k4 measures the same rate on B200 (scripts/ubench/fp64_ubench.cu); "
+                                        "MEASURED_PEAKS.json holds no FP64 figure",
+                         "flops_per_launch": fl_dom,
+                         "flops_note": "algorithmic: n^3 + 2 n^2 per instance (symmetric inverse + x0 = -K g), n = 60; "
+                                       "the kernel executes 1.7x that (padding to 64, full diagonal tiles, D^-1 C)",
+                         "timing": "CUDA events around each kernel class of %d serial solves of cold ring batches" % prof_n,
+                         "traffic_note": "dram bytes of one ncu --set full launch (profiles/); ncu flushes L2 between "
+                                         "kernels, in the pipeline the tiles written by the assembly kernel are L2 hits",
+                         "step": {"flops_per_step": fl_step, "achieved": fl_step / (step_ms * 1e-3) / 1e12,
+                                  "frac": (fl_step / (step_ms * 1e-3) / 1e12) / fp64 if fp64 else None,
+                                  "ms": step_ms, "serial_ms": sum(kms.values())},
+                         "kernels": kernels,
                          "hbm": {"achieved": hbm_ach, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm_ach / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                                  "bytes_per_launch": hbm_bytes, "peak_source": peak_kind}},

@@ -162,6 +162,12 @@ int cmpc_batch_reset_counters(cmpc_batch* b);
 /* Algorithmic FP64 flop count since the last reset, accumulated by the kernel from its own loop counters. */
 int cmpc_batch_last_flops(cmpc_batch* b, double* flops);
 
+/* Per kernel class (0 assembly / condensation, 1 FP64-tensor inversion, 2 dual active set, 3 fused single-kernel
+ * path): algorithmic flops since the last reset, and the device time of ONE solve of [first, first+count) on the
+ * batch stream with a CUDA event between the classes (ms[i] stays 0 for a class the range does not use). */
+int cmpc_batch_kernel_flops(cmpc_batch* b, double flops[4]);
+int cmpc_batch_profile_range(cmpc_batch* b, int first, int count, float ms[4]);
+
 /* Phase clocks (profiling aid): when enabled, thread 0 of every CTA charges SM cycles to the kernel's
  * phases (record wait, estimator, condensation, H assembly, tile load, sweep, K store, active set,
  * outputs); cycles[i] is the sum over CTAs since enabling.  Off by default. */

@@ -52,6 +52,8 @@ def lib():
         L.cmpc_batch_mark.argtypes = [C.c_void_p, C.c_int]
         L.cmpc_batch_marked_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.cmpc_batch_reset_counters.argtypes = [C.c_void_p]
+        L.cmpc_batch_kernel_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.cmpc_batch_profile_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.cmpc_batch_enable_phase_clocks.argtypes = [C.c_void_p, C.c_int]
         L.cmpc_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
         L.cmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -210,6 +212,18 @@ class Batch:
         f = C.c_double()
         _check(lib().cmpc_batch_last_flops(self._h, C.byref(f)), "cmpc_batch_last_flops")
         return f.value
+
+    KERNELS = ("assemble", "invert", "dual", "fused")
+
+    def kernel_flops(self):
+        arr = (C.c_double * 4)()
+        _check(lib().cmpc_batch_kernel_flops(self._h, arr), "cmpc_batch_kernel_flops")
+        return dict(zip(self.KERNELS, [float(x) for x in arr]))
+
+    def profile_range(self, first, count):
+        arr = (C.c_float * 4)()
+        _check(lib().cmpc_batch_profile_range(self._h, first, count, arr), "cmpc_batch_profile_range")
+        return dict(zip(self.KERNELS, [float(x) for x in arr]))
 
     PHASES = ("wait", "adapt", "prep", "hess", "load", "sweep", "store", "qp", "out")
 

@@ -103,6 +103,9 @@ struct cmpc_batch {
   // batch overlaps the next batch's kernels; these events carry the cross-stream ordering
   cudaEvent_t join_ev = nullptr;      // scratch: "stream 1 has reached this point"
   cudaEvent_t fork_ev = nullptr;      // scratch: "stream 0 has reached this point"
+  cudaEvent_t prof_ev[CMPC_K_COUNT + 1] = {};  // cmpc_batch_profile_range: events between the kernel classes
+  float prof_ms[CMPC_K_COUNT] = {};
+  bool profiling = false;
   unsigned rr = 0;                    // round-robin counter of solve_range
   bool serial = false;                // CMPC_SERIAL=1: keep every solve on the batch stream
   bool s1_dirty = false;              // stream 1 carries work that stream 0 has not waited for yet
@@ -294,6 +297,20 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     return CMPC_E_NODEVICE;
   }
   const CmpcParams base = P;
+  // cmpc_batch_profile_range: CUDA events between the kernel classes (the stream is drained per class)
+  auto prof_begin = [&]() -> int {
+    if (b->profiling) CK(cudaEventRecord(b->prof_ev[0], st));
+    return CMPC_OK;
+  };
+  auto prof_end = [&](int cls) -> int {
+    if (!b->profiling) return CMPC_OK;
+    CK(cudaEventRecord(b->prof_ev[1], st));
+    CK(cudaEventSynchronize(b->prof_ev[1]));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, b->prof_ev[0], b->prof_ev[1]));
+    b->prof_ms[cls] += t;
+    return CMPC_OK;
+  };
   for (int c = 0; c < nchunks; c++) {
     const int off = c * chunk, cnt = std::min(chunk, count - off);
     CmpcParams Q = base;
@@ -319,18 +336,23 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.count_ptr = nullptr;
     Q.sched = b->d_sched[si] + 4 * c;
     const int ipc = cmpc_condense_instances_per_cta(cshape);
+    if (int e = prof_begin()) return e;
     int rc = cmpc_launch_condense(Q, cshape, std::min((cnt + ipc - 1) / ipc, b->sm_count * per_sm1), st);
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_condense_kernel launch");
     b->launches++;
+    if (int e = prof_end(CMPC_K_ASSEMBLE)) return e;
     if (tiled) {  // the assembly kernel left H tiles: invert them in place on the FP64 tensor cores
       Q.sched = b->d_sched[si] + 4 * c + 3;
       const int ipc2 = cmpc_invert_instances_per_cta();
+      if (int e = prof_begin()) return e;
       rc = cmpc_launch_invert(Q, std::min((cnt + ipc2 - 1) / ipc2, b->sm_count * per_sm_inv), st);
       if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_invert_mma_kernel launch");
       b->launches++;
+      if (int e = prof_end(CMPC_K_INVERT)) return e;
     }
     Q.sched = b->d_sched[si] + 4 * c + 1;
     Q.qcap = qcap1;
+    if (int e = prof_begin()) return e;
     if (qcap1 < nmax) {
       Q.overflow_list = b->d_overflow[si];
       Q.overflow_count = b->d_overflow[si] + b->capacity;
@@ -352,6 +374,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel (full capacity) launch");
       b->launches++;
     }
+    if (int e = prof_end(CMPC_K_DUAL)) return e;
   }
   return CMPC_OK;
 }
@@ -458,9 +481,17 @@ int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
     } else {
       P.gws = nullptr;
     }
+    if (b->profiling) CK(cudaEventRecord(b->prof_ev[0], st));
     int rc = cmpc_launch_solve(P, shape, grid, st);
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_solve_kernel launch");
     b->launches++;
+    if (b->profiling) {
+      CK(cudaEventRecord(b->prof_ev[1], st));
+      CK(cudaEventSynchronize(b->prof_ev[1]));
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, b->prof_ev[0], b->prof_ev[1]));
+      b->prof_ms[CMPC_K_FUSED] += t;
+    }
   }
   return CMPC_OK;
 }
@@ -517,15 +548,15 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMalloc(&b->d_iters, sizeof(int) * cap));
   CK(cudaMalloc(&b->d_active, cap * 20 * hm));
   for (int i = 0; i < 2; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
-  CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long)));
-  CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long)));
+  CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long) * CMPC_K_COUNT));
+  CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMallocHost(&b->h_forces, sizeof(double) * cap * 12 * hm));
   CK(cudaMallocHost(&b->h_obj, sizeof(double) * cap));
   CK(cudaMallocHost(&b->h_status, sizeof(int) * cap));
   CK(cudaMallocHost(&b->h_iters, sizeof(int) * cap));
   CK(cudaMallocHost(&b->h_active, cap * 20 * hm));
-  CK(cudaMallocHost(&b->h_flops, sizeof(unsigned long long)));
-  *b->h_flops = 0;
+  CK(cudaMallocHost(&b->h_flops, sizeof(unsigned long long) * CMPC_K_COUNT));
+  for (int i = 0; i < CMPC_K_COUNT; i++) b->h_flops[i] = 0;
   if (const char* e = std::getenv("CMPC_SERIAL")) b->serial = std::atoi(e) != 0;
   *out = b;
   return CMPC_OK;
@@ -545,6 +576,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFreeHost(b->h_active); cudaFreeHost(b->h_flops);
   cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->mark0); cudaEventDestroy(b->mark1);
   for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->chunk_done[i]);
+  for (int i = 0; i < CMPC_K_COUNT + 1; i++) if (b->prof_ev[i]) cudaEventDestroy(b->prof_ev[i]);
   cudaEventDestroy(b->join_ev); cudaEventDestroy(b->fork_ev);
   for (int i = 0; i < 2; i++) cudaStreamDestroy(b->stream[i]);
   delete b;
@@ -811,7 +843,7 @@ int cmpc_batch_reset_counters(cmpc_batch* b) {
   if (!b) return fail_arg("cmpc_batch_reset_counters: null batch");
   CK(cudaSetDevice(b->device));
   { int rcj = join_streams(b); if (rcj) return rcj; }
-  CK(cudaMemsetAsync(b->d_flops, 0, sizeof(unsigned long long), b->stream[0]));
+  CK(cudaMemsetAsync(b->d_flops, 0, sizeof(unsigned long long) * CMPC_K_COUNT, b->stream[0]));
   b->launches = 0;
   return CMPC_OK;
 }
@@ -826,9 +858,40 @@ int cmpc_batch_last_flops(cmpc_batch* b, double* flops) {
   if (!b || !flops) return fail_arg("cmpc_batch_last_flops: null argument");
   CK(cudaSetDevice(b->device));
   CK(cudaStreamSynchronize(b->stream[1]));
-  CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream[0]));
+  b->s1_dirty = false;
+  CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long) * CMPC_K_COUNT, cudaMemcpyDeviceToHost, b->stream[0]));
   CK(cudaStreamSynchronize(b->stream[0]));
-  *flops = (double)*b->h_flops;
+  *flops = 0.0;
+  for (int i = 0; i < CMPC_K_COUNT; i++) *flops += (double)b->h_flops[i];
+  return CMPC_OK;
+}
+
+int cmpc_batch_kernel_flops(cmpc_batch* b, double flops[4]) {
+  if (!b || !flops) return fail_arg("cmpc_batch_kernel_flops: null argument");
+  double total = 0.0;
+  int rc = cmpc_batch_last_flops(b, &total);
+  if (rc) return rc;
+  for (int i = 0; i < CMPC_K_COUNT; i++) flops[i] = (double)b->h_flops[i];
+  return CMPC_OK;
+}
+
+// One solve of [first, first+count) on the batch stream with a CUDA event between the kernel classes.
+int cmpc_batch_profile_range(cmpc_batch* b, int first, int count, float ms[4]) {
+  if (!b || !ms) return fail_arg("cmpc_batch_profile_range: null argument");
+  if (!b->is_setup) { g_err = "cmpc_batch_profile_range: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  if (first < 0 || count < 0 || first + count > b->count) return fail_arg("cmpc_batch_profile_range: range outside the uploaded instances");
+  CK(cudaSetDevice(b->device));
+  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+  b->s1_dirty = false;
+  if (!b->prof_ev[0])
+    for (int i = 0; i < CMPC_K_COUNT + 1; i++) CK(cudaEventCreate(&b->prof_ev[i]));
+  for (int i = 0; i < CMPC_K_COUNT; i++) { ms[i] = 0.f; b->prof_ms[i] = 0.f; }
+  b->profiling = true;
+  int rc = launch_range(b, first, count, b->max_contact, 0);
+  b->profiling = false;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(b->stream[0]));
+  for (int i = 0; i < CMPC_K_COUNT; i++) ms[i] = b->prof_ms[i];
   return CMPC_OK;
 }
 

@@ -528,5 +528,5 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
     pc.tick(CMPC_PH_STORE);
     cur = redi[2 + (buf ^ 1)];
   }
-  if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops, (unsigned long long)flops_acc);
+  if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_ASSEMBLE, (unsigned long long)flops_acc);
 }

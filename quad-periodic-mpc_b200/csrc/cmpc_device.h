@@ -73,7 +73,7 @@ struct CmpcParams {
   int* status;                // [count]
   int* iterations;            // [count]
   signed char* active;        // [count][20h]
-  unsigned long long* flops;  // single counter, algorithmic flops
+  unsigned long long* flops;  // CMPC_K_COUNT counters of algorithmic flops, one per kernel class
   // periodic-disturbance estimator (adapt_mode >= 0)
   const double* twiddle;      // [400][2] cos, -sin of 2 pi m / 400
   const float* gk;            // CMPC_GK_TOTAL normalised Gaussian taps
@@ -95,6 +95,13 @@ struct CmpcParams {
   // optional phase clocks (profiling aid): CMPC_PH_COUNT counters of SM cycles summed over CTAs, thread 0 only
   unsigned long long* phase_cycles;
 };
+
+/* kernel classes (flop counters, per-kernel timing) */
+#define CMPC_K_ASSEMBLE 0 /* condensation: state, c2qp closed form, g, H (plus the DFMA sweep on the 64 < n <= 128 shapes) */
+#define CMPC_K_INVERT 1   /* K = H^-1, x0 = -K g on the FP64 tensor cores (n <= 63) */
+#define CMPC_K_DUAL 2     /* dual active-set iterations, outputs */
+#define CMPC_K_FUSED 3    /* single-kernel path (n > 128, or CMPC_PATH=fused) */
+#define CMPC_K_COUNT 4
 
 #define CMPC_PH_WAIT 0    /* record wait (mbarrier) */
 #define CMPC_PH_ADAPT 1   /* disturbance estimator */

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
   double* mm = pan + 8 * PS;
   double* dv = mm + 8 * PS;
   const int count = P.count;
+  double flops_acc = 0.0;  // algorithmic: n^3 for the symmetric inverse, 2 n^2 for x0 = -K g
   const int fo = q * PS + r;  // fragment offset: element (k = q, row/col = r)
 
   long long tclk = 0;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
     if (hdr[1] != CMPC_ST_SOLVED) continue;
     const int n = 3 * nc, nblk = (n + 7) >> 3;
     const double scale = slot[P.qws_goff + 2 * P.nmax];
+    flops_acc += (double)n * n * n + 2.0 * (double)n * n;
     double t[36][2];
 #pragma unroll
     for (int k = 0; k < 36; k++) {
@@ -180,4 +182,5 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
     INV_TICK(CMPC_PH_LOAD)
   }
 #undef INV_TICK
+  if (lane == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_INVERT, (unsigned long long)flops_acc);
 }

@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
     __syncthreads();  // record buffer and work arrays are reused by the next instance
     pc.tick(CMPC_PH_OUT);
   }
-  if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops, (unsigned long long)flops_acc);
+  if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_FUSED, (unsigned long long)flops_acc);
 }
 
 // ---------------------------------------------------------------------------
