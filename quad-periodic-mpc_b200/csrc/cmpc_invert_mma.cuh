@@ -1,22 +1,37 @@
 // Inversion kernel of the pipeline for reduced problems of up to 63 variables: K = H^-1 and x0 = -K g by a
-// blocked symmetric sweep on the FP64 tensor cores (DMMA m8n8k4), ONE WARP PER INSTANCE.
+// blocked symmetric sweep on the FP64 tensor cores (DMMA m8n8k4), ONE WARP PER INSTANCE, one warp per CTA.
 //
 // The assembly kernel (cmpc_condense_mma.cuh) left the scaled, bordered matrix [H g; g' .] of the instance as
 // its 36 lower-triangular 8 x 8 tiles in DMMA accumulator layout.  A warp loads them into registers
 // (72 doubles per lane), runs up to eight block steps and stores -(A - 2 diag) scale back in place:
 //   1. invert the diagonal tile (s, s) in registers (Gauss-Jordan over warp shuffles, serial chain of 8
 //      pivots) and publish the pivot rows as an 8 x 64 panel C in warp-private shared memory (tiles
-//      (s, J<=s) as they are, tiles (I>s, s) transposed: the matrix is symmetric), D - I in the diagonal block;
-//   2. M = -D^-1 C: 16 DMMAs;
-//   3. every tile (I, J) += C_I' M_J: 72 DMMAs, operands fetched once per tile row / column.
-// No block barrier anywhere: warps of a CTA work on different instances and hide each other's pivot
-// chains; the kernel is bound by the FP64 tensor pipe (88 DMMAs per step, 16 cycles each per SM quadrant).
+//      (s, J<=s) as they are, tiles (I>s, s) transposed: the matrix is symmetric), D - I in the diagonal
+//      block; tile indices are compile-time constants inside a switch over s;
+//   2. M = -D^-1 C: 16 DMMAs, the two k-steps of a tile eight DMMAs apart;
+//   3. every tile (I, J) += C_I' M_J: 72 independent DMMAs, the two k-steps of a tile 36 DMMAs apart.
+// No block barrier anywhere: warps work on different instances and hide each other's pivot chains.  Measured
+// (profiles/): the DMMA pipe is ~47 % busy at ten warps per SM; variants that form the next pivot-block
+// inverse one step ahead between the update DMMAs, or that split an instance over two warps to double the
+// warps per SM, measured the same or slower and were dropped.
 // Row 63 (the border, g) is never pivoted and ends as g' H^-1 (see cmpc_condense_mma.cuh).
 #pragma once
 
 namespace {
 // Panel of block step S from the register tiles: rows 8S..8S+7 of the symmetric matrix, tiles (S, J <= S) as
 // they are and tiles (I > S, S) transposed, D - I in the diagonal block; row 63 (the border) is published as 0.
+// -D^-1 of the diagonal tile of block step S (row / column 63, the border, excluded from the pivot block)
+template <int S>
+__device__ __forceinline__ void invert_diag(const double (&t)[36][2], double* dv, int r, int q) {
+  double d0 = t[tix(S, S)][0], d1 = t[tix(S, S)][1];
+  if (S == 7) {
+    if (r == 7) { d0 = 0.0; d1 = (q == 3) ? 1.0 : 0.0; }
+    else if (q == 3) d1 = 0.0;
+  }
+  warp_inv8_acc(d0, d1, r, q);
+  *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
+}
+
 template <int S>
 __device__ __forceinline__ void publish_panel(const double (&t)[36][2], double* pan, int r, int q) {
   constexpr int PS = MMA_PS;
@@ -37,12 +52,12 @@ __device__ __forceinline__ void publish_panel(const double (&t)[36][2], double* 
   }
 }
 
-constexpr int INV_WPC = 4;  // independent warps (instances in flight) per CTA
+constexpr int INV_WPC = 1;  // warps per CTA: one, so that the register file holds ten instances per SM
 constexpr int INV_WARP_SMEM = 8 * (2 * 8 * MMA_PS + 64);
 }  // namespace
 
-template <int MINB>
-__global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(const __grid_constant__ CmpcParams P) {
+template <int MINB /* register cap */>
+__global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mma_kernel(const __grid_constant__ CmpcParams P) {
   constexpr int PS = MMA_PS;
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -83,25 +98,21 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
       t[k][1] = v.y;
     }
     INV_TICK(CMPC_PH_LOAD)
-    // -D^-1 of the first diagonal tile; later ones are formed one step ahead, interleaved with the update DMMAs
-    {
-      double d0 = t[0][0], d1 = t[0][1];
-      warp_inv8_acc(d0, d1, r, q);
-      *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
-    }
 #pragma unroll 1
     for (int s = 0; s < nblk; s++) {
       // 1. publish the panel (static tile indices per block step)
+#define INV_HEAD(S) invert_diag<S>(t, dv, r, q); publish_panel<S>(t, pan, r, q);
       switch (s) {
-        case 0: publish_panel<0>(t, pan, r, q); break;
-        case 1: publish_panel<1>(t, pan, r, q); break;
-        case 2: publish_panel<2>(t, pan, r, q); break;
-        case 3: publish_panel<3>(t, pan, r, q); break;
-        case 4: publish_panel<4>(t, pan, r, q); break;
-        case 5: publish_panel<5>(t, pan, r, q); break;
-        case 6: publish_panel<6>(t, pan, r, q); break;
-        default: publish_panel<7>(t, pan, r, q); break;
+        case 0: INV_HEAD(0) break;
+        case 1: INV_HEAD(1) break;
+        case 2: INV_HEAD(2) break;
+        case 3: INV_HEAD(3) break;
+        case 4: INV_HEAD(4) break;
+        case 5: INV_HEAD(5) break;
+        case 6: INV_HEAD(6) break;
+        default: INV_HEAD(7) break;
       }
+#undef INV_HEAD
       __syncwarp();
       INV_TICK(CMPC_PH_WAIT)
       // 2. M = -D^-1 C: the two k-steps of a tile are issued eight DMMAs apart
@@ -122,24 +133,8 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
       }
       __syncwarp();
       INV_TICK(CMPC_PH_ADAPT)
-      // 3. every tile (I, J) += C_I' M_J.  First the next diagonal tile on its own, so that its inversion (a serial
-      //    chain of shuffles and reciprocals) can be scheduled between the 72 independent DMMAs that follow.
+      // 3. every tile (I, J) += C_I' M_J: 72 independent DMMAs, the two k-steps of a tile 36 DMMAs apart
       {
-        const int sn = (s + 1 < 8) ? s + 1 : 7;
-        double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-        for (int I = 0; I < 8; I++)
-          if (I == sn) { d0 = t[tix(I, I)][0]; d1 = t[tix(I, I)][1]; }
-        {
-          const double pn0 = pan[fo + 8 * sn], pn1 = pan[fo + 4 * PS + 8 * sn];
-          const double mn0 = mm[fo + 8 * sn], mn1 = mm[fo + 4 * PS + 8 * sn];
-          dmma884(d0, d1, pn0, mn0);
-          dmma884(d0, d1, pn1, mn1);
-        }
-        if (sn == 7) {  // the border row / column of block 7 is excluded from the pivot block
-          if (r == 7) { d0 = 0.0; d1 = (q == 3) ? 1.0 : 0.0; }
-          else if (q == 3) d1 = 0.0;
-        }
         double mf[8][2], pf[8][2];
 #pragma unroll
         for (int J = 0; J < 8; J++) {
@@ -152,13 +147,11 @@ __global__ void __launch_bounds__(32 * INV_WPC, MINB) cmpc_invert_mma_kernel(con
         for (int I = 0; I < 8; I++)
 #pragma unroll
           for (int J = 0; J <= I; J++) dmma884(t[tix(I, J)][0], t[tix(I, J)][1], pf[I][0], mf[J][0]);
-        warp_inv8_acc(d0, d1, r, q);
 #pragma unroll
         for (int I = 0; I < 8; I++)
 #pragma unroll
           for (int J = 0; J <= I; J++) dmma884(t[tix(I, J)][0], t[tix(I, J)][1], pf[I][1], mf[J][1]);
         __syncwarp();  // every lane is done with dv, pan and mm of this step
-        *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
       }
       INV_TICK(CMPC_PH_SWEEP)
     }

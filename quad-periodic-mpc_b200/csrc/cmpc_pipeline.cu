@@ -141,21 +141,20 @@ int cmpc_launch_dual(const CmpcParams& P, int wpc, int grid, void* stream) {
   }
 }
 
-// ---- inversion kernel of the n <= 63 path (cmpc_invert_mma.cuh) ----
+// ---- inversion kernel of the n <= 63 path (cmpc_invert_mma.cuh): one warp per CTA, 200 registers ----
 int cmpc_invert_max_ctas_per_sm(void) {
   int nb = 0;
   const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
-  if (cudaFuncSetAttribute(cmpc_invert_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_invert_mma_kernel<2>, 32 * INV_WPC, smem) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(cmpc_invert_mma_kernel<200>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_invert_mma_kernel<200>, 32 * INV_WPC, smem) != cudaSuccess) return -1;
   return nb;
 }
 int cmpc_invert_instances_per_cta(void) { return INV_WPC; }
 int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
   const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
-  cudaError_t e = cudaFuncSetAttribute(cmpc_invert_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(cmpc_invert_mma_kernel<200>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  cmpc_invert_mma_kernel<2><<<grid, 32 * INV_WPC, smem, (cudaStream_t)stream>>>(P);
+  cmpc_invert_mma_kernel<200><<<grid, 32 * INV_WPC, smem, (cudaStream_t)stream>>>(P);
   return (int)cudaGetLastError();
 }
 

@@ -39,6 +39,35 @@ __global__ void k_dmma_tp(double* out, int iters) {
   double s = 0; for (int i = 0; i < NACC; i++) s += d[i][0] + d[i][1];
   if (s == 1.2345) out[0] = s;
 }
+// distinct A / B operand registers per DMMA (as in a real tile update), NACC accumulators
+template <int NACC>
+__global__ void k_dmma_tp_ops(double* out, int iters) {
+  double d[NACC][2], a[NACC], b[NACC];
+  for (int i = 0; i < NACC; i++) { d[i][0] = threadIdx.x; d[i][1] = i; a[i] = 1e-3 * (threadIdx.x + i); b[i] = 1e-3 * (i + 1); }
+  for (int it = 0; it < iters; it++)
+#pragma unroll
+    for (int i = 0; i < NACC; i++) dmma(d[i][0], d[i][1], a[i], b[(i + it) & (NACC - 1)]);
+  double s = 0; for (int i = 0; i < NACC; i++) s += d[i][0] + d[i][1];
+  if (s == 1.2345) out[0] = s;
+}
+// the tile update of the inversion kernel: 36 accumulator tiles, A fragment per tile row, B fragment per tile column
+__global__ void k_dmma_update(double* out, int iters) {
+  double t[36][2], pf[8][2], mf[8][2];
+  for (int k = 0; k < 36; k++) { t[k][0] = threadIdx.x + k; t[k][1] = k; }
+  for (int k = 0; k < 8; k++) { pf[k][0] = 1e-3 * (threadIdx.x + k); pf[k][1] = 2e-3 * k; mf[k][0] = 1e-3 * k; mf[k][1] = 3e-3 * (k + 1); }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int I = 0; I < 8; I++)
+#pragma unroll
+      for (int J = 0; J <= I; J++) dmma(t[I * (I + 1) / 2 + J][0], t[I * (I + 1) / 2 + J][1], pf[I][0], mf[J][0]);
+#pragma unroll
+    for (int I = 0; I < 8; I++)
+#pragma unroll
+      for (int J = 0; J <= I; J++) dmma(t[I * (I + 1) / 2 + J][0], t[I * (I + 1) / 2 + J][1], pf[I][1], mf[J][1]);
+  }
+  double s = 0; for (int k = 0; k < 36; k++) s += t[k][0] + t[k][1];
+  if (s == 1.2345) out[0] = s;
+}
 __global__ void k_dmma_lat(double* out, long long* cyc, int iters) {
   double d0 = threadIdx.x, d1 = 1;
   double a = 1e-3 * threadIdx.x, b = 1e-3;
@@ -111,7 +140,13 @@ int main() {
     double fl2 = 2.0 * 256 * 8 * it * (double)blocks * thr / 32;
     float ms3 = timeit([&] { k_dmma_tp<2><<<blocks, thr>>>(out, it); });
     double fl3 = 2.0 * 256 * 2 * it * (double)blocks * thr / 32;
-    printf("warps/SM %2d: DFMA %.2f TF/s   DMMA(8 acc) %.2f TF/s   DMMA(2 acc) %.2f TF/s\n", wpsm, fl / ms / 1e9, fl2 / ms2 / 1e9, fl3 / ms3 / 1e9);
+    float ms4 = timeit([&] { k_dmma_tp_ops<8><<<blocks, thr>>>(out, it); });
+    printf("warps/SM %2d: DFMA %.2f TF/s   DMMA(8 acc) %.2f TF/s   DMMA(2 acc) %.2f TF/s   DMMA(8 acc, distinct operands) %.2f TF/s\n", wpsm, fl / ms / 1e9, fl2 / ms2 / 1e9, fl3 / ms3 / 1e9, fl2 / ms4 / 1e9);
+  }
+  for (int wpsm : {4, 8, 12}) {
+    int blocks = sms * wpsm;
+    float ms = timeit([&] { k_dmma_update<<<blocks, 32>>>(out, 2000); });
+    printf("tile update (72 DMMA, 36 tiles) at %d warps/SM: %.2f TF/s\n", wpsm, 2.0 * 256 * 72 * 2000 * (double)blocks / ms / 1e9);
   }
   k_dfma_lat<<<1, 32>>>(out, cyc, 1000); cudaDeviceSynchronize(); printf("DFMA dependent latency %.1f cyc\n", cyc[0] / 16000.0);
   k_dmma_lat<<<1, 32>>>(out, cyc, 1000); cudaDeviceSynchronize(); printf("DMMA dependent latency %.1f cyc\n", cyc[0] / 16000.0);
