@@ -283,3 +283,90 @@ def test_single_instance_adaptive_state_machine(built_lib, golden):
             checked += 1
     assert checked == 8 and use == 1
     L.cmpc_reset_history()
+
+
+def _solve_env(inst, env):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return solve(inst)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("h,gaits,nseg,B", [(10, ("trot",), None, 512), (10, ("trot", "bound", "pace", "gallop"), 10, 512),
+                                            (16, ("trot", "bound", "pace", "gallop"), 10, 256), (10, ("stand",), None, 128)])
+def test_every_kernel_path_agrees(built_lib, h, gaits, nseg, B):
+    """Three-kernel pipeline (DMMA inversion / DFMA condensation shapes, fast and any-capacity dual tiers) vs the
+    fused single-kernel path: the same optimum to rounding, identical activity masks."""
+    inst = synth.make_batch(B, horizon=h, seed=601, gaits=gaits, spread=2.0, n_segment=nseg)
+    ref = _solve_env(inst, {"CMPC_PATH": "fused"})
+    variants = [{}, {"CMPC_QCAP1": "4"}, {"CMPC_DUAL": "generic"}, {"CMPC_CSHAPE": "2"}, {"CMPC_SERIAL": "1"}]
+    for env in variants:
+        res = _solve_env(inst, env)
+        assert (res["status"] == ref["status"]).all(), env
+        assert np.abs(res["forces"] - ref["forces"]).max() <= 1e-7, env
+        assert (np.abs(res["objective"] - ref["objective"]) <= 1e-9 * np.abs(ref["objective"]) + 1e-12).all(), env
+        assert (res["active"] == ref["active"]).all(), env
+
+
+def test_interleaved_uploads_and_solves_stay_ordered(built_lib):
+    """Successive solve_range calls alternate between the engine's two streams; uploads, marks and downloads
+    must still see them in program order."""
+    h, B, ring = 10, 256, 6
+    inst = synth.make_batch(B * ring, horizon=h, seed=701, spread=2.0)
+    b = engine.Batch(B * ring)
+    b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    b.upload(inst)
+    for i in range(ring):
+        b.solve_range(i * B, B)
+    full = b.download()
+    whole = solve(inst)
+    assert (full["forces"] == whole["forces"]).all() and (full["status"] == 0).all()
+    # overwrite the records while solves are in flight, solve again: results follow the new records
+    perm = np.random.default_rng(1).permutation(B * ring)
+    inst2 = {k: (v[perm] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
+    for i in range(ring):
+        b.solve_range(i * B, B)
+    b.upload(inst2)
+    b.mark(0)
+    for i in range(ring):
+        b.solve_range(i * B, B)
+    b.mark(1)
+    again = b.download()
+    assert b.marked_ms() > 0
+    assert (again["forces"] == whole["forces"][perm]).all()
+    # per-kernel-class accounting: the pipeline ran, flops were counted per class
+    b.reset_counters()
+    t = b.profile_range(0, B)
+    fl = b.kernel_flops()
+    assert t["assemble"] > 0 and t["invert"] > 0 and t["dual"] > 0 and t["fused"] == 0
+    assert fl["invert"] >= B * 57 ** 3 and fl["assemble"] > 0 and fl["fused"] == 0
+    b.close()
+
+
+def test_adaptive_batch_at_scale(built_lib, golden):
+    """BASELINE.json configs[2] in miniature on the pipeline path: 4096 Adaptive-MPC instances, estimator fused
+    into the assembly kernel; every instance reproduces the golden fit of the window it was given."""
+    t, d, est_ref = golden["dist_t"], golden["dist_d"], golden["dist_est"]
+    nw, B, h = len(t), 4096, 10
+    idx = np.arange(B) % nw
+    inst = synth.make_batch(B, horizon=h, seed=801)
+    sim_time = t[idx, -1].copy()
+    b = engine.Batch(B)
+    b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    b.upload_disturbance(t[idx], d[idx], sim_time, 1)
+    res = b.solve_host(inst)
+    est, fest = b.download_disturbance()
+    assert (res["status"] == engine.ST_SOLVED).all()
+    assert (est[:, 2] == est_ref[idx, 2]).all()
+    np.testing.assert_allclose(est[:, :2], est_ref[idx, :2], rtol=1e-10, atol=1e-12)
+    b.upload_disturbance(None, None, None, -1)
+    explicit = b.solve_host(inst, f_dist=fest)
+    assert (explicit["forces"] == res["forces"]).all()
+    b.close()

@@ -36,6 +36,8 @@ def test_kernel_image_is_sm100a_with_bulk_copy(built_lib):
     assert "sm_100a" in sass
     assert "UBLKCP" in sass      # cp.async.bulk record prefetch
     assert "DFMA" in sass        # FP64 pipe
+    assert "DMMA.8x8x4" in sass  # FP64 tensor-core sweep of the inversion kernel
+    assert "REDUX" in sass       # warp argmin of the dual active-set kernel
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
