@@ -131,6 +131,10 @@ int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out);
 /* upload + solve + download: the end-to-end call with host buffers. */
 int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const cmpc_outputs* out);
 int cmpc_batch_sync(cmpc_batch* b);
+/* Pin a caller-owned host array (cudaHostRegister): cmpc_batch_solve_host / cmpc_batch_download copy results
+ * straight into pinned output arrays instead of staging them.  Unregister before freeing the array. */
+int cmpc_host_register(void* ptr, size_t bytes);
+int cmpc_host_unregister(void* ptr);
 
 /* Adaptive-MPC periodic disturbance estimation fused into the solve launch
  * (SolverMPC.cpp:688-798).  windows_t/windows_d hold, per instance, the last

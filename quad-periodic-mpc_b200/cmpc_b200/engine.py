@@ -52,6 +52,8 @@ def lib():
         L.cmpc_batch_mark.argtypes = [C.c_void_p, C.c_int]
         L.cmpc_batch_marked_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.cmpc_batch_reset_counters.argtypes = [C.c_void_p]
+        L.cmpc_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.cmpc_host_unregister.argtypes = [C.c_void_p]
         L.cmpc_batch_kernel_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.cmpc_batch_profile_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.cmpc_batch_enable_phase_clocks.argtypes = [C.c_void_p, C.c_int]
@@ -102,6 +104,7 @@ class Batch:
 
     def close(self):
         if self._h:
+            self.release_prepared()
             lib().cmpc_batch_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -184,13 +187,26 @@ class Batch:
         self.count = count
         return res
 
-    def prepare_host(self, inst, count=None, f_dist=None, want_active=True):
-        """Bind host input arrays and preallocated output arrays once; solve_prepared() then is one C call."""
+    def prepare_host(self, inst, count=None, f_dist=None, want_active=True, pin_outputs=True):
+        """Bind host input arrays and preallocated output arrays once; solve_prepared() then is one C call.
+        pin_outputs registers the output arrays with CUDA so results are copied straight into them."""
         count = len(inst["p"]) if count is None else count
         s = self._inputs(inst, count, f_dist)
         o, res = self._outputs(count, want_active)
+        self.release_prepared()
+        pinned = []
+        if pin_outputs:
+            for a in res.values():
+                if a.nbytes and lib().cmpc_host_register(a.ctypes.data, a.nbytes) == 0:
+                    pinned.append(a)
         self._prepared = (count, s, o, res)
+        self._pinned = pinned
         return res
+
+    def release_prepared(self):
+        for a in getattr(self, "_pinned", []):
+            lib().cmpc_host_unregister(a.ctypes.data)
+        self._pinned = []
 
     def solve_prepared(self):
         count, s, o, res = self._prepared

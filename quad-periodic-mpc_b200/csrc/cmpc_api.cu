@@ -8,7 +8,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -90,6 +94,74 @@ void build_adapt_tables(std::vector<double>& tw, std::vector<float>& gk) {
 
 constexpr int kMaxChunks = 8;
 
+// Small persistent worker pool for the host side of the end-to-end call (record packing, result unpacking):
+// parallel_for(n, fn) runs fn(i) for i in [0, n) on the workers and the calling thread.
+class HostPool {
+ public:
+  explicit HostPool(int workers) {
+    for (int i = 0; i < workers; i++) threads_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  int size() const { return (int)threads_.size() + 1; }
+  void parallel_for(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    if (threads_.empty() || n == 1) {
+      for (int i = 0; i < n; i++) fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      n_ = n;
+      next_.store(0);
+      pending_ = (int)threads_.size();
+      gen_++;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work() {
+    for (int i = next_.fetch_add(1); i < n_; i = next_.fetch_add(1)) (*fn_)(i);
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    while (true) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, pending_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
+
 }  // namespace
 
 struct cmpc_batch {
@@ -108,6 +180,7 @@ struct cmpc_batch {
   bool profiling = false;
   unsigned rr = 0;                    // round-robin counter of solve_range
   bool serial = false;                // CMPC_SERIAL=1: keep every solve on the batch stream
+  HostPool* pool = nullptr;           // host workers of the end-to-end call, created on first use
   bool s1_dirty = false;              // stream 1 carries work that stream 0 has not waited for yet
   // problem setup
   bool is_setup = false;
@@ -194,6 +267,37 @@ int pack_records(cmpc_batch* b, const cmpc_inputs* in, int first, int count) {
     maxc = std::max(maxc, c);
   }
   return maxc;
+}
+
+HostPool* host_pool(cmpc_batch* b) {
+  if (!b->pool) {
+    int workers = (int)std::thread::hardware_concurrency() - 1;
+    if (const char* e = std::getenv("CMPC_HOST_THREADS")) workers = std::atoi(e) - 1;
+    b->pool = new HostPool(std::max(0, std::min(workers, 7)));
+  }
+  return b->pool;
+}
+
+// pack_records over the pool: blocks of 256 instances
+int pack_records_parallel(cmpc_batch* b, const cmpc_inputs* in, int first, int count) {
+  if (count < 8192) return pack_records(b, in, first, count);  // below this the hand-off costs more than it saves
+  const int blk = 256, nb = (count + blk - 1) / blk;
+  std::vector<int> maxc(nb, 0);
+  host_pool(b)->parallel_for(nb, [&](int i) {
+    const int f = first + i * blk, n = std::min(blk, first + count - f);
+    maxc[i] = pack_records(b, in, f, n);
+  });
+  return *std::max_element(maxc.begin(), maxc.end());
+}
+
+bool is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
 }
 
 int check_inputs(const cmpc_batch* b, int count, const cmpc_inputs* in, const char* who) {
@@ -579,6 +683,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   for (int i = 0; i < CMPC_K_COUNT + 1; i++) if (b->prof_ev[i]) cudaEventDestroy(b->prof_ev[i]);
   cudaEventDestroy(b->join_ev); cudaEventDestroy(b->fork_ev);
   for (int i = 0; i < 2; i++) cudaStreamDestroy(b->stream[i]);
+  delete b->pool;
   delete b;
 }
 
@@ -668,27 +773,52 @@ int cmpc_batch_sync(cmpc_batch* b) {
   return CMPC_OK;
 }
 
-static int enqueue_d2h(cmpc_batch* b, const cmpc_outputs* out, int first, int n, cudaStream_t st) {
+// Results travel device -> pinned staging -> caller's array; an output array that is itself pinned
+// (cudaHostRegister / cmpc_host_register) receives the copy directly (bit i of `direct`).
+enum { kOutForces = 1, kOutObj = 2, kOutStatus = 4, kOutIters = 8, kOutActive = 16 };
+
+static int direct_mask(const cmpc_outputs* out) {
+  int m = 0;
+  if (is_pinned(out->forces)) m |= kOutForces;
+  if (is_pinned(out->objective)) m |= kOutObj;
+  if (is_pinned(out->status)) m |= kOutStatus;
+  if (is_pinned(out->iterations)) m |= kOutIters;
+  if (is_pinned(out->active)) m |= kOutActive;
+  return m;
+}
+
+static int enqueue_d2h(cmpc_batch* b, const cmpc_outputs* out, int first, int n, cudaStream_t st, int direct = 0) {
   const int h = b->h;
   const size_t f = (size_t)first, c = (size_t)n;
   if (n <= 0) return CMPC_OK;
-  if (out->forces) CK(cudaMemcpyAsync(b->h_forces + f * 12 * h, b->d_forces + f * 12 * h, sizeof(double) * c * 12 * h, cudaMemcpyDeviceToHost, st));
-  if (out->objective) CK(cudaMemcpyAsync(b->h_obj + f, b->d_obj + f, sizeof(double) * c, cudaMemcpyDeviceToHost, st));
-  if (out->status) CK(cudaMemcpyAsync(b->h_status + f, b->d_status + f, sizeof(int) * c, cudaMemcpyDeviceToHost, st));
-  if (out->iterations) CK(cudaMemcpyAsync(b->h_iters + f, b->d_iters + f, sizeof(int) * c, cudaMemcpyDeviceToHost, st));
-  if (out->active) CK(cudaMemcpyAsync(b->h_active + f * 20 * h, b->d_active + f * 20 * h, c * 20 * h, cudaMemcpyDeviceToHost, st));
+  if (out->forces) CK(cudaMemcpyAsync(((direct & kOutForces) ? out->forces : b->h_forces) + f * 12 * h, b->d_forces + f * 12 * h, sizeof(double) * c * 12 * h, cudaMemcpyDeviceToHost, st));
+  if (out->objective) CK(cudaMemcpyAsync(((direct & kOutObj) ? out->objective : b->h_obj) + f, b->d_obj + f, sizeof(double) * c, cudaMemcpyDeviceToHost, st));
+  if (out->status) CK(cudaMemcpyAsync(((direct & kOutStatus) ? out->status : b->h_status) + f, b->d_status + f, sizeof(int) * c, cudaMemcpyDeviceToHost, st));
+  if (out->iterations) CK(cudaMemcpyAsync(((direct & kOutIters) ? out->iterations : b->h_iters) + f, b->d_iters + f, sizeof(int) * c, cudaMemcpyDeviceToHost, st));
+  if (out->active) CK(cudaMemcpyAsync(((direct & kOutActive) ? out->active : b->h_active) + f * 20 * h, b->d_active + f * 20 * h, c * 20 * h, cudaMemcpyDeviceToHost, st));
   return CMPC_OK;
 }
 
-static void unpack_results(cmpc_batch* b, const cmpc_outputs* out, int first, int n) {
+static void unpack_results(cmpc_batch* b, const cmpc_outputs* out, int first, int n, int direct = 0) {
   const int h = b->h;
   const size_t f = (size_t)first, c = (size_t)n;
   if (n <= 0) return;
-  if (out->forces) std::memcpy(out->forces + f * 12 * h, b->h_forces + f * 12 * h, sizeof(double) * c * 12 * h);
-  if (out->objective) std::memcpy(out->objective + f, b->h_obj + f, sizeof(double) * c);
-  if (out->status) std::memcpy(out->status + f, b->h_status + f, sizeof(int) * c);
-  if (out->iterations) std::memcpy(out->iterations + f, b->h_iters + f, sizeof(int) * c);
-  if (out->active) std::memcpy(out->active + f * 20 * h, b->h_active + f * 20 * h, c * 20 * h);
+  if (out->forces && !(direct & kOutForces)) {
+    const size_t bytes = sizeof(double) * c * 12 * h;
+    if (bytes >= (8u << 20)) {  // a large array: split over the host workers
+      const int parts = 8;
+      host_pool(b)->parallel_for(parts, [&](int i) {
+        const size_t lo = bytes * i / parts, hi = bytes * (i + 1) / parts;
+        std::memcpy(reinterpret_cast<char*>(out->forces + f * 12 * h) + lo, reinterpret_cast<const char*>(b->h_forces + f * 12 * h) + lo, hi - lo);
+      });
+    } else {
+      std::memcpy(out->forces + f * 12 * h, b->h_forces + f * 12 * h, bytes);
+    }
+  }
+  if (out->objective && !(direct & kOutObj)) std::memcpy(out->objective + f, b->h_obj + f, sizeof(double) * c);
+  if (out->status && !(direct & kOutStatus)) std::memcpy(out->status + f, b->h_status + f, sizeof(int) * c);
+  if (out->iterations && !(direct & kOutIters)) std::memcpy(out->iterations + f, b->h_iters + f, sizeof(int) * c);
+  if (out->active && !(direct & kOutActive)) std::memcpy(out->active + f * 20 * h, b->h_active + f * 20 * h, c * 20 * h);
 }
 
 int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out) {
@@ -696,10 +826,11 @@ int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out) {
   CK(cudaSetDevice(b->device));
   CK(cudaStreamSynchronize(b->stream[1]));
   b->s1_dirty = false;
-  int rc = enqueue_d2h(b, out, 0, b->count, b->stream[0]);
+  const int direct = direct_mask(out);
+  int rc = enqueue_d2h(b, out, 0, b->count, b->stream[0], direct);
   if (rc) return rc;
   CK(cudaStreamSynchronize(b->stream[0]));
-  unpack_results(b, out, 0, b->count);
+  unpack_results(b, out, 0, b->count, direct);
   return CMPC_OK;
 }
 
@@ -713,8 +844,9 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
   CK(cudaSetDevice(b->device));
   int nchunks = 1;
   if (const char* e = std::getenv("CMPC_CHUNKS")) nchunks = std::atoi(e);
-  else if (count >= 2048) nchunks = 4;
+  else if (count >= 2048) nchunks = std::min(kMaxChunks, std::max(2, count / 16384));  // measured: scripts/e2e_probe.py
   nchunks = std::max(1, std::min(nchunks, kMaxChunks));
+  const int direct = direct_mask(out);
   const int per = (count + nchunks - 1) / nchunks;
   CK(cudaStreamSynchronize(b->stream[1]));
   b->s1_dirty = false;
@@ -726,13 +858,13 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
     if (n <= 0) break;
     const int si = c & 1;
     cudaStream_t st = b->stream[si];
-    const int maxc = pack_records(b, in, first, n);
+    const int maxc = pack_records_parallel(b, in, first, n);
     maxc_all = std::max(maxc_all, maxc);
     CK(cudaMemcpyAsync(b->d_rec + (size_t)first * b->rec_stride, b->h_rec + (size_t)first * b->rec_stride,
                        (size_t)n * b->rec_stride, cudaMemcpyHostToDevice, st));
     rc = launch_range(b, first, n, maxc, si);
     if (rc) return rc;
-    rc = enqueue_d2h(b, out, first, n, st);
+    rc = enqueue_d2h(b, out, first, n, st, direct);
     if (rc) return rc;
     CK(cudaEventRecord(b->chunk_done[c], st));
     used = c + 1;
@@ -741,7 +873,7 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
   for (int c = 0; c < used; c++) {
     const int first = c * per, n = std::min(per, count - first);
     CK(cudaEventSynchronize(b->chunk_done[c]));
-    unpack_results(b, out, first, n);
+    unpack_results(b, out, first, n, direct);
   }
   CK(cudaStreamWaitEvent(b->stream[0], b->chunk_done[used > 0 ? used - 1 : 0], 0));
   CK(cudaEventRecord(b->ev1, b->stream[0]));
@@ -819,6 +951,18 @@ int cmpc_batch_last_solve_ms(cmpc_batch* b, float* ms) {
   CK(cudaSetDevice(b->device));
   CK(cudaEventSynchronize(b->ev1));
   CK(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+  return CMPC_OK;
+}
+
+int cmpc_host_register(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return fail_arg("cmpc_host_register: bad arguments");
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return CMPC_OK;
+}
+
+int cmpc_host_unregister(void* ptr) {
+  if (!ptr) return fail_arg("cmpc_host_unregister: null pointer");
+  CK(cudaHostUnregister(ptr));
   return CMPC_OK;
 }
 
