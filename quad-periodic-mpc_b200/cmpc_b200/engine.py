@@ -187,19 +187,25 @@ class Batch:
         self.count = count
         return res
 
-    def prepare_host(self, inst, count=None, f_dist=None, want_active=True, pin_outputs=True):
+    def prepare_host(self, inst, count=None, f_dist=None, want_active=True, pin_outputs=True, pin_inputs=True):
         """Bind host input arrays and preallocated output arrays once; solve_prepared() then is one C call.
-        pin_outputs registers the output arrays with CUDA so results are copied straight into them."""
+        pin_outputs registers the output arrays with CUDA so results are copied straight into them;
+        pin_inputs registers the input arrays so the device reads them itself and packs the records (cmpc_pack.cu)."""
         count = len(inst["p"]) if count is None else count
         s = self._inputs(inst, count, f_dist)
         o, res = self._outputs(count, want_active)
         self.release_prepared()
         pinned = []
+        if pin_inputs:
+            for a in self._keep.values():
+                if a.nbytes and lib().cmpc_host_register(a.ctypes.data, a.nbytes) == 0:
+                    pinned.append(a)
         if pin_outputs:
             for a in res.values():
                 if a.nbytes and lib().cmpc_host_register(a.ctypes.data, a.nbytes) == 0:
                     pinned.append(a)
         self._prepared = (count, s, o, res)
+        self._prepared_inputs = self._keep   # later uploads rebind self._keep; these arrays stay alive with the binding
         self._pinned = pinned
         return res
 

@@ -93,6 +93,7 @@ void build_adapt_tables(std::vector<double>& tw, std::vector<float>& gk) {
 }
 
 constexpr int kMaxChunks = 8;
+constexpr int kMaxStreams = 8;
 
 // Small persistent worker pool for the host side of the end-to-end call (record packing, result unpacking):
 // parallel_for(n, fn) runs fn(i) for i in [0, n) on the workers and the calling thread.
@@ -168,12 +169,14 @@ struct cmpc_batch {
   int device = 0;
   int capacity = 0;
   int sm_count = 0;
-  cudaStream_t stream[2] = {nullptr, nullptr};  // [0] is "the batch stream"; [1] only carries pipelined chunks
+  cudaStream_t stream[kMaxStreams] = {};  // [0] is "the batch stream"; the others only carry pipelined chunks / solves
+  int nstreams = 2;                       // streams that successive solve_range calls rotate through (CMPC_NSTREAMS)
+  int split = 1;                          // parts a solve_range call is cut into, one per stream in turn (CMPC_SPLIT)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, mark0 = nullptr, mark1 = nullptr;
   cudaEvent_t chunk_done[kMaxChunks] = {};
   // successive solve_range calls alternate between the two streams so that the latency-bound tail of one
   // batch overlaps the next batch's kernels; these events carry the cross-stream ordering
-  cudaEvent_t join_ev = nullptr;      // scratch: "stream 1 has reached this point"
+  cudaEvent_t join_ev = nullptr;      // scratch: "stream i has reached this point"
   cudaEvent_t fork_ev = nullptr;      // scratch: "stream 0 has reached this point"
   cudaEvent_t prof_ev[CMPC_K_COUNT + 1] = {};  // cmpc_batch_profile_range: events between the kernel classes
   float prof_ms[CMPC_K_COUNT] = {};
@@ -181,7 +184,7 @@ struct cmpc_batch {
   unsigned rr = 0;                    // round-robin counter of solve_range
   bool serial = false;                // CMPC_SERIAL=1: keep every solve on the batch stream
   HostPool* pool = nullptr;           // host workers of the end-to-end call, created on first use
-  bool s1_dirty = false;              // stream 1 carries work that stream 0 has not waited for yet
+  unsigned dirty = 0;                 // bit i: stream i carries work that stream 0 has not waited for yet
   // problem setup
   bool is_setup = false;
   int h = 0;
@@ -198,16 +201,16 @@ struct cmpc_batch {
   int* d_status = nullptr;
   int* d_iters = nullptr;
   signed char* d_active = nullptr;
-  int* d_overflow[2] = {nullptr, nullptr};  // per stream: [capacity] list + [1] count at the end
+  int* d_overflow[kMaxStreams] = {};  // per stream: [capacity] list + [1] count at the end
   unsigned long long* d_flops = nullptr;
   unsigned long long* d_phase = nullptr;  // CMPC_PH_COUNT phase clocks, allocated by cmpc_batch_enable_phase_clocks
   double* d_gws = nullptr;  // global workspace of the large-problem tier, grown on demand
   size_t gws_bytes = 0;
   // two-kernel pipeline: per-stream workspace slots (K, g, x0 per instance of a chunk) and work counters
-  double* d_qws[2] = {nullptr, nullptr};
-  size_t qws_bytes[2] = {0, 0};
-  int* d_sched[2] = {nullptr, nullptr};
-  int sched_ints[2] = {0, 0};
+  double* d_qws[kMaxStreams] = {};
+  size_t qws_bytes[kMaxStreams] = {};
+  int* d_sched[kMaxStreams] = {};
+  int sched_ints[kMaxStreams] = {};
   // adaptive stage
   double* d_twiddle = nullptr;
   float* d_gk = nullptr;
@@ -223,6 +226,13 @@ struct cmpc_batch {
   int* h_iters = nullptr;
   signed char* h_active = nullptr;
   unsigned long long* h_flops = nullptr;
+  // end-to-end call: device views of the (pinned) host arrays the kernels write their outputs to, instead of
+  // the device arrays above; null = the device array
+  double* o_forces = nullptr;
+  double* o_obj = nullptr;
+  int* o_status = nullptr;
+  int* o_iters = nullptr;
+  signed char* o_active = nullptr;
   // state
   int count = 0;
   int max_contact = 0;  // max contact foot-steps over the uploaded instances
@@ -300,6 +310,65 @@ bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// Device-side view of a pinned (cudaHostAlloc / cudaHostRegister) host array, or nullptr if the array is pageable.
+const void* device_view(const void* p) {
+  if (!p) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a.type != cudaMemoryTypeHost) return nullptr;
+  return a.devicePointer;
+}
+
+// The eleven input arrays as device-accessible pointers when every one of them is pinned (and word aligned):
+// the end-to-end call then packs the records on the device (cmpc_pack.cu) instead of on the host.
+struct SoaView {
+  const char* p[11];
+  bool ok;
+};
+SoaView soa_view(const cmpc_inputs* in) {
+  SoaView s;
+  const void* src[11] = {in->p, in->v, in->q, in->w, in->r, in->weights, in->traj, in->alpha, in->gait, in->x_drag, in->f_dist};
+  s.ok = true;
+  for (int i = 0; i < 11; i++) {
+    s.p[i] = static_cast<const char*>(device_view(src[i]));
+    if (src[i] && (!s.p[i] || (reinterpret_cast<uintptr_t>(s.p[i]) & 3u))) s.ok = false;
+  }
+  return s;
+}
+
+// max contact foot-steps over instances [first, first+n) (what pack_records returns), from the gait bytes alone
+int max_contact_scan(const cmpc_batch* b, const uint8_t* gait, int first, int n) {
+  const int h4 = 4 * b->h;
+  const double fmax = (double)(float)b->f_max;
+  bool keep[256];
+  bool plain = true;  // keep[v] == (v != 0): the usual case (f_max >= 0.01), counted eight bytes at a time
+  for (int v = 0; v < 256; v++) {
+    const double ub = (double)v * fmax;
+    keep[v] = !(ub < 0.01 && ub > -0.01);
+    plain = plain && (keep[v] == (v != 0));
+  }
+  int maxc = 0;
+  for (int i = first; i < first + n; i++) {
+    const uint8_t* g = gait + (size_t)i * h4;
+    int c = 0, k = 0;
+    if (plain) {
+      for (; k + 8 <= h4; k += 8) {
+        uint64_t x;
+        std::memcpy(&x, g + k, 8);
+        // bit 7 of every non-zero byte
+        x = ((x & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | x;
+        c += __builtin_popcountll(x & 0x8080808080808080ull);
+      }
+    }
+    for (; k < h4; k++) c += keep[g[k]];
+    maxc = std::max(maxc, c);
+  }
+  return maxc;
+}
+
 int check_inputs(const cmpc_batch* b, int count, const cmpc_inputs* in, const char* who) {
   if (!b || !in) return fail_arg("null argument");
   if (!b->is_setup) { g_err = std::string(who) + ": call cmpc_batch_setup first"; return CMPC_E_STATE; }
@@ -312,16 +381,33 @@ int check_inputs(const cmpc_batch* b, int count, const cmpc_inputs* in, const ch
 
 // stream 0 ("the batch stream") waits for everything enqueued on stream 1 so far
 int join_streams(cmpc_batch* b) {
-  if (!b->s1_dirty) return CMPC_OK;
-  CK(cudaEventRecord(b->join_ev, b->stream[1]));
-  CK(cudaStreamWaitEvent(b->stream[0], b->join_ev, 0));
-  b->s1_dirty = false;
+  for (int i = 1; i < kMaxStreams; i++) {
+    if (!((b->dirty >> i) & 1u)) continue;
+    CK(cudaEventRecord(b->join_ev, b->stream[i]));
+    CK(cudaStreamWaitEvent(b->stream[0], b->join_ev, 0));
+  }
+  b->dirty = 0;
   return CMPC_OK;
 }
-// stream 1 waits for everything enqueued on stream 0 so far (uploads, marks)
-int fork_streams(cmpc_batch* b) {
+// the host waits for every stream
+int sync_all(cmpc_batch* b) {
+  for (int i = 0; i < kMaxStreams; i++)
+    if (b->stream[i]) CK(cudaStreamSynchronize(b->stream[i]));
+  b->dirty = 0;
+  return CMPC_OK;
+}
+// the host waits for the auxiliary streams (the batch stream keeps running)
+int sync_aux(cmpc_batch* b) {
+  for (int i = 1; i < kMaxStreams; i++)
+    if ((b->dirty >> i) & 1u) CK(cudaStreamSynchronize(b->stream[i]));
+  b->dirty = 0;
+  return CMPC_OK;
+}
+// the auxiliary streams wait for everything enqueued on stream 0 so far (uploads, marks)
+int fork_streams(cmpc_batch* b, int only = -1) {
   CK(cudaEventRecord(b->fork_ev, b->stream[0]));
-  CK(cudaStreamWaitEvent(b->stream[1], b->fork_ev, 0));
+  for (int i = 1; i < kMaxStreams; i++)
+    if (only < 0 ? i < b->nstreams : i == only) CK(cudaStreamWaitEvent(b->stream[i], b->fork_ev, 0));
   return CMPC_OK;
 }
 
@@ -346,7 +432,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
   const int nchunks = (count + chunk - 1) / chunk;
   const size_t need = (size_t)chunk * slot * sizeof(double);
   if (need > b->qws_bytes[si] || 4 * nchunks > b->sched_ints[si]) {
-    for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+    { int rcs = sync_all(b); if (rcs) return rcs; }
     if (need > b->qws_bytes[si]) {
       if (b->d_qws[si]) CK(cudaFree(b->d_qws[si]));
       b->d_qws[si] = nullptr;
@@ -508,11 +594,11 @@ int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
   P.worklist = nullptr;
   P.overflow_list = b->d_overflow[si];
   P.overflow_count = b->d_overflow[si] + b->capacity;
-  P.forces = b->d_forces + (size_t)first * 12 * b->h;
-  P.objective = b->d_obj + first;
-  P.status = b->d_status + first;
-  P.iterations = b->d_iters + first;
-  P.active = b->d_active + (size_t)first * 20 * b->h;
+  P.forces = (b->o_forces ? b->o_forces : b->d_forces) + (size_t)first * 12 * b->h;
+  P.objective = (b->o_obj ? b->o_obj : b->d_obj) + first;
+  P.status = (b->o_status ? b->o_status : b->d_status) + first;
+  P.iterations = (b->o_iters ? b->o_iters : b->d_iters) + first;
+  P.active = (b->o_active ? b->o_active : b->d_active) + (size_t)first * 20 * b->h;
   P.flops = b->d_flops;
   P.phase_cycles = b->d_phase;
   if (b->adapt_mode >= 0) {
@@ -572,9 +658,9 @@ int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
     int grid = std::min(count, b->sm_count * per_sm);
     if (shape == CMPC_SHAPE_GMEM) {
       const size_t stride = (size_t)P.nmax * P.nmax + (size_t)(P.nmax + 1) * (P.nmax + 2) / 2;
-      const size_t need = sizeof(double) * stride * (size_t)b->sm_count * 2 * 2;  // two streams' worth
+      const size_t need = sizeof(double) * stride * (size_t)b->sm_count * 2 * kMaxStreams;  // every stream's worth
       if (need > b->gws_bytes) {
-        for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+        { int rcs = sync_all(b); if (rcs) return rcs; }
         if (b->d_gws) CK(cudaFree(b->d_gws));
         b->d_gws = nullptr;
         CK(cudaMalloc(&b->d_gws, need));
@@ -632,7 +718,9 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   b->sm_count = prop.multiProcessorCount;
-  for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&b->stream[i], cudaStreamNonBlocking));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaStreamCreateWithFlags(&b->stream[i], cudaStreamNonBlocking));
+  if (const char* e = std::getenv("CMPC_NSTREAMS")) b->nstreams = std::max(1, std::min(kMaxStreams, std::atoi(e)));
+  if (const char* e = std::getenv("CMPC_SPLIT")) b->split = std::max(1, std::min(kMaxStreams, std::atoi(e)));
   CK(cudaEventCreate(&b->ev0));
   CK(cudaEventCreate(&b->ev1));
   CK(cudaEventCreate(&b->mark0));
@@ -651,7 +739,7 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMalloc(&b->d_status, sizeof(int) * cap));
   CK(cudaMalloc(&b->d_iters, sizeof(int) * cap));
   CK(cudaMalloc(&b->d_active, cap * 20 * hm));
-  for (int i = 0; i < 2; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
   CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMallocHost(&b->h_forces, sizeof(double) * cap * 12 * hm));
@@ -669,11 +757,11 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
 void cmpc_batch_destroy(cmpc_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  for (int i = 0; i < 2; i++) cudaStreamSynchronize(b->stream[i]);
+  for (int i = 0; i < kMaxStreams; i++) cudaStreamSynchronize(b->stream[i]);
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
   cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops); cudaFree(b->d_phase);
-  cudaFree(b->d_overflow[0]); cudaFree(b->d_overflow[1]); cudaFree(b->d_gws);
-  for (int i = 0; i < 2; i++) { cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); }
+  cudaFree(b->d_gws);
+  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); }
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFreeHost(b->h_forces); cudaFreeHost(b->h_obj); cudaFreeHost(b->h_status); cudaFreeHost(b->h_iters);
@@ -682,7 +770,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->chunk_done[i]);
   for (int i = 0; i < CMPC_K_COUNT + 1; i++) if (b->prof_ev[i]) cudaEventDestroy(b->prof_ev[i]);
   cudaEventDestroy(b->join_ev); cudaEventDestroy(b->fork_ev);
-  for (int i = 0; i < 2; i++) cudaStreamDestroy(b->stream[i]);
+  for (int i = 0; i < kMaxStreams; i++) cudaStreamDestroy(b->stream[i]);
   delete b->pool;
   delete b;
 }
@@ -702,7 +790,7 @@ int cmpc_batch_setup(cmpc_batch* b, double dt, int horizon, double mu, double f_
     // the reference narrows dt to float (problem_setup.dt, convexMPC_interface.h:17)
     std::vector<double> sig;
     build_sigma(horizon, (double)(float)dt, sig);
-    for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+    { int rcs = sync_all(b); if (rcs) return rcs; }
     CK(cudaMemcpyAsync(b->d_sigma, sig.data(), sizeof(double) * sig.size(), cudaMemcpyHostToDevice, b->stream[0]));
     CK(cudaStreamSynchronize(b->stream[0]));
     b->count = 0;
@@ -750,17 +838,25 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
   if (!b->is_setup) { g_err = "cmpc_batch_solve: call cmpc_batch_setup first"; return CMPC_E_STATE; }
   if (first < 0 || count < 0 || first + count > b->count) return fail_arg("cmpc_batch_solve_range: range outside the uploaded instances");
   CK(cudaSetDevice(b->device));
-  int si = 0;
-  if (!b->serial) si = (int)(b->rr++ & 1u);
-  if (si == 1) {
-    int rcf = fork_streams(b);  // after the uploads / marks already enqueued on the batch stream
-    if (rcf) return rcf;
-    b->s1_dirty = true;
+  // a large range is cut into `split` parts on successive streams: kernels of different parts (assembly,
+  // inversion, active set) then share the SMs instead of each waiting for the previous kernel's tail
+  const int parts = (b->serial || count < 512 * b->split) ? 1 : b->split;
+  const int per = (count + parts - 1) / parts;
+  for (int part = 0; part < parts; part++) {
+    const int pf = first + part * per, pn = std::min(per, first + count - pf);
+    if (pn <= 0) break;
+    int si = 0;
+    if (!b->serial) si = (int)(b->rr++ % (unsigned)b->nstreams);
+    if (si != 0) {
+      int rcf = fork_streams(b, si);  // after the uploads / marks already enqueued on the batch stream
+      if (rcf) return rcf;
+      b->dirty |= 1u << si;
+    }
+    if (part == 0) CK(cudaEventRecord(b->ev0, b->stream[si]));
+    int rc = launch_range(b, pf, pn, b->max_contact, si);
+    if (rc) return rc;
+    if (part == parts - 1) CK(cudaEventRecord(b->ev1, b->stream[si]));
   }
-  CK(cudaEventRecord(b->ev0, b->stream[si]));
-  int rc = launch_range(b, first, count, b->max_contact, si);
-  if (rc) return rc;
-  CK(cudaEventRecord(b->ev1, b->stream[si]));
   b->timed = true;
   return CMPC_OK;
 }
@@ -768,9 +864,7 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
 int cmpc_batch_sync(cmpc_batch* b) {
   if (!b) return fail_arg("cmpc_batch_sync: null batch");
   CK(cudaSetDevice(b->device));
-  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
-  b->s1_dirty = false;
-  return CMPC_OK;
+  return sync_all(b);
 }
 
 // Results travel device -> pinned staging -> caller's array; an output array that is itself pinned
@@ -824,8 +918,7 @@ static void unpack_results(cmpc_batch* b, const cmpc_outputs* out, int first, in
 int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out) {
   if (!b || !out) return fail_arg("cmpc_batch_download: null argument");
   CK(cudaSetDevice(b->device));
-  CK(cudaStreamSynchronize(b->stream[1]));
-  b->s1_dirty = false;
+  { int rcs = sync_aux(b); if (rcs) return rcs; }
   const int direct = direct_mask(out);
   int rc = enqueue_d2h(b, out, 0, b->count, b->stream[0], direct);
   if (rc) return rc;
@@ -834,9 +927,12 @@ int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out) {
   return CMPC_OK;
 }
 
-// End-to-end call with host buffers.  The batch is cut into chunks that alternate between two
-// streams: while chunk c is copied in and solved, the host packs chunk c+1 into pinned records, and
-// the results of earlier chunks are copied out and unpacked while later chunks are still being solved.
+// End-to-end call with host buffers.  The batch is cut into chunks that alternate between two streams.  Inputs:
+// pinned arrays are read by the device itself, which packs the records (cmpc_pack.cu); pageable arrays are packed
+// into pinned records on the host, chunk c+1 while chunk c is copied in and solved.  Outputs: the kernels write
+// them straight into host memory over PCIe as instances finish (the caller's arrays if pinned, else pinned staging
+// that is copied out here), so no device-to-host copy waits behind the last kernel.  CMPC_D2H_COPY=1 restores
+// device-side outputs + cudaMemcpyAsync.
 int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const cmpc_outputs* out) {
   int rc = check_inputs(b, count, in, "cmpc_batch_solve_host");
   if (rc) return rc;
@@ -847,25 +943,68 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
   else if (count >= 2048) nchunks = std::min(kMaxChunks, std::max(2, count / 16384));  // measured: scripts/e2e_probe.py
   nchunks = std::max(1, std::min(nchunks, kMaxChunks));
   const int direct = direct_mask(out);
+  // pinned input arrays are read by the device itself (cmpc_pack.cu); pageable ones are packed into pinned records here
+  SoaView soa = soa_view(in);
+  if (const char* e = std::getenv("CMPC_HOST_PACK")) soa.ok = soa.ok && std::atoi(e) == 0;
   const int per = (count + nchunks - 1) / nchunks;
-  CK(cudaStreamSynchronize(b->stream[1]));
-  b->s1_dirty = false;
+  { int rcs = sync_aux(b); if (rcs) return rcs; }
   CK(cudaEventRecord(b->ev0, b->stream[0]));
   b->count = count;
   int maxc_all = 0, used = 0;
+  const int h = b->h;
+  bool zc_out = true;
+  if (const char* e = std::getenv("CMPC_D2H_COPY")) zc_out = std::atoi(e) == 0;
+  struct OutGuard {  // the overrides only live for this call
+    cmpc_batch* b;
+    ~OutGuard() { b->o_forces = nullptr; b->o_obj = nullptr; b->o_status = nullptr; b->o_iters = nullptr; b->o_active = nullptr; }
+  } guard{b};
+  void* vo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (zc_out) {
+    auto view = [&](void* user, void* staging, int bit) -> void* {
+      if (!user) return nullptr;
+      return const_cast<void*>(device_view((direct & bit) ? user : staging));
+    };
+    vo[0] = view(out->forces, b->h_forces, kOutForces);
+    vo[1] = view(out->objective, b->h_obj, kOutObj);
+    vo[2] = view(out->status, b->h_status, kOutStatus);
+    vo[3] = view(out->iterations, b->h_iters, kOutIters);
+    vo[4] = view(out->active, b->h_active, kOutActive);
+  }
   for (int c = 0; c < nchunks; c++) {
     const int first = c * per, n = std::min(per, count - first);
     if (n <= 0) break;
     const int si = c & 1;
     cudaStream_t st = b->stream[si];
-    const int maxc = pack_records_parallel(b, in, first, n);
+    int maxc;
+    if (soa.ok) {
+      maxc = max_contact_scan(b, in->gait, first, n);
+      const size_t f = (size_t)first;
+      auto at = [&](int i, size_t bytes_per_instance) -> const void* { return soa.p[i] ? soa.p[i] + f * bytes_per_instance : nullptr; };
+      const int rcp = cmpc_launch_pack(at(0, 12), at(1, 12), at(2, 16), at(3, 12), at(4, 48), at(5, 48), at(6, 48 * (size_t)h),
+                                       at(7, 4), at(8, 4 * (size_t)h), at(9, 4), at(10, 24),
+                                       b->d_rec + f * b->rec_stride, b->rec_stride, h, n, b->sm_count, st);
+      if (rcp != 0) return fail_cuda((cudaError_t)rcp, "cmpc_pack_records_kernel launch");
+      b->launches++;
+    } else {
+      maxc = pack_records_parallel(b, in, first, n);
+      CK(cudaMemcpyAsync(b->d_rec + (size_t)first * b->rec_stride, b->h_rec + (size_t)first * b->rec_stride,
+                         (size_t)n * b->rec_stride, cudaMemcpyHostToDevice, st));
+    }
     maxc_all = std::max(maxc_all, maxc);
-    CK(cudaMemcpyAsync(b->d_rec + (size_t)first * b->rec_stride, b->h_rec + (size_t)first * b->rec_stride,
-                       (size_t)n * b->rec_stride, cudaMemcpyHostToDevice, st));
+    // the staged, word-wide output stores live in the pipeline's active-set kernel (reduced problems of up to 128
+    // variables); the single-kernel path of larger problems keeps device-side outputs and a copy
+    const bool zc = zc_out && 3 * maxc <= CMPC_PIPELINE_NMAX;
+    b->o_forces = zc ? static_cast<double*>(vo[0]) : nullptr;
+    b->o_obj = zc ? static_cast<double*>(vo[1]) : nullptr;
+    b->o_status = zc ? static_cast<int*>(vo[2]) : nullptr;
+    b->o_iters = zc ? static_cast<int*>(vo[3]) : nullptr;
+    b->o_active = zc ? static_cast<signed char*>(vo[4]) : nullptr;
     rc = launch_range(b, first, n, maxc, si);
     if (rc) return rc;
-    rc = enqueue_d2h(b, out, first, n, st, direct);
-    if (rc) return rc;
+    if (!zc) {
+      rc = enqueue_d2h(b, out, first, n, st, direct);
+      if (rc) return rc;
+    }
     CK(cudaEventRecord(b->chunk_done[c], st));
     used = c + 1;
   }
@@ -885,8 +1024,7 @@ int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows
                                   const float* sim_time, int mode) {
   if (!b) return fail_arg("cmpc_batch_upload_disturbance: null batch");
   CK(cudaSetDevice(b->device));
-  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));  // solves in flight read the old windows
-  b->s1_dirty = false;
+  { int rcs = sync_all(b); if (rcs) return rcs; }  // solves in flight read the old windows
   if (mode < 0 || (!windows_t && mode != 2)) {
     b->adapt_mode = -1;
     return CMPC_OK;
@@ -926,7 +1064,7 @@ int cmpc_batch_download_disturbance(cmpc_batch* b, double* est, float* f_est) {
   if (!b) return fail_arg("cmpc_batch_download_disturbance: null batch");
   if (!b->d_est) { g_err = "cmpc_batch_download_disturbance: no disturbance data was uploaded"; return CMPC_E_STATE; }
   CK(cudaSetDevice(b->device));
-  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+  { int rcs = sync_all(b); if (rcs) return rcs; }
   if (est) CK(cudaMemcpy(est, b->d_est, sizeof(double) * (size_t)b->count * 4, cudaMemcpyDeviceToHost));
   if (f_est) CK(cudaMemcpy(f_est, b->d_fest, sizeof(float) * (size_t)b->count * 6, cudaMemcpyDeviceToHost));
   return CMPC_OK;
@@ -1001,8 +1139,7 @@ int cmpc_batch_kernel_launches(cmpc_batch* b, long long* launches) {
 int cmpc_batch_last_flops(cmpc_batch* b, double* flops) {
   if (!b || !flops) return fail_arg("cmpc_batch_last_flops: null argument");
   CK(cudaSetDevice(b->device));
-  CK(cudaStreamSynchronize(b->stream[1]));
-  b->s1_dirty = false;
+  { int rcs = sync_aux(b); if (rcs) return rcs; }
   CK(cudaMemcpyAsync(b->h_flops, b->d_flops, sizeof(unsigned long long) * CMPC_K_COUNT, cudaMemcpyDeviceToHost, b->stream[0]));
   CK(cudaStreamSynchronize(b->stream[0]));
   *flops = 0.0;
@@ -1025,8 +1162,7 @@ int cmpc_batch_profile_range(cmpc_batch* b, int first, int count, float ms[4]) {
   if (!b->is_setup) { g_err = "cmpc_batch_profile_range: call cmpc_batch_setup first"; return CMPC_E_STATE; }
   if (first < 0 || count < 0 || first + count > b->count) return fail_arg("cmpc_batch_profile_range: range outside the uploaded instances");
   CK(cudaSetDevice(b->device));
-  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
-  b->s1_dirty = false;
+  { int rcs = sync_all(b); if (rcs) return rcs; }
   if (!b->prof_ev[0])
     for (int i = 0; i < CMPC_K_COUNT + 1; i++) CK(cudaEventCreate(&b->prof_ev[i]));
   for (int i = 0; i < CMPC_K_COUNT; i++) { ms[i] = 0.f; b->prof_ms[i] = 0.f; }
@@ -1042,7 +1178,7 @@ int cmpc_batch_profile_range(cmpc_batch* b, int first, int count, float ms[4]) {
 int cmpc_batch_enable_phase_clocks(cmpc_batch* b, int on) {
   if (!b) return fail_arg("cmpc_batch_enable_phase_clocks: null batch");
   CK(cudaSetDevice(b->device));
-  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+  { int rcs = sync_all(b); if (rcs) return rcs; }
   if (on && !b->d_phase) CK(cudaMalloc(&b->d_phase, sizeof(unsigned long long) * CMPC_PH_COUNT));
   if (!on && b->d_phase) {
     CK(cudaFree(b->d_phase));
@@ -1056,7 +1192,7 @@ int cmpc_batch_phase_cycles(cmpc_batch* b, unsigned long long* cycles, int n) {
   if (!b || !cycles || n < 1) return fail_arg("cmpc_batch_phase_cycles: bad arguments");
   if (!b->d_phase) { g_err = "cmpc_batch_phase_cycles: phase clocks are not enabled"; return CMPC_E_STATE; }
   CK(cudaSetDevice(b->device));
-  for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(b->stream[i]));
+  { int rcs = sync_all(b); if (rcs) return rcs; }
   unsigned long long tmp[CMPC_PH_COUNT];
   CK(cudaMemcpy(tmp, b->d_phase, sizeof(tmp), cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; i++) cycles[i] = i < CMPC_PH_COUNT ? tmp[i] : 0ull;

@@ -158,3 +158,7 @@ int cmpc_shape_threads(int shape);
 int cmpc_launch_solve(const CmpcParams& P, int shape, int grid, void* stream);
 int cmpc_max_ctas_per_sm(int shape, size_t smem, bool adapt);
 int cmpc_run_dfma_peak(int sm_count, void* stream, double* out_dev, int iters);
+/* cmpc_pack.cu: instance records from structure-of-arrays inputs (device-accessible pointers, e.g. pinned host memory) */
+int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w, const void* r, const void* weights,
+                     const void* traj, const void* alpha, const void* gait, const void* x_drag, const void* f_dist,
+                     unsigned char* records, int rec_stride, int horizon, int count, int sm_count, void* stream);

@@ -16,7 +16,7 @@
 namespace {
 
 struct FCarve {
-  int kn, z, d, r, P, KN, misc, total;
+  int kn, z, d, r, P, KN, misc, ostage, total;
 };
 
 __host__ __device__ inline FCarve make_fcarve(int npl, int qcap) {
@@ -29,6 +29,8 @@ __host__ __device__ inline FCarve make_fcarve(int npl, int qcap) {
   c.P = o; o += align16(8 * (qcap * ((qcap + 4) | 1) + 8));
   c.KN = o; o += 8 * (qcap + 4) * 32 * npl;
   c.misc = o; o += 3 * CMPC_MAX_FS + 16;  // fs, gv, fsinv bytes
+  o = align16(o);
+  c.ostage = o; o += 20 * CMPC_MAX_HORIZON + 4;  // activity bytes of one instance, staged for word-wide stores
   c.total = align16(o);
   return c;
 }
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
   unsigned char* fs = base + cv.misc;
   unsigned char* gv = fs + CMPC_MAX_FS;
   signed char* fsinv = reinterpret_cast<signed char*>(gv + CMPC_MAX_FS);
+  signed char* astage = reinterpret_cast<signed char*>(base + cv.ostage);
   constexpr int NS = 32 * NPL;  // KN row stride
   const int PSQ = (qcap + 4) | 1;  // P row stride: room for the 4-wide padded loops, odd (conflict-free row-per-lane access)
 
@@ -382,16 +385,16 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
 #pragma unroll
     for (int e = 0; e < NPL; e++) kns[lane + 32 * e] = x[e];
     __syncwarp();
+    // staged in shared memory (the first rows of KN are free now and only ever need to hold finite values), then
+    // written as whole 16-byte / 4-byte words, contiguous across the warp: the output arrays may be pinned HOST
+    // memory that the kernel writes over PCIe (cmpc_batch_solve_host), where full-line writes are what counts
+    double* fstage = KN;
     for (int k = lane; k < 4 * h; k += 32) {  // one foot-step per lane
       const int j = fsinv[k];
       double fx = 0.0, fy = 0.0, fz = 0.0;
       if (j >= 0 && have_x) { fx = kns[3 * j]; fy = kns[3 * j + 1]; fz = kns[3 * j + 2]; }
-      if (P.forces) {
-        double* out = P.forces + (size_t)inst * 12 * h + 3 * k;
-        out[0] = fx; out[1] = fy; out[2] = fz;
-      }
+      fstage[3 * k] = fx; fstage[3 * k + 1] = fy; fstage[3 * k + 2] = fz;
       if (P.active) {
-        signed char* out = P.active + (size_t)inst * 20 * h + 5 * k;
         signed char a[5] = {0, 0, 0, 0, 0};
         if (j >= 0 && have_x) {
           const double ub = (double)gv[j] * P.f_max;
@@ -403,8 +406,19 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
           if (fz >= ub - P.tol_active) a[4] = 1;
         }
 #pragma unroll
-        for (int t = 0; t < 5; t++) out[t] = a[t];
+        for (int t = 0; t < 5; t++) astage[5 * k + t] = a[t];
       }
+    }
+    __syncwarp();
+    if (P.forces) {
+      double2* out = reinterpret_cast<double2*>(P.forces + (size_t)inst * 12 * h);  // 96 h bytes per instance: 16-byte aligned
+      const double2* src = reinterpret_cast<const double2*>(fstage);
+      for (int i = lane; i < 6 * h; i += 32) out[i] = src[i];
+    }
+    if (P.active) {
+      int* out = reinterpret_cast<int*>(P.active + (size_t)inst * 20 * h);  // 20 h bytes per instance: 4-byte aligned
+      const int* src = reinterpret_cast<const int*>(astage);
+      for (int i = lane; i < 5 * h; i += 32) out[i] = src[i];
     }
     {
       // objective 0.5 x'Hx + g'x = 0.5 g'x + 0.5 lambda'b at a KKT point

@@ -56,7 +56,7 @@ constexpr int INV_WPC = 1;  // warps per CTA: one, so that the register file hol
 constexpr int INV_WARP_SMEM = 8 * (2 * 8 * MMA_PS + 64);
 }  // namespace
 
-template <int MINB /* register cap */>
+template <int MINB /* register cap */, bool CLK /* per-phase SM cycles (profiling launches only) */>
 __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mma_kernel(const __grid_constant__ CmpcParams P) {
   constexpr int PS = MMA_PS;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -66,11 +66,11 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
   double* mm = pan + 8 * PS;
   double* dv = mm + 8 * PS;
   const int count = P.count;
-  double flops_acc = 0.0;  // algorithmic: n^3 for the symmetric inverse, 2 n^2 for x0 = -K g
+  unsigned flops_acc = 0u;  // algorithmic: n^3 for the symmetric inverse, 2 n^2 for x0 = -K g (n <= 63: fits 32 bits for 16 k instances per warp)
   const int fo = q * PS + r;  // fragment offset: element (k = q, row/col = r)
 
   long long tclk = 0;
-  const bool clk = P.phase_cycles != nullptr;
+  constexpr bool clk = CLK;
   if (clk) tclk = clock64();
 #define INV_TICK(PH)                                                                    \
   if (clk) {                                                                            \
@@ -88,8 +88,7 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
     const int nc = hdr[0];
     if (hdr[1] != CMPC_ST_SOLVED) continue;
     const int n = 3 * nc, nblk = (n + 7) >> 3;
-    const double scale = slot[P.qws_goff + 2 * P.nmax];
-    flops_acc += (double)n * n * n + 2.0 * (double)n * n;
+    flops_acc += (unsigned)(n * n * (n + 2));
     double t[36][2];
 #pragma unroll
     for (int k = 0; k < 36; k++) {
@@ -115,47 +114,48 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
 #undef INV_HEAD
       __syncwarp();
       INV_TICK(CMPC_PH_WAIT)
-      // 2. M = -D^-1 C: the two k-steps of a tile are issued eight DMMAs apart
+      // 2. M = -D^-1 C: the two k-steps of a tile are issued four DMMAs apart
       {
         const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
-        double mt[8][2];
 #pragma unroll
-        for (int J = 0; J < 8; J++) {
-          mt[J][0] = 0.0;
-          mt[J][1] = 0.0;
-          dmma884(mt[J][0], mt[J][1], a0, pan[fo + 8 * J]);
-        }
+        for (int half = 0; half < 2; half++) {  // four tiles at a time: the accumulators share the register file with all 36 tiles
+          double mt[4][2];
 #pragma unroll
-        for (int J = 0; J < 8; J++) {
-          dmma884(mt[J][0], mt[J][1], a1, pan[fo + 4 * PS + 8 * J]);
-          *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(mt[J][0], mt[J][1]);
+          for (int J = 0; J < 4; J++) {
+            mt[J][0] = 0.0;
+            mt[J][1] = 0.0;
+            dmma884(mt[J][0], mt[J][1], a0, pan[fo + 8 * (4 * half + J)]);
+          }
+#pragma unroll
+          for (int J = 0; J < 4; J++) {
+            dmma884(mt[J][0], mt[J][1], a1, pan[fo + 4 * PS + 8 * (4 * half + J)]);
+            *reinterpret_cast<double2*>(mm + r * PS + 8 * (4 * half + J) + 2 * q) = make_double2(mt[J][0], mt[J][1]);
+          }
         }
       }
       __syncwarp();
       INV_TICK(CMPC_PH_ADAPT)
       // 3. every tile (I, J) += C_I' M_J: 72 independent DMMAs, the two k-steps of a tile 36 DMMAs apart
       {
-        double mf[8][2], pf[8][2];
+        // J-major: the eight A fragments of a k-step stay in registers, the B fragments stream from shared memory
 #pragma unroll
-        for (int J = 0; J < 8; J++) {
-          mf[J][0] = mm[fo + 8 * J];
-          mf[J][1] = mm[fo + 4 * PS + 8 * J];
-          pf[J][0] = pan[fo + 8 * J];
-          pf[J][1] = pan[fo + 4 * PS + 8 * J];
+        for (int ks = 0; ks < 2; ks++) {
+          double pf[8];
+#pragma unroll
+          for (int I = 0; I < 8; I++) pf[I] = pan[fo + 4 * PS * ks + 8 * I];
+#pragma unroll
+          for (int J = 0; J < 8; J++) {
+            const double mj = mm[fo + 4 * PS * ks + 8 * J];
+#pragma unroll
+            for (int I = J; I < 8; I++) dmma884(t[tix(I, J)][0], t[tix(I, J)][1], pf[I], mj);
+          }
         }
-#pragma unroll
-        for (int I = 0; I < 8; I++)
-#pragma unroll
-          for (int J = 0; J <= I; J++) dmma884(t[tix(I, J)][0], t[tix(I, J)][1], pf[I][0], mf[J][0]);
-#pragma unroll
-        for (int I = 0; I < 8; I++)
-#pragma unroll
-          for (int J = 0; J <= I; J++) dmma884(t[tix(I, J)][0], t[tix(I, J)][1], pf[I][1], mf[J][1]);
         __syncwarp();  // every lane is done with dv, pan and mm of this step
       }
       INV_TICK(CMPC_PH_SWEEP)
     }
     // K_ij = -(A_ij - 2 d_ij) scale in place; x0 = -scale A[63][:]
+    const double scale = slot[P.qws_goff + 2 * P.nmax];
 #pragma unroll
     for (int I = 0; I < 8; I++)
 #pragma unroll
@@ -175,5 +175,5 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
     INV_TICK(CMPC_PH_LOAD)
   }
 #undef INV_TICK
-  if (lane == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_INVERT, (unsigned long long)flops_acc);
+  if (lane == 0 && P.flops && flops_acc) atomicAdd(P.flops + CMPC_K_INVERT, (unsigned long long)flops_acc);
 }

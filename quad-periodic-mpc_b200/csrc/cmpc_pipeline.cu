@@ -11,6 +11,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <cstdlib>
 
 #include "cmpc_device.h"
 
@@ -141,21 +144,40 @@ int cmpc_launch_dual(const CmpcParams& P, int wpc, int grid, void* stream) {
   }
 }
 
-// ---- inversion kernel of the n <= 63 path (cmpc_invert_mma.cuh): one warp per CTA, 200 registers ----
-int cmpc_invert_max_ctas_per_sm(void) {
+// ---- inversion kernel of the n <= 63 path (cmpc_invert_mma.cuh): one warp per CTA; the register cap decides how
+//      many instances an SM sub-partition holds (16384 registers each): 200 -> two, 168 -> three ----
+namespace {
+int inv_regs() {
+  static int v = [] {
+    const char* e = std::getenv("CMPC_INV_REGS");
+    const int x = e ? std::atoi(e) : 168;
+    return x >= 184 ? 200 : 168;
+  }();
+  return v;
+}
+template <int REGS, bool CLK>
+int occ_invert_t() {
   int nb = 0;
   const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
-  if (cudaFuncSetAttribute(cmpc_invert_mma_kernel<200>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_invert_mma_kernel<200>, 32 * INV_WPC, smem) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(cmpc_invert_mma_kernel<REGS, CLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_invert_mma_kernel<REGS, CLK>, 32 * INV_WPC, smem) != cudaSuccess) return -1;
   return nb;
 }
+template <int REGS, bool CLK>
+int launch_invert_t(const CmpcParams& P, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
+  cudaError_t e = cudaFuncSetAttribute(cmpc_invert_mma_kernel<REGS, CLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cmpc_invert_mma_kernel<REGS, CLK><<<grid, 32 * INV_WPC, smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+int cmpc_invert_max_ctas_per_sm(void) { return inv_regs() == 200 ? occ_invert_t<200, false>() : occ_invert_t<168, false>(); }
 int cmpc_invert_instances_per_cta(void) { return INV_WPC; }
 int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
-  const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
-  cudaError_t e = cudaFuncSetAttribute(cmpc_invert_mma_kernel<200>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  cmpc_invert_mma_kernel<200><<<grid, 32 * INV_WPC, smem, (cudaStream_t)stream>>>(P);
-  return (int)cudaGetLastError();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (P.phase_cycles) return inv_regs() == 200 ? launch_invert_t<200, true>(P, grid, st) : launch_invert_t<168, true>(P, grid, st);
+  return inv_regs() == 200 ? launch_invert_t<200, false>(P, grid, st) : launch_invert_t<168, false>(P, grid, st);
 }
 
 // ---- fast tier of the dual active-set kernel (cmpc_dual_fast.cuh): working sets of up to 32 rows ----
