@@ -130,6 +130,13 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count);
 int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out);
 /* upload + solve + download: the end-to-end call with host buffers. */
 int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const cmpc_outputs* out);
+/* The same call for a caller that reuses its arrays (a controller loop): bind them once — which arrays are pinned
+ * is looked up here, not on every call — then solve `count` instances from / into the bound arrays.  With pinned
+ * inputs the device reads the arrays itself and packs the records; outputs are written by the kernels straight into
+ * host memory (the bound arrays if pinned, pinned staging otherwise).  The arrays must stay allocated and keep their
+ * pinning while bound; bind (NULL, NULL) to drop the binding. */
+int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_outputs* out);
+int cmpc_batch_solve_bound(cmpc_batch* b, int count);
 int cmpc_batch_sync(cmpc_batch* b);
 /* Pin a caller-owned host array (cudaHostRegister): cmpc_batch_solve_host / cmpc_batch_download copy results
  * straight into pinned output arrays instead of staging them.  Unregister before freeing the array. */

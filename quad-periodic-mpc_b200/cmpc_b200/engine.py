@@ -42,6 +42,8 @@ def lib():
         L.cmpc_batch_sync.argtypes = [C.c_void_p]
         L.cmpc_batch_download.argtypes = [C.c_void_p, C.POINTER(Outputs)]
         L.cmpc_batch_solve_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(Outputs)]
+        L.cmpc_batch_bind_host.argtypes = [C.c_void_p, C.POINTER(Inputs), C.POINTER(Outputs)]
+        L.cmpc_batch_solve_bound.argtypes = [C.c_void_p, C.c_int]
         L.cmpc_batch_upload_disturbance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.cmpc_batch_download_disturbance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cmpc_batch_set_count.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -206,17 +208,21 @@ class Batch:
                     pinned.append(a)
         self._prepared = (count, s, o, res)
         self._prepared_inputs = self._keep   # later uploads rebind self._keep; these arrays stay alive with the binding
+        _check(lib().cmpc_batch_bind_host(self._h, C.byref(s), C.byref(o)), "cmpc_batch_bind_host")
         self._pinned = pinned
         return res
 
     def release_prepared(self):
+        if getattr(self, "_prepared", None) is not None and self._h:
+            lib().cmpc_batch_bind_host(self._h, None, None)
+            self._prepared = None
         for a in getattr(self, "_pinned", []):
             lib().cmpc_host_unregister(a.ctypes.data)
         self._pinned = []
 
     def solve_prepared(self):
         count, s, o, res = self._prepared
-        _check(lib().cmpc_batch_solve_host(self._h, count, C.byref(s), C.byref(o)), "cmpc_batch_solve_host")
+        _check(lib().cmpc_batch_solve_bound(self._h, count), "cmpc_batch_solve_bound")
         self.count = count
         return res
 

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -165,6 +166,40 @@ class HostPool {
 
 }  // namespace
 
+namespace {
+// Launch plan of the pipeline for one (reduced size bound, horizon, adaptive) combination: kernel shapes, shared
+// memory, CTAs per SM.  The occupancy queries behind it cost tens of microseconds, so a batch keeps its plans.
+struct PipePlan {
+  int nmax = 0, h = 0, adapt = 0;
+  int cshape = 0, tiled = 0;
+  size_t slot = 0;
+  int chunk_cap = 0;  // instances whose workspace stays L2-sized
+  int per_sm1 = 0, per_sm_inv = 0;
+  int qcap1 = 0, fast = 0, per_sm_fast = 0, wpc1 = 0, per_sm2 = 0, wpc2 = 0, per_sm3 = 0;
+};
+
+}  // namespace
+
+namespace {
+struct SoaView {
+  const char* p[11];
+  bool ok;
+};
+
+// What the end-to-end call needs to know about the caller's arrays; resolving it costs a cudaPointerGetAttributes
+// per array, so cmpc_batch_bind_host keeps it across calls.
+struct HostBinding {
+  cmpc_inputs in;
+  cmpc_outputs out;
+  SoaView soa;     // device views of the input arrays (ok: every one pinned)
+  int direct = 0;  // output arrays that are pinned (kOut* bits)
+  void* vo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // device views the kernels write outputs through (zero-copy)
+  bool zc_out = true;
+  bool valid = false;
+};
+
+}  // namespace
+
 struct cmpc_batch {
   int device = 0;
   int capacity = 0;
@@ -211,6 +246,8 @@ struct cmpc_batch {
   size_t qws_bytes[kMaxStreams] = {};
   int* d_sched[kMaxStreams] = {};
   int sched_ints[kMaxStreams] = {};
+  std::vector<PipePlan> plans;        // launch plans by (reduced size bound, horizon, adaptive)
+  HostBinding bound;                  // cmpc_batch_bind_host
   // adaptive stage
   double* d_twiddle = nullptr;
   float* d_gk = nullptr;
@@ -324,10 +361,6 @@ const void* device_view(const void* p) {
 
 // The eleven input arrays as device-accessible pointers when every one of them is pinned (and word aligned):
 // the end-to-end call then packs the records on the device (cmpc_pack.cu) instead of on the host.
-struct SoaView {
-  const char* p[11];
-  bool ok;
-};
 SoaView soa_view(const cmpc_inputs* in) {
   SoaView s;
   const void* src[11] = {in->p, in->v, in->q, in->w, in->r, in->weights, in->traj, in->alpha, in->gait, in->x_drag, in->f_dist};
@@ -414,21 +447,86 @@ int fork_streams(cmpc_batch* b, int only = -1) {
 // Two-kernel pipeline (cmpc_pipeline.cu) over the instances P describes, in chunks whose workspace stays
 // L2-sized: condensation + K = H^-1 (one CTA per instance), then the dual active set (one warp per
 // instance) with a small working-set capacity, then the few instances that outgrew it at full capacity.
-int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
-  cudaStream_t st = b->stream[si];
+int make_pipe_plan(const CmpcParams& P, PipePlan& pl) {
   const bool adapt = P.adapt_mode >= 0;
   const int nmax = P.nmax;
+  pl.nmax = nmax;
+  pl.h = P.horizon;
+  pl.adapt = adapt;
   int cshape = nmax < 64 ? CMPC_CSHAPE_MMA64 : (nmax <= 96 ? CMPC_CSHAPE_96 : CMPC_CSHAPE_128);
   if (const char* e = std::getenv("CMPC_CSHAPE")) {  // experiments: force a shape that still fits
     const int sh = std::atoi(e);
     if ((sh == CMPC_CSHAPE_64 && nmax <= 64) || (sh == CMPC_CSHAPE_96 && nmax <= 96) || sh == CMPC_CSHAPE_128) cshape = sh;
   }
-  const int tiled = (cshape == CMPC_CSHAPE_MMA64) ? 1 : 0;
-  const size_t slot = cmpc_qws_slot_doubles(nmax, tiled);
+  pl.cshape = cshape;
+  pl.tiled = (cshape == CMPC_CSHAPE_MMA64) ? 1 : 0;
+  pl.slot = cmpc_qws_slot_doubles(nmax, pl.tiled);
   size_t budget = 160;
   if (const char* e = std::getenv("CMPC_WS_MB")) budget = (size_t)std::max(1, std::atoi(e));
   budget <<= 20;
-  int chunk = (int)std::min<size_t>((size_t)count, std::max<size_t>(1, budget / (slot * sizeof(double))));
+  pl.chunk_cap = (int)std::max<size_t>(1, budget / (pl.slot * sizeof(double)));
+  // kernel 1
+  const size_t smem1 = cmpc_condense_smem_bytes(P.horizon, nmax, cshape, adapt);
+  pl.per_sm1 = cmpc_condense_max_ctas_per_sm(cshape, smem1, adapt);
+  if (pl.per_sm1 < 1) {
+    g_err = "cmpc_batch_solve: condensation kernel not launchable on this device (no sm_100a image?)";
+    return CMPC_E_NODEVICE;
+  }
+  pl.per_sm_inv = pl.tiled ? cmpc_invert_max_ctas_per_sm() : 1;
+  if (pl.per_sm_inv < 1) {
+    g_err = "cmpc_batch_solve: inversion kernel not launchable on this device (no sm_100a image?)";
+    return CMPC_E_NODEVICE;
+  }
+  // kernel 2, two working-set capacity tiers
+  int qcap1 = 32;
+  if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
+  if (qcap1 < 1 || qcap1 > nmax) qcap1 = nmax;
+  bool fast = qcap1 <= 32;  // tier 1 on the register-resident kernel (cmpc_dual_fast.cuh)
+  if (const char* e = std::getenv("CMPC_DUAL")) fast = fast && std::strcmp(e, "generic") != 0;
+  if (fast) {
+    pl.per_sm_fast = cmpc_dual_fast_max_ctas_per_sm(nmax, cmpc_dual_fast_smem_bytes(nmax, qcap1));
+    if (pl.per_sm_fast < 1) fast = false;
+  }
+  int wpc1 = 4;
+  if (const char* e = std::getenv("CMPC_WPC")) wpc1 = std::atoi(e);
+  if (wpc1 != 1 && wpc1 != 2 && wpc1 != 4 && wpc1 != 8) wpc1 = 4;
+  const size_t smax = 227 * 1024;
+  while (wpc1 > 1 && cmpc_dual_smem_bytes_per_warp(nmax, qcap1) * wpc1 > smax) wpc1 >>= 1;
+  pl.per_sm2 = cmpc_dual_max_ctas_per_sm(wpc1, cmpc_dual_smem_bytes_per_warp(nmax, qcap1) * wpc1);
+  int wpc2 = 4;
+  while (wpc2 > 1 && cmpc_dual_smem_bytes_per_warp(nmax, nmax) * wpc2 > 100 * 1024) wpc2 >>= 1;
+  pl.per_sm3 = cmpc_dual_max_ctas_per_sm(wpc2, cmpc_dual_smem_bytes_per_warp(nmax, nmax) * wpc2);
+  if (pl.per_sm2 < 1 || pl.per_sm3 < 1) {
+    g_err = "cmpc_batch_solve: active-set kernel not launchable on this device (no sm_100a image?)";
+    return CMPC_E_NODEVICE;
+  }
+  pl.qcap1 = qcap1;
+  pl.fast = fast ? 1 : 0;
+  pl.wpc1 = wpc1;
+  pl.wpc2 = wpc2;
+  return CMPC_OK;
+}
+
+int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
+  cudaStream_t st = b->stream[si];
+  const bool adapt = P.adapt_mode >= 0;
+  const int nmax = P.nmax;
+  const PipePlan* plp = nullptr;
+  for (const PipePlan& c : b->plans)
+    if (c.nmax == nmax && c.h == P.horizon && c.adapt == (int)adapt) plp = &c;
+  if (!plp) {
+    PipePlan pl;
+    if (int e = make_pipe_plan(P, pl)) return e;
+    b->plans.push_back(pl);
+    plp = &b->plans.back();
+  }
+  const PipePlan& pl = *plp;
+  const int cshape = pl.cshape, tiled = pl.tiled;
+  const size_t slot = pl.slot;
+  const int per_sm1 = pl.per_sm1, per_sm_inv = pl.per_sm_inv, qcap1 = pl.qcap1, per_sm_fast = pl.per_sm_fast;
+  const int wpc1 = pl.wpc1, per_sm2 = pl.per_sm2, wpc2 = pl.wpc2, per_sm3 = pl.per_sm3;
+  const bool fast = pl.fast != 0;
+  const int chunk = std::min(count, pl.chunk_cap);
   const int nchunks = (count + chunk - 1) / chunk;
   const size_t need = (size_t)chunk * slot * sizeof(double);
   if (need > b->qws_bytes[si] || 4 * nchunks > b->sched_ints[si]) {
@@ -450,42 +548,6 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     }
   }
   CK(cudaMemsetAsync(b->d_sched[si], 0, sizeof(int) * 4 * nchunks, st));
-  // kernel 1
-  const size_t smem1 = cmpc_condense_smem_bytes(P.horizon, nmax, cshape, adapt);
-  const int per_sm1 = cmpc_condense_max_ctas_per_sm(cshape, smem1, adapt);
-  if (per_sm1 < 1) {
-    g_err = "cmpc_batch_solve: condensation kernel not launchable on this device (no sm_100a image?)";
-    return CMPC_E_NODEVICE;
-  }
-  const int per_sm_inv = tiled ? cmpc_invert_max_ctas_per_sm() : 1;
-  if (per_sm_inv < 1) {
-    g_err = "cmpc_batch_solve: inversion kernel not launchable on this device (no sm_100a image?)";
-    return CMPC_E_NODEVICE;
-  }
-  // kernel 2, two working-set capacity tiers
-  int qcap1 = 32;
-  if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
-  if (qcap1 < 1 || qcap1 > nmax) qcap1 = nmax;
-  bool fast = qcap1 <= 32;  // tier 1 on the register-resident kernel (cmpc_dual_fast.cuh)
-  if (const char* e = std::getenv("CMPC_DUAL")) fast = fast && std::strcmp(e, "generic") != 0;
-  int per_sm_fast = 0;
-  if (fast) {
-    per_sm_fast = cmpc_dual_fast_max_ctas_per_sm(nmax, cmpc_dual_fast_smem_bytes(nmax, qcap1));
-    if (per_sm_fast < 1) fast = false;
-  }
-  int wpc1 = 4;
-  if (const char* e = std::getenv("CMPC_WPC")) wpc1 = std::atoi(e);
-  if (wpc1 != 1 && wpc1 != 2 && wpc1 != 4 && wpc1 != 8) wpc1 = 4;
-  const size_t smax = 227 * 1024;
-  while (wpc1 > 1 && cmpc_dual_smem_bytes_per_warp(nmax, qcap1) * wpc1 > smax) wpc1 >>= 1;
-  const int per_sm2 = cmpc_dual_max_ctas_per_sm(wpc1, cmpc_dual_smem_bytes_per_warp(nmax, qcap1) * wpc1);
-  int wpc2 = 4;
-  while (wpc2 > 1 && cmpc_dual_smem_bytes_per_warp(nmax, nmax) * wpc2 > 100 * 1024) wpc2 >>= 1;
-  const int per_sm3 = cmpc_dual_max_ctas_per_sm(wpc2, cmpc_dual_smem_bytes_per_warp(nmax, nmax) * wpc2);
-  if (per_sm2 < 1 || per_sm3 < 1) {
-    g_err = "cmpc_batch_solve: active-set kernel not launchable on this device (no sm_100a image?)";
-    return CMPC_E_NODEVICE;
-  }
   const CmpcParams base = P;
   // cmpc_batch_profile_range: CUDA events between the kernel classes (the stream is drained per class)
   auto prof_begin = [&]() -> int {
@@ -933,51 +995,68 @@ int cmpc_batch_download(cmpc_batch* b, const cmpc_outputs* out) {
 // them straight into host memory over PCIe as instances finish (the caller's arrays if pinned, else pinned staging
 // that is copied out here), so no device-to-host copy waits behind the last kernel.  CMPC_D2H_COPY=1 restores
 // device-side outputs + cudaMemcpyAsync.
-int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const cmpc_outputs* out) {
-  int rc = check_inputs(b, count, in, "cmpc_batch_solve_host");
-  if (rc) return rc;
-  if (!out) return fail_arg("cmpc_batch_solve_host: null outputs");
+static int resolve_binding(cmpc_batch* b, const cmpc_inputs* in, const cmpc_outputs* out, HostBinding& hb) {
+  hb.in = *in;
+  hb.out = *out;
+  hb.direct = direct_mask(out);
+  // pinned input arrays are read by the device itself (cmpc_pack.cu); pageable ones are packed into pinned records on the host
+  hb.soa = soa_view(in);
+  if (const char* e = std::getenv("CMPC_HOST_PACK")) hb.soa.ok = hb.soa.ok && std::atoi(e) == 0;
+  hb.zc_out = true;
+  if (const char* e = std::getenv("CMPC_D2H_COPY")) hb.zc_out = std::atoi(e) == 0;
+  for (int i = 0; i < 5; i++) hb.vo[i] = nullptr;
+  if (hb.zc_out) {
+    auto view = [&](void* user, void* staging, int bit) -> void* {
+      if (!user) return nullptr;
+      return const_cast<void*>(device_view((hb.direct & bit) ? user : staging));
+    };
+    hb.vo[0] = view(out->forces, b->h_forces, kOutForces);
+    hb.vo[1] = view(out->objective, b->h_obj, kOutObj);
+    hb.vo[2] = view(out->status, b->h_status, kOutStatus);
+    hb.vo[3] = view(out->iterations, b->h_iters, kOutIters);
+    hb.vo[4] = view(out->active, b->h_active, kOutActive);
+  }
+  hb.valid = true;
+  return CMPC_OK;
+}
+
+static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
+  static const bool trace = std::getenv("CMPC_TRACE") != nullptr;
+  static double tr_enq = 0, tr_wait = 0, tr_scan = 0, tr_pack = 0, tr_pipe = 0;
+  static int tr_n = 0;
+  const auto tr0 = std::chrono::steady_clock::now();
+  const cmpc_inputs* in = &hb.in;
+  const cmpc_outputs* out = &hb.out;
+  int rc = CMPC_OK;
   CK(cudaSetDevice(b->device));
   int nchunks = 1;
   if (const char* e = std::getenv("CMPC_CHUNKS")) nchunks = std::atoi(e);
   else if (count >= 2048) nchunks = std::min(kMaxChunks, std::max(2, count / 16384));  // measured: scripts/e2e_probe.py
   nchunks = std::max(1, std::min(nchunks, kMaxChunks));
-  const int direct = direct_mask(out);
-  // pinned input arrays are read by the device itself (cmpc_pack.cu); pageable ones are packed into pinned records here
-  SoaView soa = soa_view(in);
-  if (const char* e = std::getenv("CMPC_HOST_PACK")) soa.ok = soa.ok && std::atoi(e) == 0;
+  const int direct = hb.direct;
+  const SoaView& soa = hb.soa;
+  const bool zc_out = hb.zc_out;
+  void* const* vo = hb.vo;
   const int per = (count + nchunks - 1) / nchunks;
   { int rcs = sync_aux(b); if (rcs) return rcs; }
   CK(cudaEventRecord(b->ev0, b->stream[0]));
   b->count = count;
   int maxc_all = 0, used = 0;
   const int h = b->h;
-  bool zc_out = true;
-  if (const char* e = std::getenv("CMPC_D2H_COPY")) zc_out = std::atoi(e) == 0;
   struct OutGuard {  // the overrides only live for this call
     cmpc_batch* b;
     ~OutGuard() { b->o_forces = nullptr; b->o_obj = nullptr; b->o_status = nullptr; b->o_iters = nullptr; b->o_active = nullptr; }
   } guard{b};
-  void* vo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  if (zc_out) {
-    auto view = [&](void* user, void* staging, int bit) -> void* {
-      if (!user) return nullptr;
-      return const_cast<void*>(device_view((direct & bit) ? user : staging));
-    };
-    vo[0] = view(out->forces, b->h_forces, kOutForces);
-    vo[1] = view(out->objective, b->h_obj, kOutObj);
-    vo[2] = view(out->status, b->h_status, kOutStatus);
-    vo[3] = view(out->iterations, b->h_iters, kOutIters);
-    vo[4] = view(out->active, b->h_active, kOutActive);
-  }
   for (int c = 0; c < nchunks; c++) {
     const int first = c * per, n = std::min(per, count - first);
     if (n <= 0) break;
     const int si = c & 1;
     cudaStream_t st = b->stream[si];
     int maxc;
+    const auto tq0 = std::chrono::steady_clock::now();
     if (soa.ok) {
       maxc = max_contact_scan(b, in->gait, first, n);
+      if (trace) tr_scan += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
       const size_t f = (size_t)first;
       auto at = [&](int i, size_t bytes_per_instance) -> const void* { return soa.p[i] ? soa.p[i] + f * bytes_per_instance : nullptr; };
       const int rcp = cmpc_launch_pack(at(0, 12), at(1, 12), at(2, 16), at(3, 12), at(4, 48), at(5, 48), at(6, 48 * (size_t)h),
@@ -999,8 +1078,13 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
     b->o_status = zc ? static_cast<int*>(vo[2]) : nullptr;
     b->o_iters = zc ? static_cast<int*>(vo[3]) : nullptr;
     b->o_active = zc ? static_cast<signed char*>(vo[4]) : nullptr;
+    const auto tq1 = std::chrono::steady_clock::now();
     rc = launch_range(b, first, n, maxc, si);
     if (rc) return rc;
+    if (trace) {
+      tr_pack += std::chrono::duration<double, std::micro>(tq1 - tq0).count();
+      tr_pipe += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq1).count();
+    }
     if (!zc) {
       rc = enqueue_d2h(b, out, first, n, st, direct);
       if (rc) return rc;
@@ -1009,6 +1093,7 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
     used = c + 1;
   }
   b->max_contact = maxc_all;
+  const auto tr1 = std::chrono::steady_clock::now();
   for (int c = 0; c < used; c++) {
     const int first = c * per, n = std::min(per, count - first);
     CK(cudaEventSynchronize(b->chunk_done[c]));
@@ -1017,7 +1102,50 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
   CK(cudaStreamWaitEvent(b->stream[0], b->chunk_done[used > 0 ? used - 1 : 0], 0));
   CK(cudaEventRecord(b->ev1, b->stream[0]));
   b->timed = true;
+  if (trace) {
+    const auto tr2 = std::chrono::steady_clock::now();
+    tr_enq += std::chrono::duration<double, std::micro>(tr1 - tr0).count();
+    tr_wait += std::chrono::duration<double, std::micro>(tr2 - tr1).count();
+    if (++tr_n == 50) {
+      std::fprintf(stderr, "[cmpc] solve_host: enqueue %.1f us (gait scan %.1f, scan + pack launch %.1f, pipeline launches %.1f), wait %.1f us per call\n",
+                   tr_enq / tr_n, tr_scan / tr_n, tr_pack / tr_n, tr_pipe / tr_n, tr_wait / tr_n);
+      tr_enq = tr_wait = tr_scan = tr_pack = tr_pipe = 0;
+      tr_n = 0;
+    }
+  }
   return CMPC_OK;
+}
+
+int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const cmpc_outputs* out) {
+  int rc = check_inputs(b, count, in, "cmpc_batch_solve_host");
+  if (rc) return rc;
+  if (!out) return fail_arg("cmpc_batch_solve_host: null outputs");
+  CK(cudaSetDevice(b->device));
+  HostBinding hb;
+  rc = resolve_binding(b, in, out, hb);
+  if (rc) return rc;
+  return solve_host_core(b, count, hb);
+}
+
+int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_outputs* out) {
+  if (!b) return fail_arg("cmpc_batch_bind_host: null batch");
+  if (!in && !out) {
+    b->bound.valid = false;
+    return CMPC_OK;
+  }
+  int rc = check_inputs(b, 0, in, "cmpc_batch_bind_host");
+  if (rc) return rc;
+  if (!out) return fail_arg("cmpc_batch_bind_host: null outputs");
+  CK(cudaSetDevice(b->device));
+  return resolve_binding(b, in, out, b->bound);
+}
+
+int cmpc_batch_solve_bound(cmpc_batch* b, int count) {
+  if (!b) return fail_arg("cmpc_batch_solve_bound: null batch");
+  if (!b->bound.valid) { g_err = "cmpc_batch_solve_bound: call cmpc_batch_bind_host first"; return CMPC_E_STATE; }
+  if (!b->is_setup) { g_err = "cmpc_batch_solve_bound: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  if (count < 0 || count > b->capacity) return fail_arg("cmpc_batch_solve_bound: count exceeds capacity");
+  return solve_host_core(b, count, b->bound);
 }
 
 int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows_t, const float* windows_d,

@@ -31,10 +31,28 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 namespace {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize of kernel K is raised when a launch (or an occupancy query) needs
+// more than was set so far on the device, not on every launch
+template <auto K>
+struct SmemAttr {
+  static size_t have[16];  // per device: bytes set + 1
+};
+template <auto K>
+size_t SmemAttr<K>::have[16] = {};
+template <auto K>
+cudaError_t smem_attr(size_t smem) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& have = SmemAttr<K>::have[dev & 15];
+  if (have >= smem + 1) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) have = smem + 1;
+  return e;
+}
+
 template <class S, bool ADAPT>
 int launch_condense_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e =
-      cudaFuncSetAttribute(cmpc_condense_kernel<S, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr<cmpc_condense_kernel<S, ADAPT>>(smem);
   if (e != cudaSuccess) return (int)e;
   cmpc_condense_kernel<S, ADAPT><<<grid, S::NT, smem, st>>>(P);
   return (int)cudaGetLastError();
@@ -42,7 +60,7 @@ int launch_condense_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t s
 template <class S, bool ADAPT>
 int occ_condense_t(size_t smem) {
   int nb = 0;
-  if (cudaFuncSetAttribute(cmpc_condense_kernel<S, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+  if (smem_attr<cmpc_condense_kernel<S, ADAPT>>(smem) !=
       cudaSuccess)
     return -1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_condense_kernel<S, ADAPT>, S::NT, smem) != cudaSuccess)
@@ -51,8 +69,7 @@ int occ_condense_t(size_t smem) {
 }
 template <bool ADAPT, int MINB>
 int launch_mma_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cmpc_assemble_mma_kernel<ADAPT, MINB>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr<cmpc_assemble_mma_kernel<ADAPT, MINB>>(smem);
   if (e != cudaSuccess) return (int)e;
   cmpc_assemble_mma_kernel<ADAPT, MINB><<<grid, MMA_NT, smem, st>>>(P);
   return (int)cudaGetLastError();
@@ -60,8 +77,7 @@ int launch_mma_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
 template <bool ADAPT, int MINB>
 int occ_mma_t(size_t smem) {
   int nb = 0;
-  if (cudaFuncSetAttribute(cmpc_assemble_mma_kernel<ADAPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem) != cudaSuccess)
+  if (smem_attr<cmpc_assemble_mma_kernel<ADAPT, MINB>>(smem) != cudaSuccess)
     return -1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_assemble_mma_kernel<ADAPT, MINB>, MMA_NT, smem) !=
       cudaSuccess)
@@ -78,7 +94,7 @@ int cnpad_of(int cshape) {
 
 template <int WPC>
 int launch_dual_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cmpc_dual_kernel<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr<cmpc_dual_kernel<WPC>>(smem);
   if (e != cudaSuccess) return (int)e;
   cmpc_dual_kernel<WPC><<<grid, 32 * WPC, smem, st>>>(P);
   return (int)cudaGetLastError();
@@ -86,7 +102,7 @@ int launch_dual_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
 template <int WPC>
 int occ_dual_t(size_t smem) {
   int nb = 0;
-  if (cudaFuncSetAttribute(cmpc_dual_kernel<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (smem_attr<cmpc_dual_kernel<WPC>>(smem) != cudaSuccess)
     return -1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_dual_kernel<WPC>, 32 * WPC, smem) != cudaSuccess) return -1;
   return nb;
@@ -159,14 +175,14 @@ template <int REGS, bool CLK>
 int occ_invert_t() {
   int nb = 0;
   const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
-  if (cudaFuncSetAttribute(cmpc_invert_mma_kernel<REGS, CLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  if (smem_attr<cmpc_invert_mma_kernel<REGS, CLK>>(smem) != cudaSuccess) return -1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_invert_mma_kernel<REGS, CLK>, 32 * INV_WPC, smem) != cudaSuccess) return -1;
   return nb;
 }
 template <int REGS, bool CLK>
 int launch_invert_t(const CmpcParams& P, int grid, cudaStream_t st) {
   const size_t smem = (size_t)INV_WPC * INV_WARP_SMEM;
-  cudaError_t e = cudaFuncSetAttribute(cmpc_invert_mma_kernel<REGS, CLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr<cmpc_invert_mma_kernel<REGS, CLK>>(smem);
   if (e != cudaSuccess) return (int)e;
   cmpc_invert_mma_kernel<REGS, CLK><<<grid, 32 * INV_WPC, smem, st>>>(P);
   return (int)cudaGetLastError();
@@ -184,7 +200,7 @@ int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
 namespace {
 template <int NPL, int MPL>
 int launch_fast_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cmpc_dual_fast_kernel<1, NPL, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr<cmpc_dual_fast_kernel<1, NPL, MPL>>(smem);
   if (e != cudaSuccess) return (int)e;
   cmpc_dual_fast_kernel<1, NPL, MPL><<<grid, 32, smem, st>>>(P);
   return (int)cudaGetLastError();
@@ -192,7 +208,7 @@ int launch_fast_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
 template <int NPL, int MPL>
 int occ_fast_t(size_t smem) {
   int nb = 0;
-  if (cudaFuncSetAttribute(cmpc_dual_fast_kernel<1, NPL, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (smem_attr<cmpc_dual_fast_kernel<1, NPL, MPL>>(smem) != cudaSuccess)
     return -1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_dual_fast_kernel<1, NPL, MPL>, 32, smem) != cudaSuccess) return -1;
   return nb;
