@@ -95,6 +95,7 @@ void build_adapt_tables(std::vector<double>& tw, std::vector<float>& gk) {
 
 constexpr int kMaxChunks = 8;
 constexpr int kMaxStreams = 8;
+constexpr int kPackStream = 2;  // end-to-end call: the record-packing kernels of all chunks, in order
 
 // Small persistent worker pool for the host side of the end-to-end call (record packing, result unpacking):
 // parallel_for(n, fn) runs fn(i) for i in [0, n) on the workers and the calling thread.
@@ -209,6 +210,7 @@ struct cmpc_batch {
   int split = 1;                          // parts a solve_range call is cut into, one per stream in turn (CMPC_SPLIT)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, mark0 = nullptr, mark1 = nullptr;
   cudaEvent_t chunk_done[kMaxChunks] = {};
+  cudaEvent_t packed[kMaxChunks] = {};    // end-to-end call: chunk c's records are in HBM
   // successive solve_range calls alternate between the two streams so that the latency-bound tail of one
   // batch overlaps the next batch's kernels; these events carry the cross-stream ordering
   cudaEvent_t join_ev = nullptr;      // scratch: "stream i has reached this point"
@@ -393,7 +395,7 @@ int max_contact_scan(const cmpc_batch* b, const uint8_t* gait, int first, int n)
         std::memcpy(&x, g + k, 8);
         // bit 7 of every non-zero byte
         x = ((x & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | x;
-        c += __builtin_popcountll(x & 0x8080808080808080ull);
+        c += (int)((((x >> 7) & 0x0101010101010101ull) * 0x0101010101010101ull) >> 56);  // byte-wise sum of the flags
       }
     }
     for (; k < h4; k++) c += keep[g[k]];
@@ -788,6 +790,7 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaEventCreate(&b->mark0));
   CK(cudaEventCreate(&b->mark1));
   for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->chunk_done[i], cudaEventDisableTiming));
+  for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->packed[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&b->join_ev, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming));
   const size_t cap = (size_t)capacity;
@@ -830,6 +833,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFreeHost(b->h_active); cudaFreeHost(b->h_flops);
   cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->mark0); cudaEventDestroy(b->mark1);
   for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->chunk_done[i]);
+  for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->packed[i]);
   for (int i = 0; i < CMPC_K_COUNT + 1; i++) if (b->prof_ev[i]) cudaEventDestroy(b->prof_ev[i]);
   cudaEventDestroy(b->join_ev); cudaEventDestroy(b->fork_ev);
   for (int i = 0; i < kMaxStreams; i++) cudaStreamDestroy(b->stream[i]);
@@ -1023,6 +1027,7 @@ static int resolve_binding(cmpc_batch* b, const cmpc_inputs* in, const cmpc_outp
 static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
   static const bool trace = std::getenv("CMPC_TRACE") != nullptr;
   static double tr_enq = 0, tr_wait = 0, tr_scan = 0, tr_pack = 0, tr_pipe = 0;
+  static cudaEvent_t tr_ev[2 * kMaxChunks] = {};
   static int tr_n = 0;
   const auto tr0 = std::chrono::steady_clock::now();
   const cmpc_inputs* in = &hb.in;
@@ -1047,6 +1052,34 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
     cmpc_batch* b;
     ~OutGuard() { b->o_forces = nullptr; b->o_obj = nullptr; b->o_status = nullptr; b->o_iters = nullptr; b->o_active = nullptr; }
   } guard{b};
+  // Pinned inputs: every chunk's records are packed by the device first, chunk after chunk on a stream of their own
+  // (the reads are PCIe bound, and queued ahead of the solve kernels they find free SM slots); a chunk's solve
+  // waits for its own records only.
+  int chunk_maxc[kMaxChunks] = {};
+  if (soa.ok) {
+    cudaStream_t ps = b->stream[kPackStream];
+    CK(cudaStreamWaitEvent(ps, b->ev0, 0));
+    for (int c = 0; c < nchunks; c++) {
+      const int first = c * per, n = std::min(per, count - first);
+      if (n <= 0) break;
+      const auto tq0 = std::chrono::steady_clock::now();
+      chunk_maxc[c] = max_contact_scan(b, in->gait, first, n);
+      if (trace) tr_scan += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
+      const size_t f = (size_t)first;
+      auto at = [&](int i, size_t bytes_per_instance) -> const void* { return soa.p[i] ? soa.p[i] + f * bytes_per_instance : nullptr; };
+      const int rcp = cmpc_launch_pack(at(0, 12), at(1, 12), at(2, 16), at(3, 12), at(4, 48), at(5, 48), at(6, 48 * (size_t)h),
+                                       at(7, 4), at(8, 4 * (size_t)h), at(9, 4), at(10, 24),
+                                       b->d_rec + f * b->rec_stride, b->rec_stride, h, n, b->sm_count, ps);
+      if (rcp != 0) return fail_cuda((cudaError_t)rcp, "cmpc_pack_records_kernel launch");
+      b->launches++;
+      CK(cudaEventRecord(b->packed[c], ps));
+      if (trace) {
+        if (!tr_ev[0]) for (int i = 0; i < 2 * kMaxChunks; i++) cudaEventCreate(&tr_ev[i]);
+        CK(cudaEventRecord(tr_ev[2 * c], ps));
+        tr_pack += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
+      }
+    }
+  }
   for (int c = 0; c < nchunks; c++) {
     const int first = c * per, n = std::min(per, count - first);
     if (n <= 0) break;
@@ -1055,15 +1088,8 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
     int maxc;
     const auto tq0 = std::chrono::steady_clock::now();
     if (soa.ok) {
-      maxc = max_contact_scan(b, in->gait, first, n);
-      if (trace) tr_scan += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
-      const size_t f = (size_t)first;
-      auto at = [&](int i, size_t bytes_per_instance) -> const void* { return soa.p[i] ? soa.p[i] + f * bytes_per_instance : nullptr; };
-      const int rcp = cmpc_launch_pack(at(0, 12), at(1, 12), at(2, 16), at(3, 12), at(4, 48), at(5, 48), at(6, 48 * (size_t)h),
-                                       at(7, 4), at(8, 4 * (size_t)h), at(9, 4), at(10, 24),
-                                       b->d_rec + f * b->rec_stride, b->rec_stride, h, n, b->sm_count, st);
-      if (rcp != 0) return fail_cuda((cudaError_t)rcp, "cmpc_pack_records_kernel launch");
-      b->launches++;
+      maxc = chunk_maxc[c];
+      CK(cudaStreamWaitEvent(st, b->packed[c], 0));
     } else {
       maxc = pack_records_parallel(b, in, first, n);
       CK(cudaMemcpyAsync(b->d_rec + (size_t)first * b->rec_stride, b->h_rec + (size_t)first * b->rec_stride,
@@ -1082,7 +1108,7 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
     rc = launch_range(b, first, n, maxc, si);
     if (rc) return rc;
     if (trace) {
-      tr_pack += std::chrono::duration<double, std::micro>(tq1 - tq0).count();
+      if (!soa.ok) tr_pack += std::chrono::duration<double, std::micro>(tq1 - tq0).count();
       tr_pipe += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq1).count();
     }
     if (!zc) {
@@ -1090,6 +1116,7 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
       if (rc) return rc;
     }
     CK(cudaEventRecord(b->chunk_done[c], st));
+    if (trace && tr_ev[0]) CK(cudaEventRecord(tr_ev[2 * c + 1], st));
     used = c + 1;
   }
   b->max_contact = maxc_all;
@@ -1106,6 +1133,14 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
     const auto tr2 = std::chrono::steady_clock::now();
     tr_enq += std::chrono::duration<double, std::micro>(tr1 - tr0).count();
     tr_wait += std::chrono::duration<double, std::micro>(tr2 - tr1).count();
+    if (tr_n == 49 && tr_ev[0] && soa.ok) {
+      for (int c = 0; c < used; c++) {
+        float a = 0.f, d = 0.f;
+        cudaEventElapsedTime(&a, b->ev0, tr_ev[2 * c]);
+        cudaEventElapsedTime(&d, b->ev0, tr_ev[2 * c + 1]);
+        std::fprintf(stderr, "[cmpc]   chunk %d: records packed at %.1f us, solved at %.1f us after the call's first event\n", c, 1e3 * a, 1e3 * d);
+      }
+    }
     if (++tr_n == 50) {
       std::fprintf(stderr, "[cmpc] solve_host: enqueue %.1f us (gait scan %.1f, scan + pack launch %.1f, pipeline launches %.1f), wait %.1f us per call\n",
                    tr_enq / tr_n, tr_scan / tr_n, tr_pack / tr_n, tr_pipe / tr_n, tr_wait / tr_n);

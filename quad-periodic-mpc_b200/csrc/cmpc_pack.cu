@@ -83,7 +83,7 @@ int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w,
   A.tail_words = A.rec_words - A.tail_dst;
   const long long words = (long long)count * (12 * h);
   int grid = (int)((words + 255) / 256);
-  if (grid > sm_count * 8) grid = sm_count * 8;
+  if (grid > sm_count * 2) grid = sm_count * 2;  // few, fat CTAs: they also have to find room beside resident solve kernels
   if (grid < 1) grid = 1;
   cmpc_pack_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
   return (int)cudaGetLastError();
