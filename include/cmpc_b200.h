@@ -143,6 +143,78 @@ int cmpc_batch_sync(cmpc_batch* b);
 int cmpc_host_register(void* ptr, size_t bytes);
 int cmpc_host_unregister(void* ptr);
 
+/* ------------------------------------------------------------------------
+ * 2b. the caller of the path on the device: ConvexMPCLocomotion::updateMPCIfNeeded + solveDenseMPC
+ *     (ConvexMPCLocomotion.cpp:511-870) and the gait's getMpcTable (Gait.cpp:158-215) for a whole batch.
+ *     One cmpc_command per robot carries what those functions read from the state estimator, the command,
+ *     the gait object and the /log_data message; the device builds the reference trajectory, the contact
+ *     table, r = pFoot - p, the f_ext residual and the x_drag integral, pushes (simulation_time, f_ext[3])
+ *     into the instance's disturbance history (SolverMPC.cpp:688-700), solves, and returns what
+ *     solveDenseMPC leaves behind: Fr_des, f_ff = -rBody f, and the updated command state.
+ * ---------------------------------------------------------------------- */
+enum { CMPC_GAIT_OFFSET_DURATION = 0, CMPC_GAIT_MIXED_FREQUENCY = 1 };
+
+typedef struct {
+  /* StateEstimate<float> (stateEstimator->getResult()) */
+  float position[3];
+  float ground_z;          /* ground_truth_position[2], the z that solveDenseMPC hands the solver (:640) */
+  float v_world[3];
+  float omega_world[3];
+  float orientation[4];    /* w,x,y,z */
+  float rpy[3];
+  float r_body[9];         /* rBody, row major */
+  float p_foot[12];        /* pFoot[leg][axis], world frame */
+  /* command state of ConvexMPCLocomotion */
+  float x_vel_des, y_vel_des, yaw_turn_rate, yaw_des, body_height;
+  float rpy_comp[2];
+  float world_position_desired[2];
+  float roll_des, pitch_des;
+  float stand_traj[3];     /* stand_traj[0], [1], [5] (:526) */
+  float x_comp_integral;
+  float cmpc_x_drag;       /* _dyn_params->cmpc_x_drag */
+  /* gait object (Gait.h): nIterations == horizon */
+  int32_t gait_kind;       /* CMPC_GAIT_* */
+  int32_t gait_iteration;  /* _iteration */
+  int32_t gait_offsets[4]; /* OffsetDurationGait::_offsets; MixedFrequncyGait::_periods */
+  int32_t gait_durations[4];
+  float gait_duty;         /* MixedFrequncyGait::_duty_cycle */
+  int32_t omni_mode;
+  int32_t stand;           /* current_gait == 4 (:524) */
+  int32_t have_log;        /* received_log_data_ (:647) */
+  /* /log_data of the previous step (:650-765) */
+  float log_x_prev[12];    /* euler_act xyz, pos_act xyz, vel_act.angular xyz, vel_act.linear xyz */
+  float log_R[9];          /* R_00 .. R_22, row major */
+  float log_r_feet[12];    /* r_x_1..4, r_y_1..4, r_z_1..4 */
+  float log_foot_force[12];/* foot_force{0..3}_{x,y,z} */
+  float log_x_drag;
+  float sim_time;          /* simulation_time (be2r_cmpc_unitree.hpp:156) */
+  float pad_;
+} cmpc_command;            /* 464 bytes */
+
+typedef struct {
+  float fr_des[12];                 /* Fr_des[leg][axis] = first-step ground reaction forces (:836-845) */
+  float f_ff[12];                   /* f_ff[leg] = -rBody * f (:841) */
+  float world_position_desired[2];  /* after the max_pos_error clamp (:535-548) */
+  float x_comp_integral;            /* after the update at :811-816 */
+  float f_ext[6];                   /* the residual handed to the solver (:771); unchanged without /log_data */
+  int32_t status;                   /* CMPC_ST_* */
+  int32_t iterations;
+  float pad_[1];
+} cmpc_command_result;              /* 144 bytes */
+
+/* Q and alpha of solveDenseMPC (:627, :634); defaults are the reference's hard-coded values. */
+int cmpc_batch_set_weights(cmpc_batch* b, const float weights[12], float alpha);
+/* One MPC update of `count` robots from host command structs (any host memory; pinned is faster).
+ * forces_out may be NULL; when given it receives the full q_soln [count][12*horizon] as well. */
+int cmpc_batch_solve_commands(cmpc_batch* b, int count, const cmpc_command* commands, cmpc_command_result* results,
+                              double* forces_out);
+/* Forget the per-instance disturbance histories, estimates and f_ext (the reference's file-scope vectors). */
+int cmpc_batch_reset_history(cmpc_batch* b);
+/* samples pushed into the histories so far (the reference's time_history.size()) */
+int cmpc_batch_history_length(cmpc_batch* b, int* samples);
+/* Test / debug helper: copy the instance records [first, first+count) as the device holds them. */
+int cmpc_batch_copy_records(cmpc_batch* b, int first, int count, void* dst);
+
 /* Adaptive-MPC periodic disturbance estimation fused into the solve launch
  * (SolverMPC.cpp:688-798).  windows_t/windows_d hold, per instance, the last
  * CMPC_ADAPT_WINDOW samples of time and f_ext[3]; sim_time is the time the

@@ -23,6 +23,24 @@ class Outputs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("forces", "objective", "status", "iterations", "active")]
 
 
+# cmpc_command / cmpc_command_result (include/cmpc_b200.h), as numpy structured dtypes
+COMMAND_DTYPE = np.dtype([
+    ("position", "<f4", 3), ("ground_z", "<f4"), ("v_world", "<f4", 3), ("omega_world", "<f4", 3),
+    ("orientation", "<f4", 4), ("rpy", "<f4", 3), ("r_body", "<f4", 9), ("p_foot", "<f4", 12),
+    ("x_vel_des", "<f4"), ("y_vel_des", "<f4"), ("yaw_turn_rate", "<f4"), ("yaw_des", "<f4"), ("body_height", "<f4"),
+    ("rpy_comp", "<f4", 2), ("world_position_desired", "<f4", 2), ("roll_des", "<f4"), ("pitch_des", "<f4"),
+    ("stand_traj", "<f4", 3), ("x_comp_integral", "<f4"), ("cmpc_x_drag", "<f4"),
+    ("gait_kind", "<i4"), ("gait_iteration", "<i4"), ("gait_offsets", "<i4", 4), ("gait_durations", "<i4", 4),
+    ("gait_duty", "<f4"), ("omni_mode", "<i4"), ("stand", "<i4"), ("have_log", "<i4"),
+    ("log_x_prev", "<f4", 12), ("log_R", "<f4", 9), ("log_r_feet", "<f4", 12), ("log_foot_force", "<f4", 12),
+    ("log_x_drag", "<f4"), ("sim_time", "<f4"), ("pad_", "<f4"),
+])
+RESULT_DTYPE = np.dtype([
+    ("fr_des", "<f4", 12), ("f_ff", "<f4", 12), ("world_position_desired", "<f4", 2), ("x_comp_integral", "<f4"),
+    ("f_ext", "<f4", 6), ("status", "<i4"), ("iterations", "<i4"), ("pad_", "<f4", 1),
+])
+assert COMMAND_DTYPE.itemsize == 464 and RESULT_DTYPE.itemsize == 144
+
 _lib = None
 
 
@@ -61,6 +79,11 @@ def lib():
         L.cmpc_batch_enable_phase_clocks.argtypes = [C.c_void_p, C.c_int]
         L.cmpc_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
         L.cmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.cmpc_batch_set_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        L.cmpc_batch_solve_commands.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cmpc_batch_reset_history.argtypes = [C.c_void_p]
+        L.cmpc_batch_history_length.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.cmpc_batch_copy_records.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.cmpc_batch_device_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.cmpc_batch_device_forces.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.setup_problem.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double]
@@ -262,6 +285,37 @@ class Batch:
         arr = (C.c_ulonglong * len(self.PHASES))()
         _check(lib().cmpc_batch_phase_cycles(self._h, arr, len(self.PHASES)), "cmpc_batch_phase_cycles")
         return dict(zip(self.PHASES, [int(x) for x in arr]))
+
+    # ---- the caller of the path on the device (updateMPCIfNeeded / solveDenseMPC / getMpcTable) ----
+    def set_weights(self, weights, alpha):
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        _check(lib().cmpc_batch_set_weights(self._h, _ptr(w), float(alpha)), "cmpc_batch_set_weights")
+
+    def solve_commands(self, commands, want_forces=False, results=None):
+        """One MPC update of len(commands) robots from cmpc_command structs (a COMMAND_DTYPE array)."""
+        cmds = np.ascontiguousarray(commands, dtype=COMMAND_DTYPE)
+        n = len(cmds)
+        res = np.zeros(n, dtype=RESULT_DTYPE) if results is None else results
+        forces = np.zeros((n, 12 * self.horizon)) if want_forces else None
+        _check(lib().cmpc_batch_solve_commands(self._h, n, _ptr(cmds), _ptr(res), None if forces is None else _ptr(forces)),
+               "cmpc_batch_solve_commands")
+        self.count = n
+        return (res, forces) if want_forces else res
+
+    def reset_history(self):
+        _check(lib().cmpc_batch_reset_history(self._h), "cmpc_batch_reset_history")
+
+    def history_length(self):
+        n = C.c_int()
+        _check(lib().cmpc_batch_history_length(self._h, C.byref(n)), "cmpc_batch_history_length")
+        return n.value
+
+    def copy_records(self, first, count):
+        h = self.horizon
+        stride = (4 * (48 + 12 * h) + 4 * h + 15) & ~15
+        out = np.zeros((count, stride), dtype=np.uint8)
+        _check(lib().cmpc_batch_copy_records(self._h, first, count, _ptr(out)), "cmpc_batch_copy_records")
+        return out
 
     def upload_disturbance(self, win_t, win_d, sim_time, mode):
         """mode 0 estimate, 1 estimate+apply, 2 apply the stored estimate (windows may be None), <0 off."""

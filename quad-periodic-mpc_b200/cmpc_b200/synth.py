@@ -137,3 +137,70 @@ def make_disturbance_windows(batch, n=400, dt=0.03, seed=0):
     off = rng.normal(0, 0.5, (batch, 1))
     d = off + amp * np.sin(2 * np.pi * freq * t + phase) + rng.normal(0, 0.05, (batch, n))
     return t.astype(np.float32), d.astype(np.float32), dict(amp=amp, freq=freq, phase=phase, off=off)
+
+
+def rot_from_quat(q):
+    """Rotation matrix of the estimator (rBody: body <- world), row major, from (w,x,y,z)."""
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y + w * z), 2 * (x * z - w * y),
+                  2 * (x * y - w * z), 1 - 2 * (x * x + z * z), 2 * (y * z + w * x),
+                  2 * (x * z + w * y), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)], axis=-1)
+    return R
+
+
+def make_commands(batch, dtype, horizon=10, gaits=("trot",), seed=0, spread=1.0, body_height=0.24, mixed_fraction=0.0,
+                  stand_fraction=0.0, with_log=True, sim_time=0.0, disturbance=None):
+    """Randomised controller-level inputs (`cmpc_command`, include/cmpc_b200.h): what ConvexMPCLocomotion's
+    updateMPCIfNeeded / solveDenseMPC read per robot.  `dtype` is engine.COMMAND_DTYPE.
+    disturbance = (amp, freq, phase) arrays adds a periodic force residual to the logged model so that f_ext[3]
+    oscillates (the signal the estimator fits)."""
+    rng = np.random.default_rng(seed + 4241)
+    B, h = batch, horizon
+    base = make_batch(B, horizon=h, gaits=gaits, seed=seed, spread=spread, body_height=body_height)
+    c = np.zeros(B, dtype=dtype)
+    p, q = base["p"], base["q"]
+    c["position"] = p
+    c["ground_z"] = p[:, 2] + rng.normal(0, 0.003, B)
+    c["v_world"], c["omega_world"], c["orientation"], c["rpy"] = base["v"], base["w"], q, base["rpy"]
+    c["r_body"] = rot_from_quat(q.astype(np.float64))
+    r = base["r"].reshape(B, 3, 4)                                    # r[axis][leg] = pFoot[leg][axis] - position[axis]
+    c["p_foot"] = (r.transpose(0, 2, 1) + p[:, None, :]).reshape(B, 12)
+    c["x_vel_des"], c["y_vel_des"] = rng.uniform(-0.7, 0.7, B), rng.uniform(-0.4, 0.4, B)
+    c["yaw_turn_rate"] = rng.uniform(-1.0, 1.0, B)
+    c["yaw_des"] = base["rpy"][:, 2] + rng.normal(0, 0.05, B)
+    c["body_height"] = body_height
+    c["rpy_comp"] = rng.normal(0, 0.02, (B, 2))
+    c["world_position_desired"] = p[:, :2] + rng.uniform(-0.25, 0.25, (B, 2))   # some beyond max_pos_error
+    c["roll_des"], c["pitch_des"] = rng.normal(0, 0.02, B), rng.normal(0, 0.02, B)
+    c["stand_traj"] = np.stack([p[:, 0], p[:, 1], base["rpy"][:, 2]], -1)
+    c["x_comp_integral"] = rng.normal(0, 0.05, B)
+    c["cmpc_x_drag"] = 3.0
+    names = list(gaits)
+    gid = rng.integers(0, len(names), B)
+    for b in range(B):
+        off, dur = scaled_gait(names[gid[b]], h)
+        c["gait_offsets"][b], c["gait_durations"][b] = off, dur
+    c["gait_iteration"] = rng.integers(0, h, B)
+    mixed = rng.random(B) < mixed_fraction
+    c["gait_kind"] = mixed.astype(np.int32)
+    periods = rng.integers(3, h + 1, (B, 4))
+    c["gait_offsets"][mixed] = periods[mixed]
+    c["gait_duty"] = rng.uniform(0.35, 0.65, B)
+    c["omni_mode"] = rng.random(B) < 0.25
+    c["stand"] = rng.random(B) < stand_fraction
+    c["gait_durations"][c["stand"] != 0] = h
+    c["gait_offsets"][(c["stand"] != 0) & ~mixed] = 0
+    c["gait_kind"][c["stand"] != 0] = 0
+    c["have_log"] = 1 if with_log else 0
+    c["log_x_prev"] = np.concatenate([base["rpy"], p, base["w"], base["v"]], axis=1) + rng.normal(0, 0.01, (B, 12))
+    c["log_R"] = rot_from_quat(q.astype(np.float64)).reshape(B, 3, 3).transpose(0, 2, 1).reshape(B, 9)
+    c["log_r_feet"] = base["r"] + rng.normal(0, 0.005, (B, 12))
+    ff = rng.normal(0, 8.0, (B, 12))
+    ff[:, 2::3] = rng.uniform(20, 70, (B, 4))
+    if disturbance is not None:
+        amp, freq, phase = disturbance
+        ff[:, 0] += 12.0 * (amp * np.sin(2 * np.pi * freq * sim_time + phase))   # shows up in f_ext[3] = v_x - sum u_x / 12
+    c["log_foot_force"] = ff
+    c["log_x_drag"] = c["x_comp_integral"]
+    c["sim_time"] = sim_time
+    return c

@@ -258,6 +258,13 @@ struct cmpc_batch {
   float* d_simtime = nullptr;
   double* d_est = nullptr;
   float* d_fest = nullptr;
+  // command front end (cmpc_batch_solve_commands)
+  unsigned char* d_cmds = nullptr;     // [capacity] cmpc_command
+  unsigned char* d_results = nullptr;  // [capacity] cmpc_command_result
+  float* d_fext = nullptr;             // [capacity][6] the reference's global f_ext, per instance
+  int hist_len = 0;                    // samples pushed into the disturbance histories (time_history.size())
+  float weights[12] = {0.25f, 0.25f, 10.f, 10.f, 2.f, 50.f, 0.f, 0.f, 0.3f, 0.2f, 0.2f, 0.1f};  // ConvexMPCLocomotion.cpp:627
+  float alpha = 4e-5f;                 // :634
   // pinned result staging
   double* h_forces = nullptr;
   double* h_obj = nullptr;
@@ -829,6 +836,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); }
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
+  cudaFree(b->d_cmds); cudaFree(b->d_results); cudaFree(b->d_fext);
   cudaFreeHost(b->h_forces); cudaFreeHost(b->h_obj); cudaFreeHost(b->h_status); cudaFreeHost(b->h_iters);
   cudaFreeHost(b->h_active); cudaFreeHost(b->h_flops);
   cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->mark0); cudaEventDestroy(b->mark1);
@@ -1183,6 +1191,30 @@ int cmpc_batch_solve_bound(cmpc_batch* b, int count) {
   return solve_host_core(b, count, b->bound);
 }
 
+// device tables and per-instance arrays of the disturbance estimator stage, allocated on first use
+static int ensure_adapt_buffers(cmpc_batch* b) {
+  if (b->d_twiddle) return CMPC_OK;
+  const size_t cap = (size_t)b->capacity, N = CMPC_ADAPT_WINDOW;
+  std::vector<double> tw;
+  std::vector<float> gk;
+  build_adapt_tables(tw, gk);
+  CK(cudaMalloc(&b->d_twiddle, sizeof(double) * tw.size()));
+  CK(cudaMalloc(&b->d_gk, sizeof(float) * gk.size()));
+  CK(cudaMalloc(&b->d_win_t, sizeof(float) * cap * N));
+  CK(cudaMalloc(&b->d_win_d, sizeof(float) * cap * N));
+  CK(cudaMalloc(&b->d_simtime, sizeof(float) * cap));
+  CK(cudaMalloc(&b->d_est, sizeof(double) * cap * 4));
+  CK(cudaMalloc(&b->d_fest, sizeof(float) * cap * 6));
+  CK(cudaMemset(b->d_est, 0, sizeof(double) * cap * 4));
+  CK(cudaMemset(b->d_fest, 0, sizeof(float) * cap * 6));
+  CK(cudaMemset(b->d_win_t, 0, sizeof(float) * cap * N));
+  CK(cudaMemset(b->d_win_d, 0, sizeof(float) * cap * N));
+  CK(cudaMemset(b->d_simtime, 0, sizeof(float) * cap));
+  CK(cudaMemcpy(b->d_twiddle, tw.data(), sizeof(double) * tw.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->d_gk, gk.data(), sizeof(float) * gk.size(), cudaMemcpyHostToDevice));
+  return CMPC_OK;
+}
+
 int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows_t, const float* windows_d,
                                   const float* sim_time, int mode) {
   if (!b) return fail_arg("cmpc_batch_upload_disturbance: null batch");
@@ -1195,23 +1227,8 @@ int cmpc_batch_upload_disturbance(cmpc_batch* b, int count, const float* windows
   if (mode > 2) return fail_arg("cmpc_batch_upload_disturbance: mode must be 0, 1 or 2");
   if (count < 0 || count > b->capacity) return fail_arg("cmpc_batch_upload_disturbance: count exceeds capacity");
   if (!sim_time) return fail_arg("cmpc_batch_upload_disturbance: null sim_time");
-  const size_t cap = (size_t)b->capacity, N = CMPC_ADAPT_WINDOW;
-  if (!b->d_twiddle) {
-    std::vector<double> tw;
-    std::vector<float> gk;
-    build_adapt_tables(tw, gk);
-    CK(cudaMalloc(&b->d_twiddle, sizeof(double) * tw.size()));
-    CK(cudaMalloc(&b->d_gk, sizeof(float) * gk.size()));
-    CK(cudaMalloc(&b->d_win_t, sizeof(float) * cap * N));
-    CK(cudaMalloc(&b->d_win_d, sizeof(float) * cap * N));
-    CK(cudaMalloc(&b->d_simtime, sizeof(float) * cap));
-    CK(cudaMalloc(&b->d_est, sizeof(double) * cap * 4));
-    CK(cudaMalloc(&b->d_fest, sizeof(float) * cap * 6));
-    CK(cudaMemset(b->d_est, 0, sizeof(double) * cap * 4));
-    CK(cudaMemset(b->d_fest, 0, sizeof(float) * cap * 6));
-    CK(cudaMemcpy(b->d_twiddle, tw.data(), sizeof(double) * tw.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(b->d_gk, gk.data(), sizeof(float) * gk.size(), cudaMemcpyHostToDevice));
-  }
+  const size_t N = CMPC_ADAPT_WINDOW;
+  { int rca = ensure_adapt_buffers(b); if (rca) return rca; }
   cudaStream_t st = b->stream[0];
   if (windows_t && windows_d && mode != 2) {
     CK(cudaMemcpyAsync(b->d_win_t, windows_t, sizeof(float) * (size_t)count * N, cudaMemcpyHostToDevice, st));
@@ -1230,6 +1247,115 @@ int cmpc_batch_download_disturbance(cmpc_batch* b, double* est, float* f_est) {
   { int rcs = sync_all(b); if (rcs) return rcs; }
   if (est) CK(cudaMemcpy(est, b->d_est, sizeof(double) * (size_t)b->count * 4, cudaMemcpyDeviceToHost));
   if (f_est) CK(cudaMemcpy(f_est, b->d_fest, sizeof(float) * (size_t)b->count * 6, cudaMemcpyDeviceToHost));
+  return CMPC_OK;
+}
+
+int cmpc_batch_set_weights(cmpc_batch* b, const float weights[12], float alpha) {
+  if (!b || !weights) return fail_arg("cmpc_batch_set_weights: null argument");
+  for (int i = 0; i < 12; i++) b->weights[i] = weights[i];
+  b->alpha = alpha;
+  return CMPC_OK;
+}
+
+// contact foot-steps of the table getMpcTable will produce for this command (an upper bound is enough: it sizes the launch)
+static int command_contacts(const cmpc_command& c, int h) {
+  if (c.gait_kind == CMPC_GAIT_MIXED_FREQUENCY) {
+    int n = 0;
+    for (int k = 0; k < h; k++)
+      for (int j = 0; j < 4; j++) {
+        const int period = c.gait_offsets[j] > 0 ? c.gait_offsets[j] : 1;
+        n += (float)((k + c.gait_iteration + 1) % period) < (float)period * c.gait_duty;
+      }
+    return n;
+  }
+  int n = 0;  // the table covers exactly one period: leg j is down for min(duration, h) of the h steps
+  for (int j = 0; j < 4; j++) n += std::max(0, std::min(c.gait_durations[j], h));
+  return n;
+}
+
+int cmpc_batch_solve_commands(cmpc_batch* b, int count, const cmpc_command* commands, cmpc_command_result* results,
+                              double* forces_out) {
+  if (!b || !commands || !results) return fail_arg("cmpc_batch_solve_commands: null argument");
+  if (!b->is_setup) { g_err = "cmpc_batch_solve_commands: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  if (count < 0 || count > b->capacity) return fail_arg("cmpc_batch_solve_commands: count exceeds capacity");
+  static_assert(sizeof(cmpc_command) == 464 && sizeof(cmpc_command_result) == 144, "command layout");
+  CK(cudaSetDevice(b->device));
+  { int rcs = sync_aux(b); if (rcs) return rcs; }
+  const size_t cap = (size_t)b->capacity;
+  if (!b->d_cmds) {
+    CK(cudaMalloc(&b->d_cmds, cap * sizeof(cmpc_command)));
+    CK(cudaMalloc(&b->d_results, cap * sizeof(cmpc_command_result)));
+    CK(cudaMalloc(&b->d_fext, cap * 6 * sizeof(float)));
+    CK(cudaMemset(b->d_fext, 0, cap * 6 * sizeof(float)));
+  }
+  { int rca = ensure_adapt_buffers(b); if (rca) return rca; }
+  if (count == 0) return CMPC_OK;
+  cudaStream_t st = b->stream[0];
+  const int h = b->h;
+  CK(cudaEventRecord(b->ev0, st));
+  CK(cudaMemcpyAsync(b->d_cmds, commands, (size_t)count * sizeof(cmpc_command), cudaMemcpyHostToDevice, st));
+  int maxc = 0;
+  for (int i = 0; i < count; i++) maxc = std::max(maxc, command_contacts(commands[i], h));
+  maxc = std::min(maxc, 4 * h);
+  float alpha = b->alpha;
+  if (alpha > 1e-4f) alpha = 1e-5f;  // "Alpha was set too high", ConvexMPCLocomotion.cpp:785-789
+  int rc = cmpc_launch_frontend(b->d_cmds, b->d_rec, b->d_results, b->d_fext, b->d_simtime, count, h, b->rec_stride,
+                                (float)b->dt, alpha, b->weights, st);
+  if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_frontend_kernel launch");
+  b->launches++;
+  // solve_mpc's bookkeeping (SolverMPC.cpp:688-706, :806-813): push the sample; fit while the history holds
+  // 400..500 samples (the estimate is not applied yet); beyond 500 the stored fit is refreshed at
+  // simulation_time and applied in g.  The windows are not read any more once the history is past 500.
+  if (b->hist_len < 500) {
+    rc = cmpc_launch_history_push(b->d_cmds, b->d_fext, b->d_win_t, b->d_win_d, count, b->hist_len, st);
+    if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_history_push_kernel launch");
+    b->launches++;
+  }
+  if (b->hist_len < (1 << 30)) b->hist_len++;
+  b->adapt_mode = b->hist_len < CMPC_ADAPT_WINDOW ? -1 : (b->hist_len <= 500 ? 0 : 2);
+  b->count = count;
+  b->max_contact = maxc;
+  rc = launch_range(b, 0, count, maxc, 0);
+  if (rc) return rc;
+  rc = cmpc_launch_epilogue(b->d_cmds, b->d_forces, b->d_status, b->d_iters, b->d_results, count, h, st);
+  if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_epilogue_kernel launch");
+  b->launches++;
+  CK(cudaMemcpyAsync(results, b->d_results, (size_t)count * sizeof(cmpc_command_result), cudaMemcpyDeviceToHost, st));
+  if (forces_out)
+    CK(cudaMemcpyAsync(forces_out, b->d_forces, sizeof(double) * (size_t)count * 12 * h, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(b->ev1, st));
+  b->timed = true;
+  CK(cudaStreamSynchronize(st));
+  return CMPC_OK;
+}
+
+int cmpc_batch_reset_history(cmpc_batch* b) {
+  if (!b) return fail_arg("cmpc_batch_reset_history: null batch");
+  CK(cudaSetDevice(b->device));
+  { int rcs = sync_all(b); if (rcs) return rcs; }
+  b->hist_len = 0;
+  b->adapt_mode = -1;
+  const size_t cap = (size_t)b->capacity;
+  if (b->d_fext) CK(cudaMemset(b->d_fext, 0, cap * 6 * sizeof(float)));
+  if (b->d_est) {
+    CK(cudaMemset(b->d_est, 0, sizeof(double) * cap * 4));
+    CK(cudaMemset(b->d_fest, 0, sizeof(float) * cap * 6));
+  }
+  return CMPC_OK;
+}
+
+int cmpc_batch_history_length(cmpc_batch* b, int* samples) {
+  if (!b || !samples) return fail_arg("cmpc_batch_history_length: null argument");
+  *samples = b->hist_len;
+  return CMPC_OK;
+}
+
+int cmpc_batch_copy_records(cmpc_batch* b, int first, int count, void* dst) {
+  if (!b || !dst || first < 0 || count < 0 || first + count > b->capacity) return fail_arg("cmpc_batch_copy_records: bad arguments");
+  if (!b->is_setup) { g_err = "cmpc_batch_copy_records: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  CK(cudaSetDevice(b->device));
+  { int rcs = sync_all(b); if (rcs) return rcs; }
+  CK(cudaMemcpy(dst, b->d_rec + (size_t)first * b->rec_stride, (size_t)count * b->rec_stride, cudaMemcpyDeviceToHost));
   return CMPC_OK;
 }
 

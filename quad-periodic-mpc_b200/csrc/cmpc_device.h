@@ -158,6 +158,13 @@ int cmpc_shape_threads(int shape);
 int cmpc_launch_solve(const CmpcParams& P, int shape, int grid, void* stream);
 int cmpc_max_ctas_per_sm(int shape, size_t smem, bool adapt);
 int cmpc_run_dfma_peak(int sm_count, void* stream, double* out_dev, int iters);
+/* cmpc_frontend.cu: the caller of the path (updateMPCIfNeeded / solveDenseMPC / getMpcTable) on the device */
+int cmpc_launch_frontend(const void* cmds, unsigned char* records, void* results, float* f_ext, float* sim_time, int count,
+                         int horizon, int rec_stride, float dt, float alpha, const float weights[12], void* stream);
+int cmpc_launch_history_push(const void* cmds, const float* f_ext, float* win_t, float* win_d, int count, int have,
+                             void* stream);
+int cmpc_launch_epilogue(const void* cmds, const double* forces, const int* status, const int* iterations, void* results,
+                         int count, int horizon, void* stream);
 /* cmpc_pack.cu: instance records from structure-of-arrays inputs (device-accessible pointers, e.g. pinned host memory) */
 int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w, const void* r, const void* weights,
                      const void* traj, const void* alpha, const void* gait, const void* x_drag, const void* f_dist,
