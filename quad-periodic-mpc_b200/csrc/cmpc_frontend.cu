@@ -9,8 +9,8 @@
 //   cmpc_epilogue_kernel      one thread per robot: Fr_des, f_ff = -rBody f from the first horizon step
 //
 // The reference computes all of this in fp32; so do these kernels, with explicitly rounded operations
-// (__fmul_rn / __fadd_rn, no FMA contraction) in the order oracle/cmpc_frontend.py states, so that the records
-// they write are bit-identical to the oracle's.
+// (__fmul_rn / __fadd_rn, no FMA contraction) in a stated order — products left to right, the third term added
+// last — so that the records they write can be checked bit for bit by the tests' CPU restatement.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
