@@ -4,15 +4,17 @@ reference's qpOASES path on the host cores.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-One "step" = one pass of the fused condensation + QP kernel over one batch of 4096 synthetic
+One "step" = one pass of the condensation + inversion + QP kernels over one batch of 4096 synthetic
 randomised A1 trot instances (BASELINE.json configs[1]) per GPU.  Instances are independent, so the
 path shards with no collective (weak scaling: every rank solves its own 4096-instance batches).
 
   value      solves/s with the instance records resident in HBM.  A ring of RING distinct batches
              (> L2 in total) is uploaded once; timed steps walk the ring so every step reads cold
              records.  CUDA events on the engine's stream, max over ranks.
-  e2e        the same metric through cmpc_batch_solve_host() with HOST buffers: pack into pinned
-             records, H2D, kernel, D2H of forces/status, every step inside the timed region.
+  e2e        the same metric through the host-buffer call (cmpc_batch_bind_host + cmpc_batch_solve_bound, one
+             synchronous call per step): the device reads the pinned input arrays over PCIe and packs the
+             records, the kernels write forces/objective/status into pinned host arrays, every step inside
+             the timed region.  e2e.commands is the controller-level call one level up (row (f)).
   roofline   the FP64 tensor-core inversion kernel (K = H^-1 by blocked sweeps of DMMA m8n8k4, ~90 % of the
              step's flops) against the measured FP64 peak of the device; every kernel class of the step
              (assembly, inversion, dual active set) is listed beside it with its own time, flops and
@@ -39,8 +41,9 @@ import numpy as np  # noqa: E402
 HORIZON, DT, BATCH = 10, 0.03, 4096
 METRIC = "cmpc_qp_solves_per_sec_h10_batched"
 L2_BYTES = 126 * 1024 * 1024
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {"assemble": None, "invert": None, "dual": None, "fused": None}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch (bytes), from the committed ncu --set full capture
+# (profiles/r1_s3_ncu_full_summary.txt; cold cache: ncu flushes L2 between kernels)
+NCU_TRAFFIC = {"assemble": 41.5e6, "invert": 96.0e6, "dual": 28.9e6, "fused": None}
 
 
 def shard_bounds(total, rank, world):
@@ -184,7 +187,6 @@ def run_b200(args, rank, world, local_rank):
     b.mark(1)
     barrier()
     region_ms = b.marked_ms()          # CUDA events on the launching stream around exactly K launches
-    clocks = sampler.stop()
     launches = b.launches()
     flops_total = b.last_flops()
     units, seconds = allreduce_sum_max(float(args.steps * BATCH), region_ms / 1e3)
@@ -205,8 +207,31 @@ def run_b200(args, rank, world, local_rank):
     e2e_wall = time.perf_counter() - t0
     e2e_units, e2e_seconds = allreduce_sum_max(float(args.steps * BATCH), e2e_wall)
     assert (res["status"] == 0).all()
-    h2d = BATCH * rec_bytes
-    d2h = BATCH * (12 * h * 8 + 8 + 4 + 4) + 8
+    h2d = int(sum(a.nbytes for a in be._prepared_inputs.values()))   # the eleven input arrays the device reads over PCIe
+    d2h = int(sum(a.nbytes for a in res.values()))                    # forces, objective, status, iterations
+
+    # ---- end to end one level up: the controller-level call (updateMPCIfNeeded / solveDenseMPC on the device) ----
+    cmds = synth.make_commands(BATCH, engine.COMMAND_DTYPE, horizon=h, gaits=("trot",), seed=2000 + rank)
+    cres = np.zeros(BATCH, dtype=engine.RESULT_DTYPE)
+    bc = engine.Batch(BATCH, device=local_rank)
+    bc.setup(DT, h, inst["mu"], inst["f_max"])
+    for a in (cmds, cres):
+        engine.lib().cmpc_host_register(a.ctypes.data, a.nbytes)
+    for _ in range(max(1, args.warmup)):
+        bc.solve_commands(cmds, results=cres)
+    csteps = max(1, min(args.steps, 200))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(csteps):
+        bc.solve_commands(cmds, results=cres)
+    barrier()
+    cmd_wall = time.perf_counter() - t0
+    cmd_units, cmd_seconds = allreduce_sum_max(float(csteps * BATCH), cmd_wall)
+    assert (cres["status"] == 0).all()
+    for a in (cmds, cres):
+        engine.lib().cmpc_host_unregister(a.ctypes.data)
+    bc.close()
+    clocks = sampler.stop()            # sampled through the three timed regions (resident, e2e, e2e commands)
 
     # ---- per-kernel-class device time: serial solves (CUDA events between the classes) on cold ring batches ----
     kflops = b.kernel_flops()                     # algorithmic flops of the timed region, per kernel class
@@ -281,7 +306,16 @@ def run_b200(args, rank, world, local_rank):
                                  "bytes_per_launch": hbm_bytes, "peak_source": peak_kind}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_units / e2e_seconds, "unit": "solves/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_seconds / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_seconds / args.steps,
+                    "call": "cmpc_batch_solve_bound: one synchronous call per step, pinned host arrays in the layout of "
+                            "update_problem_data (update_data_t); the device reads the inputs over PCIe and packs the "
+                            "records, the kernels write the results into host memory",
+                    "commands": {"value": cmd_units / cmd_seconds, "unit": "solves/s", "steps": csteps,
+                                 "h2d_bytes_per_step": int(cmds.nbytes), "d2h_bytes_per_step": int(cres.nbytes),
+                                 "ms_per_step": 1e3 * cmd_seconds / csteps,
+                                 "call": "cmpc_batch_solve_commands: the controller-level call (ConvexMPCLocomotion::"
+                                         "updateMPCIfNeeded + solveDenseMPC + getMpcTable on the device), one cmpc_command "
+                                         "in and one cmpc_command_result out per robot"}},
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -292,7 +326,7 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
