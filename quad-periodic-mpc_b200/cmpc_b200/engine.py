@@ -276,7 +276,7 @@ class Batch:
         _check(lib().cmpc_batch_profile_range(self._h, first, count, arr), "cmpc_batch_profile_range")
         return dict(zip(self.KERNELS, [float(x) for x in arr]))
 
-    PHASES = ("wait", "adapt", "prep", "hess", "load", "sweep", "store", "qp", "out")
+    PHASES = ("wait", "adapt", "prep", "hess", "load", "sweep", "store", "qp", "out", "publish", "dvwait")
 
     def enable_phase_clocks(self, on=True):
         _check(lib().cmpc_batch_enable_phase_clocks(self._h, int(on)), "cmpc_batch_enable_phase_clocks")

@@ -112,7 +112,9 @@ struct CmpcParams {
 #define CMPC_PH_STORE 6   /* K store, x0 = -K g, slacks */
 #define CMPC_PH_QP 7      /* active-set iterations */
 #define CMPC_PH_OUT 8     /* objective, outputs */
-#define CMPC_PH_COUNT 9
+#define CMPC_PH_PUBLISH 9 /* warp-specialised inversion: panel publish */
+#define CMPC_PH_DVWAIT 10 /* warp-specialised inversion: main warp waiting for the helper's pivot-block inverse */
+#define CMPC_PH_COUNT 11
 
 // kernel shapes (cmpc_kernels.cu): register-tile tiers by reduced problem size, shared-memory tier beyond
 #define CMPC_SHAPE_64 0    /* n <= 64, 64 threads, 8x8 register tiles */

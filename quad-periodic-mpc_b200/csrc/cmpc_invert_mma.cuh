@@ -177,3 +177,208 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
 #undef INV_TICK
   if (lane == 0 && P.flops && flops_acc) atomicAdd(P.flops + CMPC_K_INVERT, (unsigned long long)flops_acc);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Warp-specialised variant: the serial part of a block step — the 8-pivot chain that inverts the diagonal tile,
+// 46 % of an instance's cycles in the kernel above — moves to a HELPER warp.  A CTA is two warpgroups: four
+// main warps (one instance each, all 36 tiles in registers; setmaxnreg raises them to 168 registers) and four
+// helper warps (setmaxnreg drops them to 40).  Main warp w and helper warp w + 4 sit on the same SM sub-partition
+// and talk through two named barriers and 1 KB of shared memory:
+//   main:    ... update tile (s+1, s+1) FIRST (two DMMAs), park it in shared memory, bar.arrive(TILE);
+//            the other 72 update DMMAs of step s; publish panel s+1; bar.sync(DV); M = -D^-1 C; ...
+//   helper:  bar.sync(TILE); invert the parked tile (Gauss-Jordan over shuffles); write -D^-1; bar.arrive(DV)
+// so the pivot chain of step s+1 runs while the main warp issues the update DMMAs of step s.  Two CTAs per SM
+// (the register file: 2 x 128 x (216 + 40)), eight instances per SM, two main warps per FP64 tensor pipe.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int WS_MAIN = 4;                                   // main warps (= instances in flight) per CTA
+constexpr int WS_PAIR_SMEM = 8 * (2 * 8 * MMA_PS + 64 + 64) + 16;  // panel, M, -D^-1, parked tile, control word
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+}  // namespace
+
+template <bool CLK /* per-phase SM cycles of the main warps (profiling launches only) */>
+__global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const __grid_constant__ CmpcParams P) {
+  constexpr int PS = MMA_PS;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane >> 2, q = lane & 3;
+  const int pair = warp & (WS_MAIN - 1);
+  double* pan = reinterpret_cast<double*>(smem + (size_t)pair * WS_PAIR_SMEM);
+  double* mm = pan + 8 * PS;
+  double* dv = mm + 8 * PS;
+  double* dtile = dv + 64;
+  volatile int* ctrl = reinterpret_cast<volatile int*>(dtile + 64);
+  const int BAR_TILE = 1 + 2 * pair, BAR_DV = 2 + 2 * pair;
+
+  if (warp >= WS_MAIN) {
+    // ---------------- helper: the pivot chains ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    while (true) {
+      named_bar_sync(BAR_TILE);  // the first diagonal tile of an instance, or the end of the work
+      const int nb = ctrl[0];
+      if (nb < 0) break;
+      for (int s = 0; s < nb; s++) {
+        if (s > 0) named_bar_sync(BAR_TILE);
+        const double2 d = *reinterpret_cast<const double2*>(dtile + r * 8 + 2 * q);
+        double d0 = d.x, d1 = d.y;
+        warp_inv8_acc(d0, d1, r, q);
+        *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
+        named_bar_arrive(BAR_DV);
+      }
+    }
+    return;
+  }
+
+  // ---------------- main: tiles in registers, DMMA ----------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
+  // The two CTAs of an SM start together and every instance takes the same time, so their main warps would run their
+  // DMMA phases in lockstep (pipe saturated, then idle).  The second wave of CTAs starts half a block step late.
+  if (P.pad0 > 0 && blockIdx.x >= (gridDim.x + 1) / 2) __nanosleep((unsigned)P.pad0);
+  const int count = P.count;
+  unsigned flops_acc = 0u;
+  const int fo = q * PS + r;  // fragment offset: element (k = q, row/col = r)
+  long long tclk = 0;
+  if (CLK) tclk = clock64();
+#define WS_TICK(PH)                                                                     \
+  if (CLK) {                                                                            \
+    const long long now_ = clock64();                                                   \
+    if (lane == 0) atomicAdd(P.phase_cycles + (PH), (unsigned long long)(now_ - tclk)); \
+    tclk = now_;                                                                        \
+  }
+  // diagonal tile S of the bordered matrix as the pivot block sees it: row / column 63 (the border) masked out
+  auto park_tile = [&](double d0, double d1, int S) {
+    if (S == 7) {
+      if (r == 7) { d0 = 0.0; d1 = (q == 3) ? 1.0 : 0.0; }
+      else if (q == 3) d1 = 0.0;
+    }
+    *reinterpret_cast<double2*>(dtile + r * 8 + 2 * q) = make_double2(d0, d1);
+  };
+  while (true) {
+    int inst = 0;
+    if (lane == 0) inst = atomicAdd(P.sched, 1);
+    inst = __shfl_sync(0xffffffffu, inst, 0);
+    if (inst >= count) break;
+    double* slot = P.qws + (size_t)inst * P.qws_stride;
+    const int* hdr = reinterpret_cast<const int*>(slot + P.qws_goff + 2 * P.nmax + 2);
+    const int nc = hdr[0];
+    if (hdr[1] != CMPC_ST_SOLVED) continue;
+    const int n = 3 * nc, nblk = (n + 7) >> 3;
+    flops_acc += (unsigned)(n * n * (n + 2));
+    double t[36][2];
+#pragma unroll
+    for (int k = 0; k < 36; k++) {
+      const double2 v = *reinterpret_cast<const double2*>(slot + k * 64 + lane * 2);
+      t[k][0] = v.x;
+      t[k][1] = v.y;
+    }
+    if (lane == 0) ctrl[0] = nblk;
+    park_tile(t[0][0], t[0][1], 0);
+    named_bar_arrive(BAR_TILE);
+    WS_TICK(CMPC_PH_LOAD)
+#pragma unroll 1
+    for (int s = 0; s < nblk; s++) {
+      // 1. publish the panel of block step s (static tile indices per block step)
+      switch (s) {
+        case 0: publish_panel<0>(t, pan, r, q); break;
+        case 1: publish_panel<1>(t, pan, r, q); break;
+        case 2: publish_panel<2>(t, pan, r, q); break;
+        case 3: publish_panel<3>(t, pan, r, q); break;
+        case 4: publish_panel<4>(t, pan, r, q); break;
+        case 5: publish_panel<5>(t, pan, r, q); break;
+        case 6: publish_panel<6>(t, pan, r, q); break;
+        default: publish_panel<7>(t, pan, r, q); break;
+      }
+      __syncwarp();
+      WS_TICK(CMPC_PH_PUBLISH)
+      named_bar_sync(BAR_DV);  // -D^-1 of this step from the helper
+      WS_TICK(CMPC_PH_DVWAIT)
+      // a last block of at most four real rows: its second k-step (padding rows, the border) contributes zeros
+      const bool half_step = (8 * s + 4 >= n);
+      // 2. M = -D^-1 C
+      {
+        const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          double mt[4][2];
+#pragma unroll
+          for (int J = 0; J < 4; J++) {
+            mt[J][0] = 0.0;
+            mt[J][1] = 0.0;
+            dmma884(mt[J][0], mt[J][1], a0, pan[fo + 8 * (4 * half + J)]);
+          }
+#pragma unroll
+          for (int J = 0; J < 4; J++) {
+            dmma884(mt[J][0], mt[J][1], a1, pan[fo + 4 * PS + 8 * (4 * half + J)]);
+            *reinterpret_cast<double2*>(mm + r * PS + 8 * (4 * half + J) + 2 * q) = make_double2(mt[J][0], mt[J][1]);
+          }
+        }
+      }
+      __syncwarp();
+      WS_TICK(CMPC_PH_ADAPT)
+      // 3a. the next diagonal tile first: hand it to the helper, whose pivot chain then runs under the update DMMAs
+      if (s + 1 < nblk) {
+        double e0, e1;
+        switch (s) {
+          case 0: e0 = t[tix(1, 1)][0]; e1 = t[tix(1, 1)][1]; break;
+          case 1: e0 = t[tix(2, 2)][0]; e1 = t[tix(2, 2)][1]; break;
+          case 2: e0 = t[tix(3, 3)][0]; e1 = t[tix(3, 3)][1]; break;
+          case 3: e0 = t[tix(4, 4)][0]; e1 = t[tix(4, 4)][1]; break;
+          case 4: e0 = t[tix(5, 5)][0]; e1 = t[tix(5, 5)][1]; break;
+          case 5: e0 = t[tix(6, 6)][0]; e1 = t[tix(6, 6)][1]; break;
+          default: e0 = t[tix(7, 7)][0]; e1 = t[tix(7, 7)][1]; break;
+        }
+        const int o = 8 * (s + 1);
+        dmma884(e0, e1, pan[fo + o], mm[fo + o]);
+        if (!half_step) dmma884(e0, e1, pan[fo + 4 * PS + o], mm[fo + 4 * PS + o]);
+        park_tile(e0, e1, s + 1);
+        named_bar_arrive(BAR_TILE);
+      }
+      // 3b. every tile (I, J) += C_I' M_J: both operand sets of a k-step are loaded up front (the main warps own 216
+      //     registers), then 36 independent DMMAs issue back to back
+      {
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          if (ks == 1 && half_step) break;
+          double pf[8], mf[8];
+#pragma unroll
+          for (int I = 0; I < 8; I++) {
+            pf[I] = pan[fo + 4 * PS * ks + 8 * I];
+            mf[I] = mm[fo + 4 * PS * ks + 8 * I];
+          }
+#pragma unroll
+          for (int I = 0; I < 8; I++)
+#pragma unroll
+            for (int J = 0; J <= I; J++) dmma884(t[tix(I, J)][0], t[tix(I, J)][1], pf[I], mf[J]);
+        }
+        __syncwarp();  // every lane is done with pan and mm of this step
+      }
+      WS_TICK(CMPC_PH_SWEEP)
+    }
+    // K_ij = -(A_ij - 2 d_ij) scale in place; x0 = -scale A[63][:]
+    const double scale = slot[P.qws_goff + 2 * P.nmax];
+#pragma unroll
+    for (int I = 0; I < 8; I++)
+#pragma unroll
+      for (int J = 0; J <= I; J++) {
+        const double a0 = t[tix(I, J)][0], a1 = t[tix(I, J)][1];
+        double2 kv;
+        kv.x = -(a0 - ((I == J && r == 2 * q) ? 2.0 : 0.0)) * scale;
+        kv.y = -(a1 - ((I == J && r == 2 * q + 1) ? 2.0 : 0.0)) * scale;
+        *reinterpret_cast<double2*>(slot + tix(I, J) * 64 + lane * 2) = kv;
+        if (I == 7 && r == 7) {
+          double* xo = slot + P.qws_goff + P.nmax;
+          const int j = 8 * J + 2 * q;
+          if (j < n) xo[j] = -scale * a0;
+          if (j + 1 < n) xo[j + 1] = -scale * a1;
+        }
+      }
+    WS_TICK(CMPC_PH_LOAD)
+  }
+#undef WS_TICK
+  // release the helper
+  if (lane == 0) ctrl[0] = -1;
+  __syncwarp();
+  named_bar_arrive(BAR_TILE);
+  if (lane == 0 && P.flops && flops_acc) atomicAdd(P.flops + CMPC_K_INVERT, (unsigned long long)flops_acc);
+}

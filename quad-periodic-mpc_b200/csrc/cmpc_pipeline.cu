@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "cmpc_device.h"
@@ -188,11 +189,45 @@ int launch_invert_t(const CmpcParams& P, int grid, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 }  // namespace
-int cmpc_invert_max_ctas_per_sm(void) { return inv_regs() == 200 ? occ_invert_t<200, false>() : occ_invert_t<168, false>(); }
-int cmpc_invert_instances_per_cta(void) { return INV_WPC; }
+// warp-specialised variant (default): helper warps carry the pivot chains; CMPC_INV_WS=0 selects the kernel above
+namespace {
+bool inv_ws() {
+  static bool v = [] {
+    const char* e = std::getenv("CMPC_INV_WS");
+    return e ? std::atoi(e) != 0 : true;
+  }();
+  return v;
+}
+}  // namespace
+int cmpc_invert_max_ctas_per_sm(void) {
+  if (inv_ws()) {
+    int nb = 0;
+    const size_t smem = (size_t)WS_MAIN * WS_PAIR_SMEM;
+    if (smem_attr<cmpc_invert_ws_kernel<false>>(smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_invert_ws_kernel<false>, 64 * WS_MAIN, smem) != cudaSuccess) return -1;
+    if (const char* e = std::getenv("CMPC_INV_CTAS_PER_SM")) nb = std::max(1, std::min(nb, std::atoi(e)));  // experiments
+    return nb;
+  }
+  return inv_regs() == 200 ? occ_invert_t<200, false>() : occ_invert_t<168, false>();
+}
+int cmpc_invert_instances_per_cta(void) { return inv_ws() ? WS_MAIN : INV_WPC; }
 int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (P.phase_cycles) return inv_regs() == 200 ? launch_invert_t<200, true>(P, grid, st) : launch_invert_t<168, true>(P, grid, st);
+  if (P.phase_cycles && !inv_ws()) return inv_regs() == 200 ? launch_invert_t<200, true>(P, grid, st) : launch_invert_t<168, true>(P, grid, st);
+  if (P.phase_cycles) {
+    const size_t smem = (size_t)WS_MAIN * WS_PAIR_SMEM;
+    cudaError_t e = smem_attr<cmpc_invert_ws_kernel<true>>(smem);
+    if (e != cudaSuccess) return (int)e;
+    cmpc_invert_ws_kernel<true><<<grid, 64 * WS_MAIN, smem, st>>>(P);
+    return (int)cudaGetLastError();
+  }
+  if (inv_ws()) {
+    const size_t smem = (size_t)WS_MAIN * WS_PAIR_SMEM;
+    cudaError_t e = smem_attr<cmpc_invert_ws_kernel<false>>(smem);
+    if (e != cudaSuccess) return (int)e;
+    cmpc_invert_ws_kernel<false><<<grid, 64 * WS_MAIN, smem, st>>>(P);
+    return (int)cudaGetLastError();
+  }
   return inv_regs() == 200 ? launch_invert_t<200, false>(P, grid, st) : launch_invert_t<168, false>(P, grid, st);
 }
 
