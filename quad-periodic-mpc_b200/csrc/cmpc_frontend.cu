@@ -37,68 +37,102 @@ struct FrontArgs {
   float weights[12];
 };
 
-__global__ void __launch_bounds__(128) cmpc_frontend_kernel(const __grid_constant__ FrontArgs A) {
+constexpr int FRONT_NT = 64;  // robots per CTA: small CTAs, so that a few thousand robots still cover every SM
+
+__global__ void __launch_bounds__(FRONT_NT) cmpc_frontend_kernel(const __grid_constant__ FrontArgs A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= A.count) return;
-  const cmpc_command& c = A.cmds[i];
   const int h = A.horizon;
-  float* rec = reinterpret_cast<float*>(A.records + (size_t)i * A.rec_stride);
-  unsigned char* gait = reinterpret_cast<unsigned char*>(rec + CMPC_REC_TRAJ + 12 * h);
-  float* traj = rec + CMPC_REC_TRAJ;
   const float dt = A.dt;
 
-  // ---- updateMPCIfNeeded (:511-594): reference trajectory ----
-  float wpd0 = c.world_position_desired[0], wpd1 = c.world_position_desired[1];
-  if (c.stand) {
-    const float t0[12] = {c.roll_des, c.pitch_des, c.stand_traj[2], c.stand_traj[0], c.stand_traj[1], c.body_height,
-                          0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < h; k++)
-      for (int j = 0; j < 12; j++) traj[12 * k + j] = t0[j];
-  } else {
-    float vw0 = c.x_vel_des, vw1 = c.y_vel_des;
-    if (!c.omni_mode) {  // rBody^T * (x_vel_des, y_vel_des, 0)
-      const float* R = c.r_body;
-      vw0 = dot3(R[0], c.x_vel_des, R[3], c.y_vel_des, R[6], 0.f);
-      vw1 = dot3(R[1], c.x_vel_des, R[4], c.y_vel_des, R[7], 0.f);
+  // ---- updateMPCIfNeeded (:511-594): reference trajectory.  The thread of a robot works out the twelve constant
+  //      entries and the three walks (yaw, x, y); the CTA then fills the 12 h floats of its robots' records together,
+  //      consecutive threads on consecutive words, every entry re-running its own float accumulation (:579-581) ----
+  __shared__ float s_t0[FRONT_NT][12];
+  __shared__ float s_walk[FRONT_NT][3];   // dt * yaw_turn_rate, dt * v_des_world[0], dt * v_des_world[1]; 0 for a stand
+  __shared__ int s_gait[FRONT_NT][11];    // kind, iteration, offsets[4], durations[4], stand
+  __shared__ float s_duty[FRONT_NT];
+  const int tl = threadIdx.x;
+  float wpd0 = 0.f, wpd1 = 0.f;
+  if (i < A.count) {
+    const cmpc_command& c = A.cmds[i];
+    wpd0 = c.world_position_desired[0];
+    wpd1 = c.world_position_desired[1];
+    if (c.stand) {
+      const float t0[12] = {c.roll_des, c.pitch_des, c.stand_traj[2], c.stand_traj[0], c.stand_traj[1], c.body_height,
+                            0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < 12; j++) s_t0[tl][j] = t0[j];
+      s_walk[tl][0] = s_walk[tl][1] = s_walk[tl][2] = 0.f;   // the stand trajectory is constant (:524-531)
+    } else {
+      float vw0 = c.x_vel_des, vw1 = c.y_vel_des;
+      if (!c.omni_mode) {  // rBody^T * (x_vel_des, y_vel_des, 0)
+        const float* R = c.r_body;
+        vw0 = dot3(R[0], c.x_vel_des, R[3], c.y_vel_des, R[6], 0.f);
+        vw1 = dot3(R[1], c.x_vel_des, R[4], c.y_vel_des, R[7], 0.f);
+      }
+      const float max_pos_error = .1f;
+      const float p0 = c.position[0], p1 = c.position[1];
+      float xs = wpd0, ys = wpd1;
+      if (sub(xs, p0) > max_pos_error) xs = add(p0, max_pos_error);
+      if (sub(p0, xs) > max_pos_error) xs = sub(p0, max_pos_error);
+      if (sub(ys, p1) > max_pos_error) ys = add(p1, max_pos_error);
+      if (sub(p1, ys) > max_pos_error) ys = sub(p1, max_pos_error);
+      wpd0 = xs;
+      wpd1 = ys;
+      // i == 0: "start at current position": only the yaw does (:575)
+      const float t0[12] = {c.rpy_comp[0], c.rpy_comp[1], c.rpy[2], xs, ys, c.body_height,
+                            0.f, 0.f, c.yaw_turn_rate, vw0, vw1, 0.f};
+      for (int j = 0; j < 12; j++) s_t0[tl][j] = t0[j];
+      s_walk[tl][0] = mul(dt, c.yaw_turn_rate);
+      s_walk[tl][1] = mul(dt, vw0);
+      s_walk[tl][2] = mul(dt, vw1);
     }
-    const float max_pos_error = .1f;
-    const float p0 = c.position[0], p1 = c.position[1];
-    float xs = wpd0, ys = wpd1;
-    if (sub(xs, p0) > max_pos_error) xs = add(p0, max_pos_error);
-    if (sub(p0, xs) > max_pos_error) xs = sub(p0, max_pos_error);
-    if (sub(ys, p1) > max_pos_error) ys = add(p1, max_pos_error);
-    if (sub(p1, ys) > max_pos_error) ys = sub(p1, max_pos_error);
-    wpd0 = xs;
-    wpd1 = ys;
-    const float t0[12] = {c.rpy_comp[0], c.rpy_comp[1], c.yaw_des, xs, ys, c.body_height,
-                          0.f, 0.f, c.yaw_turn_rate, vw0, vw1, 0.f};
-    const float dx = mul(dt, vw0), dy = mul(dt, vw1), dyaw = mul(dt, c.yaw_turn_rate);
-    float yaw = c.rpy[2], x = xs, y = ys;  // i == 0: "start at current position": only the yaw does
-    for (int k = 0; k < h; k++) {
-      if (k > 0) { x = add(x, dx); y = add(y, dy); yaw = add(yaw, dyaw); }
-      for (int j = 0; j < 12; j++) traj[12 * k + j] = t0[j];
-      traj[12 * k + 2] = yaw;
-      traj[12 * k + 3] = x;
-      traj[12 * k + 4] = y;
+    s_gait[tl][0] = c.gait_kind;
+    s_gait[tl][1] = c.gait_iteration;
+    for (int j = 0; j < 4; j++) { s_gait[tl][2 + j] = c.gait_offsets[j]; s_gait[tl][6 + j] = c.gait_durations[j]; }
+    s_duty[tl] = c.gait_duty;
+    s_gait[tl][10] = c.stand;
+  }
+  __syncthreads();
+  {
+    const int base = blockIdx.x * FRONT_NT;
+    const int nrob = min(FRONT_NT, A.count - base);
+    const int tw = 12 * h;                                         // trajectory words per record
+    const int gw = (A.rec_stride - 4 * (CMPC_REC_TRAJ + 12 * h)) / 4;  // gait words per record (4 h bytes + padding)
+    for (int e = threadIdx.x; e < nrob * tw; e += FRONT_NT) {
+      const int rb = e / tw, w = e - rb * tw, k = w / 12, j = w - 12 * k;
+      float v = s_t0[rb][j];
+      if (j >= 2 && j <= 4 && !s_gait[rb][10]) {
+        const float d = s_walk[rb][j - 2];
+        for (int q = 0; q < k; q++) v = add(v, d);
+      }
+      reinterpret_cast<float*>(A.records + (size_t)(base + rb) * A.rec_stride)[CMPC_REC_TRAJ + w] = v;
+    }
+    // ---- getMpcTable (Gait.cpp:158-215), nIterations == horizon: four legs of a step per word ----
+    for (int e = threadIdx.x; e < nrob * gw; e += FRONT_NT) {
+      const int rb = e / gw, k = e - rb * gw;
+      unsigned word = 0u;
+      if (k < h) {
+        const int kind = s_gait[rb][0], it = s_gait[rb][1];
+        for (int j = 0; j < 4; j++) {
+          int on;
+          if (kind == CMPC_GAIT_MIXED_FREQUENCY) {
+            const int period = s_gait[rb][2 + j] > 0 ? s_gait[rb][2 + j] : 1;
+            const int progress = (k + it + 1) % period;
+            on = (float)progress < mul((float)period, s_duty[rb]);
+          } else {
+            int progress = (k + it + 1) % h - s_gait[rb][2 + j];
+            if (progress < 0) progress += h;
+            on = progress < s_gait[rb][6 + j];
+          }
+          word |= (unsigned)on << (8 * j);
+        }
+      }
+      reinterpret_cast<unsigned*>(A.records + (size_t)(base + rb) * A.rec_stride)[CMPC_REC_TRAJ + tw + k] = word;
     }
   }
-
-  // ---- getMpcTable (Gait.cpp:158-215), nIterations == horizon ----
-  for (int k = 0; k < h; k++)
-    for (int j = 0; j < 4; j++) {
-      int on;
-      if (c.gait_kind == CMPC_GAIT_MIXED_FREQUENCY) {
-        const int period = c.gait_offsets[j] > 0 ? c.gait_offsets[j] : 1;
-        const int progress = (k + c.gait_iteration + 1) % period;
-        on = (float)progress < mul((float)period, c.gait_duty);
-      } else {
-        int progress = (k + c.gait_iteration + 1) % h - c.gait_offsets[j];
-        if (progress < 0) progress += h;
-        on = progress < c.gait_durations[j];
-      }
-      gait[4 * k + j] = (unsigned char)on;
-    }
-  for (int k = 4 * h; k < A.rec_stride - 4 * (CMPC_REC_TRAJ + 12 * h); k++) gait[k] = 0;
+  if (i >= A.count) return;
+  const cmpc_command& c = A.cmds[i];
+  float* rec = reinterpret_cast<float*>(A.records + (size_t)i * A.rec_stride);
 
   // ---- solveDenseMPC (:618-828) ----
   float fe[6];
@@ -247,7 +281,7 @@ int cmpc_launch_frontend(const void* cmds, unsigned char* records, void* results
   A.dt = dt;
   A.alpha = alpha;
   for (int i = 0; i < 12; i++) A.weights[i] = weights[i];
-  cmpc_frontend_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A);
+  cmpc_frontend_kernel<<<(count + FRONT_NT - 1) / FRONT_NT, FRONT_NT, 0, (cudaStream_t)stream>>>(A);
   return (int)cudaGetLastError();
 }
 
