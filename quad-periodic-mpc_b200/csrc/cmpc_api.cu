@@ -248,6 +248,8 @@ struct cmpc_batch {
   size_t qws_bytes[kMaxStreams] = {};
   int* d_sched[kMaxStreams] = {};
   int sched_ints[kMaxStreams] = {};
+  int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [capacity] keys, [capacity] hardest-first worklist
+  bool lpt = true;                    // CMPC_LPT=0: natural instance order in the active-set kernel
   std::vector<PipePlan> plans;        // launch plans by (reduced size bound, horizon, adaptive)
   HostBinding bound;                  // cmpc_batch_bind_host
   // adaptive stage
@@ -602,7 +604,15 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_condense_kernel launch");
     b->launches++;
     if (int e = prof_end(CMPC_K_ASSEMBLE)) return e;
+    const bool lpt = tiled && fast && b->lpt;
+    Q.lpt_hist = nullptr;
+    Q.lpt_key = nullptr;
     if (tiled) {  // the assembly kernel left H tiles: invert them in place on the FP64 tensor cores
+      if (lpt) {
+        Q.lpt_hist = b->d_lpt[si];
+        Q.lpt_key = b->d_lpt[si] + 64;
+        CK(cudaMemsetAsync(Q.lpt_hist, 0, sizeof(int) * 64, st));
+      }
       Q.sched = b->d_sched[si] + 4 * c + 3;
       const int ipc2 = cmpc_invert_instances_per_cta();
       if (int e = prof_begin()) return e;
@@ -620,6 +630,12 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
     } else {
       Q.overflow_list = nullptr;
+    }
+    if (lpt) {  // hardest instances first: the makespan of the kernel is its longest active-set run
+      rc = cmpc_launch_lpt_order(Q.lpt_hist, Q.lpt_key, b->d_lpt[si] + 64 + b->capacity, cnt, st);
+      if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_lpt_order_kernel launch");
+      b->launches++;
+      Q.worklist = b->d_lpt[si] + 64 + b->capacity;
     }
     if (fast) rc = cmpc_launch_dual_fast(Q, std::min(cnt, b->sm_count * per_sm_fast), st);
     else rc = cmpc_launch_dual(Q, wpc1, std::min((cnt + wpc1 - 1) / wpc1, b->sm_count * per_sm2), st);
@@ -813,6 +829,8 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMalloc(&b->d_iters, sizeof(int) * cap));
   CK(cudaMalloc(&b->d_active, cap * 20 * hm));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_lpt[i], sizeof(int) * (64 + 2 * cap)));
+  if (const char* e = std::getenv("CMPC_LPT")) b->lpt = std::atoi(e) != 0;
   CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMallocHost(&b->h_forces, sizeof(double) * cap * 12 * hm));
@@ -834,7 +852,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
   cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops); cudaFree(b->d_phase);
   cudaFree(b->d_gws);
-  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); }
+  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); cudaFree(b->d_lpt[i]); }
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFree(b->d_cmds); cudaFree(b->d_results); cudaFree(b->d_fext);

@@ -92,6 +92,10 @@ struct CmpcParams {
   int* sched;                 // work counter of THIS launch (zeroed by the host)
   int k_tiled;                // K is stored as 36 lower-triangular 8x8 tiles (cmpc_condense_mma.cuh), else row-major n x n
   int qws_goff;               // offset (doubles) of g in a slot; x0 follows at +nmax, the header at +2 nmax
+  // hardest-first order of the active-set kernel: the inversion kernel files every instance under the number of
+  // constraint rows its unconstrained optimum violates (a good predictor of the active-set iterations)
+  int* lpt_hist;              // [64] instances per key, zeroed per launch; null = natural order
+  int* lpt_key;               // [count] key << 24 | position within the key's bucket
   // optional phase clocks (profiling aid): CMPC_PH_COUNT counters of SM cycles summed over CTAs, thread 0 only
   unsigned long long* phase_cycles;
 };
@@ -148,6 +152,7 @@ int cmpc_condense_instances_per_cta(int cshape);
 int cmpc_invert_max_ctas_per_sm(void);
 int cmpc_invert_instances_per_cta(void);
 int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream);
+int cmpc_launch_lpt_order(const int* hist, const int* key, int* worklist, int count, void* stream);
 size_t cmpc_dual_fast_smem_bytes(int nmax, int qcap);  /* per CTA of one warp; qcap <= 32, nmax <= 128 */
 int cmpc_dual_fast_max_ctas_per_sm(int nmax, size_t smem);
 int cmpc_launch_dual_fast(const CmpcParams& P, int grid, void* stream);

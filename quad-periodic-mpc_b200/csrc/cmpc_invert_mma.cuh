@@ -52,6 +52,27 @@ __device__ __forceinline__ void publish_panel(const double (&t)[36][2], double* 
   }
 }
 
+// Hardest-first scheduling of the active-set kernel: count the constraint rows that x0 (staged in `xs`, shared
+// memory) violates — five rows per contact foot-step, as cmpc_dual_fast.cuh lays them out — and file the instance.
+__device__ __forceinline__ void lpt_file(const CmpcParams& P, int inst, int nc, const int* hdr, const double* xs, int lane) {
+  if (!P.lpt_hist) return;
+  int viol = 0;
+  if (nc > 0) {
+    const unsigned char* gvb = reinterpret_cast<const unsigned char*>(hdr + 2) + CMPC_MAX_FS;
+    for (int f = lane; f < nc; f += 32) {
+      const double fx = xs[3 * f] * P.mu_inv, fy = xs[3 * f + 1] * P.mu_inv, fz = xs[3 * f + 2];
+      const double tol = -P.tol_violation;
+      viol += (fx + fz < tol) + (fz - fx < tol) + (fy + fz < tol) + (fz - fy < tol) + ((double)gvb[f] * P.f_max - fz < tol);
+    }
+    viol = __reduce_add_sync(0xffffffffu, viol);
+  }
+  if (lane == 0) {
+    const int key = min(viol, 63);
+    const int pos = atomicAdd(P.lpt_hist + key, 1);
+    P.lpt_key[inst] = (key << 24) | pos;
+  }
+}
+
 constexpr int INV_WPC = 1;  // warps per CTA: one, so that the register file holds ten instances per SM
 constexpr int INV_WARP_SMEM = 8 * (2 * 8 * MMA_PS + 64);
 }  // namespace
@@ -86,7 +107,7 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
     double* slot = P.qws + (size_t)inst * P.qws_stride;
     const int* hdr = reinterpret_cast<const int*>(slot + P.qws_goff + 2 * P.nmax + 2);
     const int nc = hdr[0];
-    if (hdr[1] != CMPC_ST_SOLVED) continue;
+    if (hdr[1] != CMPC_ST_SOLVED) { lpt_file(P, inst, 0, hdr, pan, lane); continue; }
     const int n = 3 * nc, nblk = (n + 7) >> 3;
     flops_acc += (unsigned)(n * n * (n + 2));
     double t[36][2];
@@ -170,8 +191,13 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
           const int j = 8 * J + 2 * q;
           if (j < n) xo[j] = -scale * a0;
           if (j + 1 < n) xo[j + 1] = -scale * a1;
+          pan[j] = -scale * a0;  // staged for lpt_file (the panel is free now)
+          pan[j + 1] = -scale * a1;
         }
       }
+    __syncwarp();
+    lpt_file(P, inst, nc, hdr, pan, lane);
+    __syncwarp();
     INV_TICK(CMPC_PH_LOAD)
   }
 #undef INV_TICK
@@ -262,7 +288,7 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
     double* slot = P.qws + (size_t)inst * P.qws_stride;
     const int* hdr = reinterpret_cast<const int*>(slot + P.qws_goff + 2 * P.nmax + 2);
     const int nc = hdr[0];
-    if (hdr[1] != CMPC_ST_SOLVED) continue;
+    if (hdr[1] != CMPC_ST_SOLVED) { lpt_file(P, inst, 0, hdr, pan, lane); continue; }
     const int n = 3 * nc, nblk = (n + 7) >> 3;
     flops_acc += (unsigned)(n * n * (n + 2));
     double t[36][2];
@@ -371,8 +397,13 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
           const int j = 8 * J + 2 * q;
           if (j < n) xo[j] = -scale * a0;
           if (j + 1 < n) xo[j + 1] = -scale * a1;
+          pan[j] = -scale * a0;  // staged for lpt_file (the panel is free now)
+          pan[j + 1] = -scale * a1;
         }
       }
+    __syncwarp();
+    lpt_file(P, inst, nc, hdr, pan, lane);
+    __syncwarp();
     WS_TICK(CMPC_PH_LOAD)
   }
 #undef WS_TICK

@@ -203,6 +203,29 @@ int launch_invert_t(const CmpcParams& P, int grid, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 }  // namespace
+// hardest-first order of the active-set kernel: instance -> position from the key histogram the inversion kernel left
+namespace {
+__global__ void __launch_bounds__(256) cmpc_lpt_order_kernel(const int* __restrict__ hist, const int* __restrict__ key,
+                                                             int* __restrict__ worklist, int count) {
+  __shared__ int off[64];
+  if (threadIdx.x < 64) {  // instances with a larger key come first
+    int o = 0;
+    for (int k = 63; k > (int)threadIdx.x; k--) o += hist[k];
+    off[threadIdx.x] = o;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int kv = key[i];
+  worklist[off[kv >> 24] + (kv & 0xffffff)] = i;
+}
+}  // namespace
+int cmpc_launch_lpt_order(const int* hist, const int* key, int* worklist, int count, void* stream) {
+  if (count <= 0) return 0;
+  cmpc_lpt_order_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(hist, key, worklist, count);
+  return (int)cudaGetLastError();
+}
+
 // warp-specialised variant (default): helper warps carry the pivot chains; CMPC_INV_WS=0 selects the kernel above
 namespace {
 bool inv_ws() {
