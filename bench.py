@@ -282,8 +282,9 @@ def run_b200(args, rank, world, local_rank):
                        "l2": "inputs rotate through a ring of %d distinct resident batches (%.0f MB > L2)"
                              % (ring, total * (rec_bytes + out_bytes) / 1e6),
                        "sharding": "independent instances, no data-path collective",
-                       "pipelining": "successive steps alternate between two CUDA streams of the engine (a step is "
-                                     "three kernels: assembly, FP64-tensor inversion, dual active set)"},
+                       "pipelining": "successive steps rotate through the engine's eight CUDA streams (a step is three "
+                                     "kernels: assembly, FP64-tensor inversion, dual active set, plus the hardest-first "
+                                     "ordering pass and the working-set overflow launch)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64, "unit": "TFLOP/s",
                          "frac": achieved / fp64 if fp64 else None,
                          "traffic": NCU_TRAFFIC.get(dom),

@@ -206,13 +206,13 @@ struct cmpc_batch {
   int capacity = 0;
   int sm_count = 0;
   cudaStream_t stream[kMaxStreams] = {};  // [0] is "the batch stream"; the others only carry pipelined chunks / solves
-  int nstreams = 2;                       // streams that successive solve_range calls rotate through (CMPC_NSTREAMS)
+  int nstreams = kMaxStreams;             // streams that successive solve_range calls rotate through (CMPC_NSTREAMS); measured: profiles/
   int split = 1;                          // parts a solve_range call is cut into, one per stream in turn (CMPC_SPLIT)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, mark0 = nullptr, mark1 = nullptr;
   cudaEvent_t chunk_done[kMaxChunks] = {};
   cudaEvent_t packed[kMaxChunks] = {};    // end-to-end call: chunk c's records are in HBM
-  // successive solve_range calls alternate between the two streams so that the latency-bound tail of one
-  // batch overlaps the next batch's kernels; these events carry the cross-stream ordering
+  // successive solve_range calls rotate through the streams so that the latency-bound tails of a batch's kernels
+  // overlap the kernels of the following batches; these events carry the cross-stream ordering
   cudaEvent_t join_ev = nullptr;      // scratch: "stream i has reached this point"
   cudaEvent_t fork_ev = nullptr;      // scratch: "stream 0 has reached this point"
   cudaEvent_t prof_ev[CMPC_K_COUNT + 1] = {};  // cmpc_batch_profile_range: events between the kernel classes
@@ -943,10 +943,10 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
     if (si != 0) {
       int rcf = fork_streams(b, si);  // after the uploads / marks already enqueued on the batch stream
       if (rcf) return rcf;
-      b->dirty |= 1u << si;
     }
     if (part == 0) CK(cudaEventRecord(b->ev0, b->stream[si]));
     int rc = launch_range(b, pf, pn, b->max_contact, si);
+    if (si != 0) b->dirty |= 1u << si;  // after the launch: growing a workspace inside it drains every stream and clears the marks
     if (rc) return rc;
     if (part == parts - 1) CK(cudaEventRecord(b->ev1, b->stream[si]));
   }

@@ -316,8 +316,8 @@ def test_every_kernel_path_agrees(built_lib, h, gaits, nseg, B):
 
 
 def test_interleaved_uploads_and_solves_stay_ordered(built_lib):
-    """Successive solve_range calls alternate between the engine's two streams; uploads, marks and downloads
-    must still see them in program order."""
+    """Successive solve_range calls rotate through the engine's streams; uploads, marks and downloads
+    must still see them in program order (a stream's first use grows its workspace mid-call)."""
     h, B, ring = 10, 256, 6
     inst = synth.make_batch(B * ring, horizon=h, seed=701, spread=2.0)
     b = engine.Batch(B * ring)
