@@ -541,21 +541,25 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
   const int nchunks = (count + chunk - 1) / chunk;
   const size_t need = (size_t)chunk * slot * sizeof(double);
   if (need > b->qws_bytes[si] || 4 * nchunks > b->sched_ints[si]) {
+    // grow the workspaces of every stream in use at once: the first solves of the other streams then find theirs
     { int rcs = sync_all(b); if (rcs) return rcs; }
-    if (need > b->qws_bytes[si]) {
-      if (b->d_qws[si]) CK(cudaFree(b->d_qws[si]));
-      b->d_qws[si] = nullptr;
-      b->qws_bytes[si] = 0;
-      CK(cudaMalloc(&b->d_qws[si], need));
-      b->qws_bytes[si] = need;
-    }
-    if (4 * nchunks > b->sched_ints[si]) {
-      if (b->d_sched[si]) CK(cudaFree(b->d_sched[si]));
-      b->d_sched[si] = nullptr;
-      b->sched_ints[si] = 0;
-      const int ints = std::max(4 * nchunks, 1024);
-      CK(cudaMalloc(&b->d_sched[si], sizeof(int) * ints));
-      b->sched_ints[si] = ints;
+    for (int k = 0; k < kMaxStreams; k++) {
+      if (k != si && !(k < b->nstreams || k < 2)) continue;
+      if (need > b->qws_bytes[k]) {
+        if (b->d_qws[k]) CK(cudaFree(b->d_qws[k]));
+        b->d_qws[k] = nullptr;
+        b->qws_bytes[k] = 0;
+        CK(cudaMalloc(&b->d_qws[k], need));
+        b->qws_bytes[k] = need;
+      }
+      if (4 * nchunks > b->sched_ints[k]) {
+        if (b->d_sched[k]) CK(cudaFree(b->d_sched[k]));
+        b->d_sched[k] = nullptr;
+        b->sched_ints[k] = 0;
+        const int ints = std::max(4 * nchunks, 1024);
+        CK(cudaMalloc(&b->d_sched[k], sizeof(int) * ints));
+        b->sched_ints[k] = ints;
+      }
     }
   }
   CK(cudaMemsetAsync(b->d_sched[si], 0, sizeof(int) * 4 * nchunks, st));
