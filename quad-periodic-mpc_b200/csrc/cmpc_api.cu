@@ -248,8 +248,10 @@ struct cmpc_batch {
   size_t qws_bytes[kMaxStreams] = {};
   int* d_sched[kMaxStreams] = {};
   int sched_ints[kMaxStreams] = {};
+  int* d_resume[kMaxStreams] = {};    // per stream: working sets of the instances in d_overflow, for the full-capacity launch
   int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [capacity] keys, [capacity] hardest-first worklist
   bool lpt = true;                    // CMPC_LPT=0: natural instance order in the active-set kernel
+  bool resume = true;                 // CMPC_RESUME=0: overflowed instances restart from scratch in the full-capacity launch
   std::vector<PipePlan> plans;        // launch plans by (reduced size bound, horizon, adaptive)
   HostBinding bound;                  // cmpc_batch_bind_host
   // adaptive stage
@@ -628,9 +630,11 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.sched = b->d_sched[si] + 4 * c + 1;
     Q.qcap = qcap1;
     if (int e = prof_begin()) return e;
+    Q.resume = nullptr;
     if (qcap1 < nmax) {
       Q.overflow_list = b->d_overflow[si];
       Q.overflow_count = b->d_overflow[si] + b->capacity;
+      if (fast && b->resume) Q.resume = b->d_resume[si];
       CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
     } else {
       Q.overflow_list = nullptr;
@@ -834,6 +838,8 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMalloc(&b->d_active, cap * 20 * hm));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_lpt[i], sizeof(int) * (64 + 2 * cap)));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume[i], sizeof(int) * CMPC_RESUME_INTS * cap));
+  if (const char* e = std::getenv("CMPC_RESUME")) b->resume = std::atoi(e) != 0;
   if (const char* e = std::getenv("CMPC_LPT")) b->lpt = std::atoi(e) != 0;
   CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long) * CMPC_K_COUNT));
@@ -856,7 +862,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
   cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops); cudaFree(b->d_phase);
   cudaFree(b->d_gws);
-  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); cudaFree(b->d_lpt[i]); }
+  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); cudaFree(b->d_lpt[i]); cudaFree(b->d_resume[i]); }
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFree(b->d_cmds); cudaFree(b->d_results); cudaFree(b->d_fext);

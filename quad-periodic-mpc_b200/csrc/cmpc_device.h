@@ -6,6 +6,7 @@
 #include "../../include/cmpc_b200.h"
 
 #define CMPC_MAX_FS 80 /* 4 * CMPC_MAX_HORIZON rounded up */
+#define CMPC_RESUME_INTS 20 /* q, iterations, 32 working-set rows as 16-bit ids */
 
 // ---------------------------------------------------------------------------
 // Instance record (HBM, one per MPC instance, 16-byte aligned, fetched with a
@@ -68,6 +69,8 @@ struct CmpcParams {
   const int* count_ptr;       // optional device-side instance count (tier-2 launch), capped by `count`
   int* overflow_list;         // instances whose working set outgrew qcap
   int* overflow_count;
+  int* resume;                // [overflow entries][CMPC_RESUME_INTS]: the working set an overflowed instance had reached
+                              // (written by the first tier next to overflow_list, read by the full-capacity launch)
   double* forces;             // [count][12h]
   double* objective;          // [count]
   int* status;                // [count]

@@ -139,6 +139,79 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
         isact[c] = 0;
       }
       __syncwarp();
+      // ---- resume: the first tier ran out of working-set capacity at a valid state of the method (x optimal on the
+      //      face of its working set A, multipliers >= 0).  Rebuild that state from A alone: border P and cache K N
+      //      row by row (no line searches), then u = -P s_A(x0), x = x0 + K N u ----
+      if (P.resume && P.worklist) {
+        const int* rs = P.resume + (size_t)slot_i * CMPC_RESUME_INTS;
+        const int rq = min(rs[0], qcap);
+        for (int k = 0; k < rq; k++) {
+          const int w2 = rs[2 + (k >> 1)];
+          const int p = (k & 1) ? ((w2 >> 16) & 0xffff) : (w2 & 0xffff);
+          int pia, piz;
+          double pva, pvz;
+          cons_of(p, mu_inv, pia, pva, piz, pvz);
+          for (int i = lane; i < n; i += 32)
+            kn[i] = pva * k_entry(slot, n, tiled, pia, i) + pvz * k_entry(slot, n, tiled, piz, i);
+          __syncwarp();
+          const double scale = pva * kn[pia] + pvz * kn[piz];
+          for (int l = lane; l < q; l += 32) {
+            int ia, iz;
+            double va, vz;
+            cons_of(act[l], mu_inv, ia, va, iz, vz);
+            dvec[l] = va * kn[ia] + vz * kn[iz];
+          }
+          __syncwarp();
+          double dr = 0.0;
+          for (int l = lane; l < q; l += 32) {
+            double acc = 0.0;
+            for (int j = 0; j < q; j++) acc = fma(psym(Pp, l, j), dvec[j], acc);
+            rvec[l] = acc;
+            dr = fma(dvec[l], acc, dr);
+          }
+          dr = warp_sum(dr);
+          __syncwarp();
+          const double rho2_inv = fast_rcp(scale - dr);
+          for (int l = lane; l < q; l += 32) {
+            const double rk = rvec[l] * rho2_inv;
+            for (int j = 0; j <= l; j++) Pp[l * (l + 1) / 2 + j] = fma(rk, rvec[j], Pp[l * (l + 1) / 2 + j]);
+            Pp[q * (q + 1) / 2 + l] = -rk;
+          }
+          for (int i = lane; i < n; i += 32) KN[q * nmax + i] = kn[i];
+          if (lane == 0) {
+            Pp[q * (q + 1) / 2 + q] = rho2_inv;
+            act[q] = (short)p;
+            isact[p] = 1;
+          }
+          q++;
+          __syncwarp();
+        }
+        if (rq > 0) {
+          for (int k = lane; k < q; k += 32) {
+            double acc = 0.0;
+            for (int l = 0; l < q; l++) acc = fma(psym(Pp, k, l), s[act[l]], acc);
+            u[k] = fmax(-acc, 0.0);
+          }
+          __syncwarp();
+          for (int i = lane; i < n; i += 32) {
+            double acc = x[i];
+            for (int k = 0; k < q; k++) acc = fma(u[k], KN[k * nmax + i], acc);
+            x[i] = acc;
+          }
+          __syncwarp();
+          for (int c = lane; c < m; c += 32) {
+            int ia, iz;
+            double va, vz;
+            cons_of(c, mu_inv, ia, va, iz, vz);
+            double b = 0.0;
+            if (c % 5 == 4) b = -(double)gv[c / 5] * P.f_max;
+            s[c] = va * x[ia] + vz * x[iz] - b;
+          }
+          iters = rs[1];
+          flops_acc += 2.0 * (double)rq * ((double)q * q + 2.0 * n);
+          __syncwarp();
+        }
+      }
       bool done = false;
       while (!done) {
         // most violated row outside the working set

@@ -373,9 +373,20 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
       tclk = now;
     }
     if (status == CMPC_ST_WSOVERFLOW && P.overflow_list) {
-      if (lane == 0) {  // left for the any-capacity launch
-        const int pos = atomicAdd(P.overflow_count, 1);
+      // left for the any-capacity launch, which resumes from the working set reached here (the candidate row that
+      // did not fit is found again there): slot k's row id travels as 16 bits
+      int pos = 0;
+      if (lane == 0) {
+        pos = atomicAdd(P.overflow_count, 1);
         P.overflow_list[pos] = inst;
+      }
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (P.resume) {
+        int* rs = P.resume + (size_t)pos * CMPC_RESUME_INTS;
+        const int mine = (lane < q) ? sact : 0;
+        const int nb = __shfl_down_sync(0xffffffffu, mine, 1);
+        if (!(lane & 1)) rs[2 + (lane >> 1)] = (mine & 0xffff) | (nb << 16);
+        if (lane == 0) { rs[0] = q; rs[1] = iters - 1; }
       }
       __syncwarp();
       continue;
