@@ -2,7 +2,7 @@
 // solveDenseMPC (ConvexMPCLocomotion.cpp:511-870) plus the gait's getMpcTable (Gait.cpp:158-215) for a batch of
 // robots.  Three small kernels around the solve pipeline:
 //
-//   cmpc_frontend_kernel      one thread per robot: reference trajectory, contact table, r = pFoot - p, the f_ext
+//   cmpc_frontend_kernel      one warp per robot: reference trajectory, contact table, r = pFoot - p, the f_ext
 //                             residual of the previous step's model, the x_drag integral -> the instance record
 //   cmpc_history_push_kernel  one CTA per robot: (simulation_time, f_ext[3]) appended to the 400-sample window the
 //                             disturbance estimator fits (SolverMPC.cpp:688-706)
@@ -37,31 +37,87 @@ struct FrontArgs {
   float weights[12];
 };
 
-constexpr int FRONT_NT = 64;  // robots per CTA: small CTAs, so that a few thousand robots still cover every SM
+constexpr int FRONT_WPC = 4;  // robots (warps) per CTA
 
-__global__ void __launch_bounds__(FRONT_NT) cmpc_frontend_kernel(const __grid_constant__ FrontArgs A) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// the f_ext residual of the previous step's model: f_external = x_k - A_prev x_prev - B_prev u_prev, rows 6..11, with
+// the signs of ConvexMPCLocomotion.cpp:771
+__device__ void external_force(const cmpc_command& c, float fe[6]) {
+  const float* R = c.log_R;
+  const float Ib[3] = {0.07f, 0.26f, 0.242f};
+  float Iw[9];  // R I_body R^T
+  for (int a = 0; a < 3; a++)
+    for (int bb = 0; bb < 3; bb++)
+      Iw[3 * a + bb] = dot3(mul(R[3 * a], Ib[0]), R[3 * bb], mul(R[3 * a + 1], Ib[1]), R[3 * bb + 1], mul(R[3 * a + 2], Ib[2]), R[3 * bb + 2]);
+  // inverse by cofactors / determinant
+  const float c00 = sub(mul(Iw[4], Iw[8]), mul(Iw[5], Iw[7]));
+  const float c01 = sub(mul(Iw[5], Iw[6]), mul(Iw[3], Iw[8]));
+  const float c02 = sub(mul(Iw[3], Iw[7]), mul(Iw[4], Iw[6]));
+  const float det = add(add(mul(Iw[0], c00), mul(Iw[1], c01)), mul(Iw[2], c02));
+  const float id = __fdiv_rn(1.f, det);
+  float Ii[9];
+  Ii[0] = mul(c00, id);
+  Ii[1] = mul(sub(mul(Iw[2], Iw[7]), mul(Iw[1], Iw[8])), id);
+  Ii[2] = mul(sub(mul(Iw[1], Iw[5]), mul(Iw[2], Iw[4])), id);
+  Ii[3] = mul(c01, id);
+  Ii[4] = mul(sub(mul(Iw[0], Iw[8]), mul(Iw[2], Iw[6])), id);
+  Ii[5] = mul(sub(mul(Iw[2], Iw[3]), mul(Iw[0], Iw[5])), id);
+  Ii[6] = mul(c02, id);
+  Ii[7] = mul(sub(mul(Iw[1], Iw[6]), mul(Iw[0], Iw[7])), id);
+  Ii[8] = mul(sub(mul(Iw[0], Iw[4]), mul(Iw[1], Iw[3])), id);
+  float bu_w[3] = {0.f, 0.f, 0.f}, bu_v[3] = {0.f, 0.f, 0.f};  // (B_prev u_prev) rows 6..8 and 9..11
+  const float minv = __fdiv_rn(1.f, 12.f);
+  for (int leg = 0; leg < 4; leg++) {
+    const float u0 = -c.log_foot_force[3 * leg], u1 = -c.log_foot_force[3 * leg + 1], u2 = -c.log_foot_force[3 * leg + 2];
+    const float rx = c.log_r_feet[leg], ry = c.log_r_feet[4 + leg], rz = c.log_r_feet[8 + leg];
+    // [r]x u
+    const float t0 = sub(mul(ry, u2), mul(rz, u1));
+    const float t1 = sub(mul(rz, u0), mul(rx, u2));
+    const float t2 = sub(mul(rx, u1), mul(ry, u0));
+    for (int a = 0; a < 3; a++) bu_w[a] = add(bu_w[a], dot3(Ii[3 * a], t0, Ii[3 * a + 1], t1, Ii[3 * a + 2], t2));
+    bu_v[0] = add(bu_v[0], mul(minv, u0));
+    bu_v[1] = add(bu_v[1], mul(minv, u1));
+    bu_v[2] = add(bu_v[2], mul(minv, u2));
+  }
+  // A_prev rows 6..10 are zero; row 11: x_drag * x_prev[9] + x_prev[12], x_prev[12] = -9.81
+  const float a11 = add(mul(c.log_x_drag, c.log_x_prev[9]), -9.81f);
+  float f6[6];
+  for (int a = 0; a < 3; a++) f6[a] = sub(c.omega_world[a], bu_w[a]);
+  f6[3] = sub(c.v_world[0], bu_v[0]);
+  f6[4] = sub(c.v_world[1], bu_v[1]);
+  f6[5] = sub(sub(c.v_world[2], a11), bu_v[2]);
+  fe[0] = -f6[0]; fe[1] = -f6[1]; fe[2] = f6[2]; fe[3] = f6[3]; fe[4] = f6[4]; fe[5] = f6[5];
+}
+
+// One warp per robot.  The command struct is staged in shared memory with coalesced loads; lane 0 works out the
+// trajectory constants and the command state (updateMPCIfNeeded), lane 1 the f_ext residual (solveDenseMPC); then the
+// warp fills the record together, consecutive lanes on consecutive words, every walking trajectory entry re-running
+// its own float accumulation (:579-581).
+__global__ void __launch_bounds__(32 * FRONT_WPC) cmpc_frontend_kernel(const __grid_constant__ FrontArgs A) {
+  constexpr int CW = sizeof(cmpc_command) / 4;
+  __shared__ __align__(16) unsigned s_cmd[FRONT_WPC][CW];
+  __shared__ float s_t0[FRONT_WPC][12];
+  __shared__ float s_walk[FRONT_WPC][3];  // dt * yaw_turn_rate, dt * v_des_world[0], dt * v_des_world[1]
+  __shared__ float s_fe[FRONT_WPC][6];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * FRONT_WPC + w;
+  if (i >= A.count) return;
   const int h = A.horizon;
   const float dt = A.dt;
-
-  // ---- updateMPCIfNeeded (:511-594): reference trajectory.  The thread of a robot works out the twelve constant
-  //      entries and the three walks (yaw, x, y); the CTA then fills the 12 h floats of its robots' records together,
-  //      consecutive threads on consecutive words, every entry re-running its own float accumulation (:579-581) ----
-  __shared__ float s_t0[FRONT_NT][12];
-  __shared__ float s_walk[FRONT_NT][3];   // dt * yaw_turn_rate, dt * v_des_world[0], dt * v_des_world[1]; 0 for a stand
-  __shared__ int s_gait[FRONT_NT][11];    // kind, iteration, offsets[4], durations[4], stand
-  __shared__ float s_duty[FRONT_NT];
-  const int tl = threadIdx.x;
-  float wpd0 = 0.f, wpd1 = 0.f;
-  if (i < A.count) {
-    const cmpc_command& c = A.cmds[i];
-    wpd0 = c.world_position_desired[0];
-    wpd1 = c.world_position_desired[1];
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(A.cmds + i);
+    for (int k = lane; k < CW; k += 32) s_cmd[w][k] = src[k];
+  }
+  __syncwarp();
+  const cmpc_command& c = *reinterpret_cast<const cmpc_command*>(s_cmd[w]);
+  cmpc_command_result& res = A.results[i];
+  if (lane == 0) {
+    // ---- updateMPCIfNeeded (:511-594) ----
+    float wpd0 = c.world_position_desired[0], wpd1 = c.world_position_desired[1];
     if (c.stand) {
       const float t0[12] = {c.roll_des, c.pitch_des, c.stand_traj[2], c.stand_traj[0], c.stand_traj[1], c.body_height,
                             0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int j = 0; j < 12; j++) s_t0[tl][j] = t0[j];
-      s_walk[tl][0] = s_walk[tl][1] = s_walk[tl][2] = 0.f;   // the stand trajectory is constant (:524-531)
+      for (int j = 0; j < 12; j++) s_t0[w][j] = t0[j];
+      s_walk[w][0] = s_walk[w][1] = s_walk[w][2] = 0.f;  // the stand trajectory is constant (:524-531)
     } else {
       float vw0 = c.x_vel_des, vw1 = c.y_vel_des;
       if (!c.omni_mode) {  // rBody^T * (x_vel_des, y_vel_des, 0)
@@ -81,136 +137,82 @@ __global__ void __launch_bounds__(FRONT_NT) cmpc_frontend_kernel(const __grid_co
       // i == 0: "start at current position": only the yaw does (:575)
       const float t0[12] = {c.rpy_comp[0], c.rpy_comp[1], c.rpy[2], xs, ys, c.body_height,
                             0.f, 0.f, c.yaw_turn_rate, vw0, vw1, 0.f};
-      for (int j = 0; j < 12; j++) s_t0[tl][j] = t0[j];
-      s_walk[tl][0] = mul(dt, c.yaw_turn_rate);
-      s_walk[tl][1] = mul(dt, vw0);
-      s_walk[tl][2] = mul(dt, vw1);
+      for (int j = 0; j < 12; j++) s_t0[w][j] = t0[j];
+      s_walk[w][0] = mul(dt, c.yaw_turn_rate);
+      s_walk[w][1] = mul(dt, vw0);
+      s_walk[w][2] = mul(dt, vw1);
     }
-    s_gait[tl][0] = c.gait_kind;
-    s_gait[tl][1] = c.gait_iteration;
-    for (int j = 0; j < 4; j++) { s_gait[tl][2 + j] = c.gait_offsets[j]; s_gait[tl][6 + j] = c.gait_durations[j]; }
-    s_duty[tl] = c.gait_duty;
-    s_gait[tl][10] = c.stand;
+    // the x_drag integral moves after update_x_drag has taken the old value (:809-816)
+    float xci = c.x_comp_integral;
+    const float vx = c.v_world[0];
+    if (vx > 0.3f || vx < -0.3f) {
+      const float pz_err = sub(c.ground_z, c.body_height);
+      xci = add(xci, __fdiv_rn(mul(mul(c.cmpc_x_drag, pz_err), dt), vx));
+    }
+    res.world_position_desired[0] = wpd0;
+    res.world_position_desired[1] = wpd1;
+    res.x_comp_integral = xci;
+    if (A.sim_time) A.sim_time[i] = c.sim_time;
+  } else if (lane == 1) {
+    // ---- solveDenseMPC (:647-776): f_ext stays as it was without /log_data ----
+    float fe[6];
+    for (int k = 0; k < 6; k++) fe[k] = A.f_ext[(size_t)i * 6 + k];
+    if (c.have_log) {
+      external_force(c, fe);
+      for (int k = 0; k < 6; k++) A.f_ext[(size_t)i * 6 + k] = fe[k];
+    }
+    for (int k = 0; k < 6; k++) { s_fe[w][k] = fe[k]; res.f_ext[k] = fe[k]; }
   }
-  __syncthreads();
-  {
-    const int base = blockIdx.x * FRONT_NT;
-    const int nrob = min(FRONT_NT, A.count - base);
-    const int tw = 12 * h;                                         // trajectory words per record
-    const int gw = (A.rec_stride - 4 * (CMPC_REC_TRAJ + 12 * h)) / 4;  // gait words per record (4 h bytes + padding)
-    for (int e = threadIdx.x; e < nrob * tw; e += FRONT_NT) {
-      const int rb = e / tw, w = e - rb * tw, k = w / 12, j = w - 12 * k;
-      float v = s_t0[rb][j];
-      if (j >= 2 && j <= 4 && !s_gait[rb][10]) {
-        const float d = s_walk[rb][j - 2];
-        for (int q = 0; q < k; q++) v = add(v, d);
-      }
-      reinterpret_cast<float*>(A.records + (size_t)(base + rb) * A.rec_stride)[CMPC_REC_TRAJ + w] = v;
-    }
-    // ---- getMpcTable (Gait.cpp:158-215), nIterations == horizon: four legs of a step per word ----
-    for (int e = threadIdx.x; e < nrob * gw; e += FRONT_NT) {
-      const int rb = e / gw, k = e - rb * gw;
-      unsigned word = 0u;
-      if (k < h) {
-        const int kind = s_gait[rb][0], it = s_gait[rb][1];
-        for (int j = 0; j < 4; j++) {
-          int on;
-          if (kind == CMPC_GAIT_MIXED_FREQUENCY) {
-            const int period = s_gait[rb][2 + j] > 0 ? s_gait[rb][2 + j] : 1;
-            const int progress = (k + it + 1) % period;
-            on = (float)progress < mul((float)period, s_duty[rb]);
-          } else {
-            int progress = (k + it + 1) % h - s_gait[rb][2 + j];
-            if (progress < 0) progress += h;
-            on = progress < s_gait[rb][6 + j];
-          }
-          word |= (unsigned)on << (8 * j);
-        }
-      }
-      reinterpret_cast<unsigned*>(A.records + (size_t)(base + rb) * A.rec_stride)[CMPC_REC_TRAJ + tw + k] = word;
-    }
-  }
-  if (i >= A.count) return;
-  const cmpc_command& c = A.cmds[i];
+  __syncwarp();
   float* rec = reinterpret_cast<float*>(A.records + (size_t)i * A.rec_stride);
-
-  // ---- solveDenseMPC (:618-828) ----
-  float fe[6];
-  for (int k = 0; k < 6; k++) fe[k] = A.f_ext[(size_t)i * 6 + k];
-  if (c.have_log) {
-    // f_external = x_k - A_prev x_prev - B_prev u_prev, rows 6..11 (:650-771)
-    const float* R = c.log_R;
-    const float Ib[3] = {0.07f, 0.26f, 0.242f};
-    float Iw[9];  // R I_body R^T
-    for (int a = 0; a < 3; a++)
-      for (int bb = 0; bb < 3; bb++)
-        Iw[3 * a + bb] = dot3(mul(R[3 * a], Ib[0]), R[3 * bb], mul(R[3 * a + 1], Ib[1]), R[3 * bb + 1], mul(R[3 * a + 2], Ib[2]), R[3 * bb + 2]);
-    // inverse by cofactors / determinant
-    const float c00 = sub(mul(Iw[4], Iw[8]), mul(Iw[5], Iw[7]));
-    const float c01 = sub(mul(Iw[5], Iw[6]), mul(Iw[3], Iw[8]));
-    const float c02 = sub(mul(Iw[3], Iw[7]), mul(Iw[4], Iw[6]));
-    const float det = add(add(mul(Iw[0], c00), mul(Iw[1], c01)), mul(Iw[2], c02));
-    const float id = __fdiv_rn(1.f, det);
-    float Ii[9];
-    Ii[0] = mul(c00, id);
-    Ii[1] = mul(sub(mul(Iw[2], Iw[7]), mul(Iw[1], Iw[8])), id);
-    Ii[2] = mul(sub(mul(Iw[1], Iw[5]), mul(Iw[2], Iw[4])), id);
-    Ii[3] = mul(c01, id);
-    Ii[4] = mul(sub(mul(Iw[0], Iw[8]), mul(Iw[2], Iw[6])), id);
-    Ii[5] = mul(sub(mul(Iw[2], Iw[3]), mul(Iw[0], Iw[5])), id);
-    Ii[6] = mul(c02, id);
-    Ii[7] = mul(sub(mul(Iw[1], Iw[6]), mul(Iw[0], Iw[7])), id);
-    Ii[8] = mul(sub(mul(Iw[0], Iw[4]), mul(Iw[1], Iw[3])), id);
-    float bu_w[3] = {0.f, 0.f, 0.f}, bu_v[3] = {0.f, 0.f, 0.f};  // (B_prev u_prev) rows 6..8 and 9..11
-    const float minv = __fdiv_rn(1.f, 12.f);
-    for (int leg = 0; leg < 4; leg++) {
-      const float u0 = -c.log_foot_force[3 * leg], u1 = -c.log_foot_force[3 * leg + 1], u2 = -c.log_foot_force[3 * leg + 2];
-      const float rx = c.log_r_feet[leg], ry = c.log_r_feet[4 + leg], rz = c.log_r_feet[8 + leg];
-      // [r]x u
-      const float t0 = sub(mul(ry, u2), mul(rz, u1));
-      const float t1 = sub(mul(rz, u0), mul(rx, u2));
-      const float t2 = sub(mul(rx, u1), mul(ry, u0));
-      for (int a = 0; a < 3; a++) bu_w[a] = add(bu_w[a], dot3(Ii[3 * a], t0, Ii[3 * a + 1], t1, Ii[3 * a + 2], t2));
-      bu_v[0] = add(bu_v[0], mul(minv, u0));
-      bu_v[1] = add(bu_v[1], mul(minv, u1));
-      bu_v[2] = add(bu_v[2], mul(minv, u2));
+  // ---- the fixed part of the record: what solveDenseMPC hands update_problem_data_floats (:779-828) ----
+  for (int k = lane; k < CMPC_REC_TRAJ; k += 32) {
+    float v = 0.f;  // xi (the estimator stage writes it when it applies), reserved words
+    if (k < 2) v = c.position[k];
+    else if (k == 2) v = c.ground_z;  // p_v (:640)
+    else if (k < CMPC_REC_Q) v = c.v_world[k - CMPC_REC_V];
+    else if (k < CMPC_REC_W) v = c.orientation[k - CMPC_REC_Q];
+    else if (k < CMPC_REC_R) v = c.omega_world[k - CMPC_REC_W];
+    else if (k < CMPC_REC_WEIGHTS) { const int j = k - CMPC_REC_R; v = sub(c.p_foot[3 * (j % 4) + j / 4], c.position[j / 4]); }  // :779
+    else if (k < CMPC_REC_ALPHA) v = A.weights[k - CMPC_REC_WEIGHTS];
+    else if (k == CMPC_REC_ALPHA) v = A.alpha;
+    else if (k == CMPC_REC_XDRAG) v = c.x_comp_integral;  // update_x_drag before the integral moves (:809)
+    else if (k == CMPC_REC_SIMTIME) v = c.sim_time;
+    rec[k] = v;
+  }
+  // ---- trajAll (:565-583) ----
+  const int tw = 12 * h;
+  const bool stand = c.stand != 0;
+  for (int e = lane; e < tw; e += 32) {
+    const int k = e / 12, j = e - 12 * k;
+    float v = s_t0[w][j];
+    if (j >= 2 && j <= 4 && !stand) {
+      const float d = s_walk[w][j - 2];
+      for (int q = 0; q < k; q++) v = add(v, d);
     }
-    const float* xp = c.log_x_prev;
-    // A_prev rows 6..10 are zero; row 11: x_drag * x_prev[9] + x_prev[12], x_prev[12] = -9.81
-    const float a11 = add(mul(c.log_x_drag, xp[9]), -9.81f);
-    float f6[6];
-    for (int a = 0; a < 3; a++) f6[a] = sub(c.omega_world[a], bu_w[a]);
-    f6[3] = sub(c.v_world[0], bu_v[0]);
-    f6[4] = sub(c.v_world[1], bu_v[1]);
-    f6[5] = sub(sub(c.v_world[2], a11), bu_v[2]);
-    fe[0] = -f6[0]; fe[1] = -f6[1]; fe[2] = f6[2]; fe[3] = f6[3]; fe[4] = f6[4]; fe[5] = f6[5];
-    for (int k = 0; k < 6; k++) A.f_ext[(size_t)i * 6 + k] = fe[k];
+    rec[CMPC_REC_TRAJ + e] = v;
   }
-  rec[CMPC_REC_P + 0] = c.position[0];
-  rec[CMPC_REC_P + 1] = c.position[1];
-  rec[CMPC_REC_P + 2] = c.ground_z;
-  for (int k = 0; k < 3; k++) { rec[CMPC_REC_V + k] = c.v_world[k]; rec[CMPC_REC_W + k] = c.omega_world[k]; }
-  for (int k = 0; k < 4; k++) rec[CMPC_REC_Q + k] = c.orientation[k];
-  for (int k = 0; k < 12; k++) rec[CMPC_REC_R + k] = sub(c.p_foot[3 * (k % 4) + k / 4], c.position[k / 4]);  // :779
-  for (int k = 0; k < 12; k++) rec[CMPC_REC_WEIGHTS + k] = A.weights[k];
-  rec[CMPC_REC_ALPHA] = A.alpha;
-  rec[CMPC_REC_XDRAG] = c.x_comp_integral;  // update_x_drag before the integral moves (:809)
-  for (int k = 0; k < 6; k++) rec[CMPC_REC_FDIST + k] = 0.f;  // the estimator stage writes xi when it applies
-  rec[CMPC_REC_SIMTIME] = c.sim_time;
-  if (A.sim_time) A.sim_time[i] = c.sim_time;
-  rec[CMPC_REC_RSV] = 0.f;
-  rec[CMPC_REC_RSV + 1] = 0.f;
-  float xci = c.x_comp_integral;
-  const float vx = c.v_world[0];
-  if (vx > 0.3f || vx < -0.3f) {
-    const float pz_err = sub(c.ground_z, c.body_height);
-    xci = add(xci, __fdiv_rn(mul(mul(c.cmpc_x_drag, pz_err), dt), vx));
+  // ---- getMpcTable (Gait.cpp:158-215), nIterations == horizon: the four legs of a step are one word ----
+  const int gw = (A.rec_stride - 4 * (CMPC_REC_TRAJ + tw)) / 4;  // 4 h bytes + padding
+  for (int k = lane; k < gw; k += 32) {
+    unsigned word = 0u;
+    if (k < h) {
+      for (int j = 0; j < 4; j++) {
+        int on;
+        if (c.gait_kind == CMPC_GAIT_MIXED_FREQUENCY) {
+          const int period = c.gait_offsets[j] > 0 ? c.gait_offsets[j] : 1;
+          const int progress = (k + c.gait_iteration + 1) % period;
+          on = (float)progress < mul((float)period, c.gait_duty);
+        } else {
+          int progress = (k + c.gait_iteration + 1) % h - c.gait_offsets[j];
+          if (progress < 0) progress += h;
+          on = progress < c.gait_durations[j];
+        }
+        word |= (unsigned)on << (8 * j);
+      }
+    }
+    reinterpret_cast<unsigned*>(rec)[CMPC_REC_TRAJ + tw + k] = word;
   }
-  cmpc_command_result& r = A.results[i];
-  r.world_position_desired[0] = wpd0;
-  r.world_position_desired[1] = wpd1;
-  r.x_comp_integral = xci;
-  for (int k = 0; k < 6; k++) r.f_ext[k] = fe[k];
 }
 
 // window[i] <- window[i+1], window[last] <- sample once the window is full; plain append before that
@@ -281,7 +283,7 @@ int cmpc_launch_frontend(const void* cmds, unsigned char* records, void* results
   A.dt = dt;
   A.alpha = alpha;
   for (int i = 0; i < 12; i++) A.weights[i] = weights[i];
-  cmpc_frontend_kernel<<<(count + FRONT_NT - 1) / FRONT_NT, FRONT_NT, 0, (cudaStream_t)stream>>>(A);
+  cmpc_frontend_kernel<<<(count + FRONT_WPC - 1) / FRONT_WPC, 32 * FRONT_WPC, 0, (cudaStream_t)stream>>>(A);
   return (int)cudaGetLastError();
 }
 
