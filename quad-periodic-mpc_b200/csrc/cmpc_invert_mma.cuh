@@ -324,20 +324,17 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
       // 2. M = -D^-1 C
       {
         const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
+        double mt[8][2];  // all eight tiles of M in flight: the two k-steps of a tile are eight DMMAs apart
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-          double mt[4][2];
+        for (int J = 0; J < 8; J++) {
+          mt[J][0] = 0.0;
+          mt[J][1] = 0.0;
+          dmma884(mt[J][0], mt[J][1], a0, pan[fo + 8 * J]);
+        }
 #pragma unroll
-          for (int J = 0; J < 4; J++) {
-            mt[J][0] = 0.0;
-            mt[J][1] = 0.0;
-            dmma884(mt[J][0], mt[J][1], a0, pan[fo + 8 * (4 * half + J)]);
-          }
-#pragma unroll
-          for (int J = 0; J < 4; J++) {
-            dmma884(mt[J][0], mt[J][1], a1, pan[fo + 4 * PS + 8 * (4 * half + J)]);
-            *reinterpret_cast<double2*>(mm + r * PS + 8 * (4 * half + J) + 2 * q) = make_double2(mt[J][0], mt[J][1]);
-          }
+        for (int J = 0; J < 8; J++) {
+          dmma884(mt[J][0], mt[J][1], a1, pan[fo + 4 * PS + 8 * J]);
+          *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(mt[J][0], mt[J][1]);
         }
       }
       __syncwarp();

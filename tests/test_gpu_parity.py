@@ -302,11 +302,15 @@ def _solve_env(inst, env):
 @pytest.mark.parametrize("h,gaits,nseg,B", [(10, ("trot",), None, 512), (10, ("trot", "bound", "pace", "gallop"), 10, 512),
                                             (16, ("trot", "bound", "pace", "gallop"), 10, 256), (10, ("stand",), None, 128)])
 def test_every_kernel_path_agrees(built_lib, h, gaits, nseg, B):
-    """Three-kernel pipeline (DMMA inversion / DFMA condensation shapes, fast and any-capacity dual tiers) vs the
-    fused single-kernel path: the same optimum to rounding, identical activity masks."""
+    """Three-kernel pipeline (DMMA inversion / DFMA condensation shapes, fast and any-capacity dual tiers, resumed
+    and restarted overflow, hardest-first and natural order) vs the fused single-kernel path: the same optimum to
+    rounding, identical activity masks."""
     inst = synth.make_batch(B, horizon=h, seed=601, gaits=gaits, spread=2.0, n_segment=nseg)
     ref = _solve_env(inst, {"CMPC_PATH": "fused"})
-    variants = [{}, {"CMPC_QCAP1": "4"}, {"CMPC_DUAL": "generic"}, {"CMPC_CSHAPE": "2"}, {"CMPC_SERIAL": "1"}]
+    variants = [{}, {"CMPC_QCAP1": "4"}, {"CMPC_DUAL": "generic"}, {"CMPC_CSHAPE": "2"}, {"CMPC_SERIAL": "1"},
+                {"CMPC_LPT": "0"},                          # natural instance order instead of hardest first
+                {"CMPC_RESUME": "0"},                       # overflowed working sets restart instead of resuming
+                {"CMPC_QCAP1": "4", "CMPC_RESUME": "0"}, {"CMPC_QCAP1": "12"}, {"CMPC_NSTREAMS": "2"}]
     for env in variants:
         res = _solve_env(inst, env)
         assert (res["status"] == ref["status"]).all(), env
