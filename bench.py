@@ -210,6 +210,30 @@ def run_b200(args, rank, world, local_rank):
     h2d = int(sum(a.nbytes for a in be._prepared_inputs.values()))   # the eleven input arrays the device reads over PCIe
     d2h = int(sum(a.nbytes for a in res.values()))                    # forces, objective, status, iterations
 
+    # ---- the same call with two batches in flight (submit / wait): step k+1 is submitted before step k is waited for ----
+    pipe = []
+    for k in range(2):
+        sk = {kk: (v[(k + 1) * BATCH:(k + 2) * BATCH] if isinstance(v, np.ndarray) else v) for kk, v in inst.items()}
+        bk = engine.Batch(BATCH, device=local_rank)
+        bk.setup(DT, h, inst["mu"], inst["f_max"])
+        bk.prepare_host(sk, want_active=False)
+        pipe.append(bk)
+    for k in range(2 * max(1, args.warmup)):
+        pipe[k % 2].solve_prepared()
+    barrier()
+    t0 = time.perf_counter()
+    pipe[0].submit_prepared()
+    for k in range(1, args.steps):
+        pipe[k % 2].submit_prepared()
+        rp = pipe[(k - 1) % 2].wait_prepared()
+    rp = pipe[(args.steps - 1) % 2].wait_prepared()
+    barrier()
+    pipe_wall = time.perf_counter() - t0
+    pipe_units, pipe_seconds = allreduce_sum_max(float(args.steps * BATCH), pipe_wall)
+    assert (rp["status"] == 0).all()
+    for bk in pipe:
+        bk.close()
+
     # ---- end to end one level up: the controller-level call (updateMPCIfNeeded / solveDenseMPC on the device) ----
     cmds = synth.make_commands(BATCH, engine.COMMAND_DTYPE, horizon=h, gaits=("trot",), seed=2000 + rank)
     cres = np.zeros(BATCH, dtype=engine.RESULT_DTYPE)
@@ -311,6 +335,10 @@ def run_b200(args, rank, world, local_rank):
                     "call": "cmpc_batch_solve_bound: one synchronous call per step, pinned host arrays in the layout of "
                             "update_problem_data (update_data_t); the device reads the inputs over PCIe and packs the "
                             "records, the kernels write the results into host memory",
+                    "two_in_flight": {"value": pipe_units / pipe_seconds, "unit": "solves/s",
+                                      "ms_per_step": 1e3 * pipe_seconds / args.steps,
+                                      "call": "cmpc_batch_submit_bound / cmpc_batch_wait_bound on two batches: every step "
+                                              "still reads its inputs from and writes its results to pinned host arrays"},
                     "commands": {"value": cmd_units / cmd_seconds, "unit": "solves/s", "steps": csteps,
                                  "h2d_bytes_per_step": int(cmds.nbytes), "d2h_bytes_per_step": int(cres.nbytes),
                                  "ms_per_step": 1e3 * cmd_seconds / csteps,

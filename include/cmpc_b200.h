@@ -137,6 +137,11 @@ int cmpc_batch_solve_host(cmpc_batch* b, int count, const cmpc_inputs* in, const
  * pinning while bound; bind (NULL, NULL) to drop the binding. */
 int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_outputs* out);
 int cmpc_batch_solve_bound(cmpc_batch* b, int count);
+/* The same in two halves: submit enqueues everything and returns, wait blocks until the results are in the bound
+ * output arrays.  A caller with two batches (two cmpc_batch objects, two sets of arrays) submits batch k+1 before it
+ * waits for batch k, so the PCIe traffic and kernel tails of one overlap the kernels of the other. */
+int cmpc_batch_submit_bound(cmpc_batch* b, int count);
+int cmpc_batch_wait_bound(cmpc_batch* b);
 int cmpc_batch_sync(cmpc_batch* b);
 /* Pin a caller-owned host array (cudaHostRegister): cmpc_batch_solve_host / cmpc_batch_download copy results
  * straight into pinned output arrays instead of staging them.  Unregister before freeing the array. */

@@ -62,6 +62,8 @@ def lib():
         L.cmpc_batch_solve_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(Outputs)]
         L.cmpc_batch_bind_host.argtypes = [C.c_void_p, C.POINTER(Inputs), C.POINTER(Outputs)]
         L.cmpc_batch_solve_bound.argtypes = [C.c_void_p, C.c_int]
+        L.cmpc_batch_submit_bound.argtypes = [C.c_void_p, C.c_int]
+        L.cmpc_batch_wait_bound.argtypes = [C.c_void_p]
         L.cmpc_batch_upload_disturbance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.cmpc_batch_download_disturbance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cmpc_batch_set_count.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -246,6 +248,16 @@ class Batch:
     def solve_prepared(self):
         count, s, o, res = self._prepared
         _check(lib().cmpc_batch_solve_bound(self._h, count), "cmpc_batch_solve_bound")
+        self.count = count
+        return res
+
+    def submit_prepared(self):
+        """Enqueue the bound solve and return; wait_prepared() delivers the results."""
+        _check(lib().cmpc_batch_submit_bound(self._h, self._prepared[0]), "cmpc_batch_submit_bound")
+
+    def wait_prepared(self):
+        count, s, o, res = self._prepared
+        _check(lib().cmpc_batch_wait_bound(self._h), "cmpc_batch_wait_bound")
         self.count = count
         return res
 

@@ -254,6 +254,7 @@ struct cmpc_batch {
   bool resume = true;                 // CMPC_RESUME=0: overflowed instances restart from scratch in the full-capacity launch
   std::vector<PipePlan> plans;        // launch plans by (reduced size bound, horizon, adaptive)
   HostBinding bound;                  // cmpc_batch_bind_host
+  int pend_count = 0, pend_per = 0, pend_used = -1;  // cmpc_batch_submit_bound: chunks in flight (-1: none)
   // adaptive stage
   double* d_twiddle = nullptr;
   float* d_gk = nullptr;
@@ -1061,7 +1062,7 @@ static int resolve_binding(cmpc_batch* b, const cmpc_inputs* in, const cmpc_outp
   return CMPC_OK;
 }
 
-static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
+static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool wait = true) {
   static const bool trace = std::getenv("CMPC_TRACE") != nullptr;
   static double tr_enq = 0, tr_wait = 0, tr_scan = 0, tr_pack = 0, tr_pipe = 0;
   static cudaEvent_t tr_ev[2 * kMaxChunks] = {};
@@ -1157,6 +1158,12 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb) {
     used = c + 1;
   }
   b->max_contact = maxc_all;
+  if (!wait) {  // cmpc_batch_submit_bound: the caller collects the results with cmpc_batch_wait_bound
+    b->pend_count = count;
+    b->pend_per = per;
+    b->pend_used = used;
+    return CMPC_OK;
+  }
   const auto tr1 = std::chrono::steady_clock::now();
   for (int c = 0; c < used; c++) {
     const int first = c * per, n = std::min(per, count - first);
@@ -1210,6 +1217,37 @@ int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_output
   if (!out) return fail_arg("cmpc_batch_bind_host: null outputs");
   CK(cudaSetDevice(b->device));
   return resolve_binding(b, in, out, b->bound);
+}
+
+int cmpc_batch_submit_bound(cmpc_batch* b, int count) {
+  if (!b) return fail_arg("cmpc_batch_submit_bound: null batch");
+  if (!b->bound.valid) { g_err = "cmpc_batch_submit_bound: call cmpc_batch_bind_host first"; return CMPC_E_STATE; }
+  if (!b->is_setup) { g_err = "cmpc_batch_submit_bound: call cmpc_batch_setup first"; return CMPC_E_STATE; }
+  if (count < 0 || count > b->capacity) return fail_arg("cmpc_batch_submit_bound: count exceeds capacity");
+  if (b->pend_used >= 0) { g_err = "cmpc_batch_submit_bound: the previous submission has not been waited for"; return CMPC_E_STATE; }
+  b->pend_used = 0;
+  int rc = solve_host_core(b, count, b->bound, false);
+  if (rc) b->pend_used = -1;
+  return rc;
+}
+
+int cmpc_batch_wait_bound(cmpc_batch* b) {
+  if (!b) return fail_arg("cmpc_batch_wait_bound: null batch");
+  if (b->pend_used < 0) { g_err = "cmpc_batch_wait_bound: nothing was submitted"; return CMPC_E_STATE; }
+  CK(cudaSetDevice(b->device));
+  const int used = b->pend_used, per = b->pend_per, count = b->pend_count;
+  b->pend_used = -1;
+  for (int c = 0; c < used; c++) {
+    const int first = c * per, n = std::min(per, count - first);
+    CK(cudaEventSynchronize(b->chunk_done[c]));
+    unpack_results(b, &b->bound.out, first, n, b->bound.direct);
+  }
+  if (used > 0) {
+    CK(cudaStreamWaitEvent(b->stream[0], b->chunk_done[used - 1], 0));
+    CK(cudaEventRecord(b->ev1, b->stream[0]));
+    b->timed = true;
+  }
+  return CMPC_OK;
 }
 
 int cmpc_batch_solve_bound(cmpc_batch* b, int count) {

@@ -374,3 +374,30 @@ def test_adaptive_batch_at_scale(built_lib, golden):
     explicit = b.solve_host(inst, f_dist=fest)
     assert (explicit["forces"] == res["forces"]).all()
     b.close()
+
+
+def test_submit_wait_overlaps_two_batches(built_lib):
+    """cmpc_batch_submit_bound / cmpc_batch_wait_bound: two batches in flight deliver what the synchronous call does;
+    call-order violations are errors, not hangs."""
+    h, B = 10, 1024
+    insts = [synth.make_batch(B, horizon=h, seed=950 + k, spread=1.5) for k in range(2)]
+    want = [solve(i) for i in insts]
+    bs = []
+    for inst in insts:
+        b = engine.Batch(B)
+        b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+        b.prepare_host(inst)
+        bs.append(b)
+    with pytest.raises(RuntimeError):
+        bs[0].wait_prepared()                       # nothing submitted
+    for rep in range(3):
+        bs[0].submit_prepared()
+        bs[1].submit_prepared()
+        with pytest.raises(RuntimeError):
+            bs[0].submit_prepared()                 # still in flight
+        for k in (0, 1):
+            res = bs[k].wait_prepared()
+            for key in ("forces", "objective", "status", "iterations", "active"):
+                assert (res[key] == want[k][key]).all(), (rep, k, key)
+    for b in bs:
+        b.close()
