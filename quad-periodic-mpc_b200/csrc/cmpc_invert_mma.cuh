@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
 // main warps (one instance each, all 36 tiles in registers; setmaxnreg raises them to 168 registers) and four
 // helper warps (setmaxnreg drops them to 40).  Main warp w and helper warp w + 4 sit on the same SM sub-partition
 // and talk through two named barriers and 1 KB of shared memory:
-//   main:    ... update tile (s+1, s+1) FIRST (two DMMAs), park it in shared memory, bar.arrive(TILE);
-//            the other 72 update DMMAs of step s; publish panel s+1; bar.sync(DV); M = -D^-1 C; ...
+//   main:    ... bar.sync(DV); column block s+1 of M and the update of tile (s+1, s+1) FIRST (four DMMAs), park the
+//            tile in shared memory, bar.arrive(TILE); M = -D^-1 C; the 72 update DMMAs of step s; publish panel s+1 ...
 //   helper:  bar.sync(TILE); invert the parked tile (Gauss-Jordan over shuffles); write -D^-1; bar.arrive(DV)
 // so the pivot chain of step s+1 runs while the main warp issues the update DMMAs of step s.  Two CTAs per SM
 // (the register file: 2 x 128 x (216 + 40)), eight instances per SM, two main warps per FP64 tensor pipe.
@@ -321,9 +321,33 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
       WS_TICK(CMPC_PH_DVWAIT)
       // a last block of at most four real rows: its second k-step (padding rows, the border) contributes zeros
       const bool half_step = (8 * s + 4 >= n);
-      // 2. M = -D^-1 C
+      const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
+      // 2a. the next diagonal tile FIRST: its column block of M (two DMMAs), its update (two DMMAs), then it is handed
+      //     to the helper, whose pivot chain runs under the rest of M and the 72 update DMMAs of this step
+      if (s + 1 < nblk) {
+        const int o = 8 * (s + 1);
+        double m0 = 0.0, m1 = 0.0;
+        dmma884(m0, m1, a0, pan[fo + o]);
+        dmma884(m0, m1, a1, pan[fo + 4 * PS + o]);
+        *reinterpret_cast<double2*>(mm + r * PS + o + 2 * q) = make_double2(m0, m1);
+        __syncwarp();
+        double e0, e1;
+        switch (s) {
+          case 0: e0 = t[tix(1, 1)][0]; e1 = t[tix(1, 1)][1]; break;
+          case 1: e0 = t[tix(2, 2)][0]; e1 = t[tix(2, 2)][1]; break;
+          case 2: e0 = t[tix(3, 3)][0]; e1 = t[tix(3, 3)][1]; break;
+          case 3: e0 = t[tix(4, 4)][0]; e1 = t[tix(4, 4)][1]; break;
+          case 4: e0 = t[tix(5, 5)][0]; e1 = t[tix(5, 5)][1]; break;
+          case 5: e0 = t[tix(6, 6)][0]; e1 = t[tix(6, 6)][1]; break;
+          default: e0 = t[tix(7, 7)][0]; e1 = t[tix(7, 7)][1]; break;
+        }
+        dmma884(e0, e1, pan[fo + o], mm[fo + o]);
+        dmma884(e0, e1, pan[fo + 4 * PS + o], mm[fo + 4 * PS + o]);
+        park_tile(e0, e1, s + 1);
+        named_bar_arrive(BAR_TILE);
+      }
+      // 2b. M = -D^-1 C (the column block of 2a is formed again, bit for bit the same)
       {
-        const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
         double mt[8][2];  // all eight tiles of M in flight: the two k-steps of a tile are eight DMMAs apart
 #pragma unroll
         for (int J = 0; J < 8; J++) {
@@ -339,24 +363,6 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
       }
       __syncwarp();
       WS_TICK(CMPC_PH_ADAPT)
-      // 3a. the next diagonal tile first: hand it to the helper, whose pivot chain then runs under the update DMMAs
-      if (s + 1 < nblk) {
-        double e0, e1;
-        switch (s) {
-          case 0: e0 = t[tix(1, 1)][0]; e1 = t[tix(1, 1)][1]; break;
-          case 1: e0 = t[tix(2, 2)][0]; e1 = t[tix(2, 2)][1]; break;
-          case 2: e0 = t[tix(3, 3)][0]; e1 = t[tix(3, 3)][1]; break;
-          case 3: e0 = t[tix(4, 4)][0]; e1 = t[tix(4, 4)][1]; break;
-          case 4: e0 = t[tix(5, 5)][0]; e1 = t[tix(5, 5)][1]; break;
-          case 5: e0 = t[tix(6, 6)][0]; e1 = t[tix(6, 6)][1]; break;
-          default: e0 = t[tix(7, 7)][0]; e1 = t[tix(7, 7)][1]; break;
-        }
-        const int o = 8 * (s + 1);
-        dmma884(e0, e1, pan[fo + o], mm[fo + o]);
-        if (!half_step) dmma884(e0, e1, pan[fo + 4 * PS + o], mm[fo + 4 * PS + o]);
-        park_tile(e0, e1, s + 1);
-        named_bar_arrive(BAR_TILE);
-      }
       // 3b. every tile (I, J) += C_I' M_J: both operand sets of a k-step are loaded up front (the main warps own 216
       //     registers), then 36 independent DMMAs issue back to back
       {
