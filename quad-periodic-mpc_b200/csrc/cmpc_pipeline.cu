@@ -1,13 +1,17 @@
-// Two-kernel pipeline of the batched convex-MPC engine for reduced problems of up to 128 variables
-// (every A1 gait at the reference's horizons except long all-feet-down stances):
+// Kernel pipeline of the batched convex-MPC engine for reduced problems of up to 128 variables (every A1 gait at the
+// reference's horizons except long all-feet-down stances).  Launchers and occupancy queries of:
 //
-//   cmpc_condense_kernel  one CTA per instance: condensation, H in register tiles, K = H^-1 by blocked
-//                         symmetric sweeps (FP64-pipe bound), x0 = -K g            cmpc_condense.cuh
-//   cmpc_dual_kernel      one warp per instance: Goldfarb-Idnani dual active set on K (latency bound,
-//                         many warps per SM), outputs                                cmpc_dual.cuh
+//   n <= 63   cmpc_assemble_mma_kernel   one CTA per instance: condensation, [H g; g' .] as DMMA tiles   cmpc_condense_mma.cuh
+//             cmpc_invert_ws_kernel      one main warp (+ helper warp) per instance: K = H^-1, x0 = -K g
+//                                        on the FP64 tensor cores                                         cmpc_invert_mma.cuh
+//             cmpc_lpt_order_kernel      hardest-first worklist for the active-set kernel                 (this file)
+//   n <= 128  cmpc_condense_kernel       one CTA per instance: condensation + blocked DFMA sweep          cmpc_condense.cuh
+//   all       cmpc_dual_fast_kernel      one warp per instance: Goldfarb-Idnani dual active set on K,
+//                                        working sets of up to 32 rows, outputs                           cmpc_dual_fast.cuh
+//             cmpc_dual_kernel           any working-set size; resumes what the fast tier handed over     cmpc_dual.cuh
 //
-// K travels between the two through a per-instance workspace slot that the host sizes to stay L2
-// resident.  Larger problems take the fused single-kernel path in cmpc_kernels.cu.
+// K travels between the kernels through a per-instance workspace slot (one workspace per stream).  Larger problems
+// take the fused single-kernel path in cmpc_kernels.cu.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
