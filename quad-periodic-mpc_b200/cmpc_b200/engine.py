@@ -288,7 +288,7 @@ class Batch:
         _check(lib().cmpc_batch_profile_range(self._h, first, count, arr), "cmpc_batch_profile_range")
         return dict(zip(self.KERNELS, [float(x) for x in arr]))
 
-    PHASES = ("wait", "adapt", "prep", "hess", "load", "sweep", "store", "qp", "out", "publish", "dvwait")
+    PHASES = ("wait", "adapt", "prep", "hess", "load", "sweep", "store", "qp", "out", "publish", "dvwait", "x0_tilewait", "x1_tileload", "x2_kstore", "x3_looptop")
 
     def enable_phase_clocks(self, on=True):
         _check(lib().cmpc_batch_enable_phase_clocks(self._h, int(on)), "cmpc_batch_enable_phase_clocks")

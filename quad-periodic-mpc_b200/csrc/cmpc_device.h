@@ -121,7 +121,11 @@ struct CmpcParams {
 #define CMPC_PH_OUT 8     /* objective, outputs */
 #define CMPC_PH_PUBLISH 9 /* warp-specialised inversion: panel publish */
 #define CMPC_PH_DVWAIT 10 /* warp-specialised inversion: main warp waiting for the helper's pivot-block inverse */
-#define CMPC_PH_COUNT 11
+#define CMPC_PH_X0 11 /* diagnostics of the inversion kernel's load / store bucket */
+#define CMPC_PH_X1 12
+#define CMPC_PH_X2 13
+#define CMPC_PH_X3 14
+#define CMPC_PH_COUNT 15
 
 // kernel shapes (cmpc_kernels.cu): register-tile tiers by reduced problem size, shared-memory tier beyond
 #define CMPC_SHAPE_64 0    /* n <= 64, 64 threads, 8x8 register tiles */

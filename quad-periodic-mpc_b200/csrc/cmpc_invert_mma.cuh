@@ -54,6 +54,22 @@ __device__ __forceinline__ void publish_panel(const double (&t)[36][2], double* 
 
 // Hardest-first scheduling of the active-set kernel: count the constraint rows that x0 (staged in `xs`, shared
 // memory) violates — five rows per contact foot-step, as cmpc_dual_fast.cuh lays them out — and file the instance.
+// deferred form: the histogram atomic is issued here, its result (lane 0) is written by lpt_store one instance later,
+// so the warp does not wait for the round trip
+__device__ __forceinline__ int lpt_count(const CmpcParams& P, int nc, const int* hdr, const double* xs, int lane) {
+  int viol = 0;
+  if (nc > 0) {
+    const unsigned char* gvb = reinterpret_cast<const unsigned char*>(hdr + 2) + CMPC_MAX_FS;
+    for (int f = lane; f < nc; f += 32) {
+      const double fx = xs[3 * f] * P.mu_inv, fy = xs[3 * f + 1] * P.mu_inv, fz = xs[3 * f + 2];
+      const double tol = -P.tol_violation;
+      viol += (fx + fz < tol) + (fz - fx < tol) + (fy + fz < tol) + (fz - fy < tol) + ((double)gvb[f] * P.f_max - fz < tol);
+    }
+    viol = __reduce_add_sync(0xffffffffu, viol);
+  }
+  return min(viol, 63);
+}
+
 __device__ __forceinline__ void lpt_file(const CmpcParams& P, int inst, int nc, const int* hdr, const double* xs, int lane) {
   if (!P.lpt_hist) return;
   int viol = 0;
@@ -218,7 +234,9 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr int WS_MAIN = 4;                                   // main warps (= instances in flight) per CTA
-constexpr int WS_PAIR_SMEM = 8 * (2 * 8 * MMA_PS + 64 + 64) + 16;  // panel, M, -D^-1, parked tile, control word
+constexpr int WS_TILE_BYTES = 8 * CMPC_KTILE_DOUBLES;                                 // the 36 tiles of one instance
+constexpr int WS_PAIR_CTRL = 8 * (2 * 8 * MMA_PS + 64 + 64);                          // panel, M, -D^-1, parked tile
+constexpr int WS_PAIR_SMEM = WS_PAIR_CTRL + 16 + WS_TILE_BYTES;  // + control word, mbarrier, prefetched tiles of the NEXT instance
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 }  // namespace
@@ -235,6 +253,8 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
   double* dv = mm + 8 * PS;
   double* dtile = dv + 64;
   volatile int* ctrl = reinterpret_cast<volatile int*>(dtile + 64);
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(dtile + 65);      // mbarrier of the tile prefetch
+  double* tbuf = dtile + 66;                                     // 36 tiles, filled by one cp.async.bulk
   const int BAR_TILE = 1 + 2 * pair, BAR_DV = 2 + 2 * pair;
 
   if (warp >= WS_MAIN) {
@@ -280,24 +300,88 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
     }
     *reinterpret_cast<double2*>(dtile + r * 8 + 2 * q) = make_double2(d0, d1);
   };
-  while (true) {
-    int inst = 0;
-    if (lane == 0) inst = atomicAdd(P.sched, 1);
-    inst = __shfl_sync(0xffffffffu, inst, 0);
-    if (inst >= count) break;
+  // Instance fetch and tile load run one instance ahead: while an instance is swept, the work counter, the header and
+  // the 18 KB of tiles of the NEXT one are already on their way (one cp.async.bulk into shared memory).
+  auto fetch = [&]() -> int {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(P.sched, 1);
+    return __shfl_sync(0xffffffffu, i, 0);
+  };
+  auto prefetch = [&](int i, int& nc_o, int& st_o, double& sc_o, int& gv_o) {
+    const double* sl = P.qws + (size_t)i * P.qws_stride;
+    const int* hd = reinterpret_cast<const int*>(sl + P.qws_goff + 2 * P.nmax + 2);
+    nc_o = hd[0];
+    st_o = hd[1];
+    sc_o = sl[P.qws_goff + 2 * P.nmax];                                                      // the scale of H
+    gv_o = reinterpret_cast<const unsigned char*>(hd + 2)[CMPC_MAX_FS + lane];               // fz bound of foot-step `lane`
+    if (lane == 0) {
+      fence_proxy_async();  // the buffer was read through the generic proxy a moment ago
+      mbar_expect_tx(tbar, (uint32_t)WS_TILE_BYTES);
+      bulk_g2s(tbuf, sl, (uint32_t)WS_TILE_BYTES, tbar);
+    }
+  };
+  if (lane == 0) {
+    mbar_init(tbar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  uint32_t tphase = 0u;
+  int inst = fetch(), nc_cur = 0, st_cur = 0, gv_cur = 0;
+  double sc_cur = 0.0;
+  if (inst < count) prefetch(inst, nc_cur, st_cur, sc_cur, gv_cur);
+  // the work counter is drawn TWO instances ahead (lane 0 holds the ticket, nobody waits for the atomic), and the
+  // hardest-first filing of an instance is completed one instance later (same reason)
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(P.sched, 1);
+  int file_inst = -1, file_key = 0, file_pos = 0;
+  auto lpt_flush = [&]() {
+    if (lane == 0 && file_inst >= 0) P.lpt_key[file_inst] = (file_key << 24) | file_pos;
+    file_inst = -1;
+  };
+  auto lpt_defer = [&](int i, int key) {
+    if (!P.lpt_hist) return;
+    lpt_flush();
+    if (lane == 0) {
+      file_pos = atomicAdd(P.lpt_hist + key, 1);
+      file_key = key;
+      file_inst = i;
+    }
+  };
+  while (inst < count) {
     double* slot = P.qws + (size_t)inst * P.qws_stride;
     const int* hdr = reinterpret_cast<const int*>(slot + P.qws_goff + 2 * P.nmax + 2);
-    const int nc = hdr[0];
-    if (hdr[1] != CMPC_ST_SOLVED) { lpt_file(P, inst, 0, hdr, pan, lane); continue; }
+    const int nc = nc_cur, gv_mine = gv_cur;
+    const double scale = sc_cur;
+    const bool solved = st_cur == CMPC_ST_SOLVED;
+    WS_TICK(CMPC_PH_X3)
+    mbar_wait(tbar, tphase);
+    tphase ^= 1u;
+    WS_TICK(CMPC_PH_X0)
+    double t[36][2];
+    if (solved) {
+#pragma unroll
+      for (int k = 0; k < 36; k++) {
+        const double2 v = *reinterpret_cast<const double2*>(tbuf + k * 64 + lane * 2);
+        t[k][0] = v.x;
+        t[k][1] = v.y;
+      }
+    }
+    __syncwarp();
+    WS_TICK(CMPC_PH_X1)
+    const int inst_next = __shfl_sync(0xffffffffu, ticket, 0);
+    if (lane == 0) ticket = atomicAdd(P.sched, 1);
+    int nc_next = 0, st_next = 0, gv_next = 0;
+    double sc_next = 0.0;
+    if (inst_next < count) prefetch(inst_next, nc_next, st_next, sc_next, gv_next);
+    const int inst_this = inst;
+    inst = inst_next;
+    nc_cur = nc_next;
+    st_cur = st_next;
+    sc_cur = sc_next;
+    gv_cur = gv_next;
+    if (!solved) { lpt_defer(inst_this, 0); continue; }
     const int n = 3 * nc, nblk = (n + 7) >> 3;
     flops_acc += (unsigned)(n * n * (n + 2));
-    double t[36][2];
-#pragma unroll
-    for (int k = 0; k < 36; k++) {
-      const double2 v = *reinterpret_cast<const double2*>(slot + k * 64 + lane * 2);
-      t[k][0] = v.x;
-      t[k][1] = v.y;
-    }
     if (lane == 0) ctrl[0] = nblk;
     park_tile(t[0][0], t[0][1], 0);
     named_bar_arrive(BAR_TILE);
@@ -385,7 +469,6 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
       WS_TICK(CMPC_PH_SWEEP)
     }
     // K_ij = -(A_ij - 2 d_ij) scale in place; x0 = -scale A[63][:]
-    const double scale = slot[P.qws_goff + 2 * P.nmax];
 #pragma unroll
     for (int I = 0; I < 8; I++)
 #pragma unroll
@@ -405,11 +488,26 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
         }
       }
     __syncwarp();
-    lpt_file(P, inst, nc, hdr, pan, lane);
+    __syncwarp();
+    WS_TICK(CMPC_PH_X2)
+    {
+      int key = 0;
+      if (P.lpt_hist) {  // rows violated at x0 (five per contact foot-step, one foot-step per lane: nc <= 21 here)
+        int viol = 0;
+        if (lane < nc) {
+          const double fx = pan[3 * lane] * P.mu_inv, fy = pan[3 * lane + 1] * P.mu_inv, fz = pan[3 * lane + 2];
+          const double tol = -P.tol_violation;
+          viol = (fx + fz < tol) + (fz - fx < tol) + (fy + fz < tol) + (fz - fy < tol) + ((double)gv_mine * P.f_max - fz < tol);
+        }
+        key = min(__reduce_add_sync(0xffffffffu, viol), 63);
+      }
+      lpt_defer(inst_this, key);
+    }
     __syncwarp();
     WS_TICK(CMPC_PH_LOAD)
   }
 #undef WS_TICK
+  lpt_flush();
   // release the helper
   if (lane == 0) ctrl[0] = -1;
   __syncwarp();
