@@ -676,7 +676,6 @@ int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
   P.rec_stride = b->rec_stride;
   P.nmax = std::max(3, 3 * max_contact);
   P.max_iter = 20 * P.nmax + 100;
-  { static const int stagger = [] { const char* e = std::getenv("CMPC_STAGGER"); return e ? std::atoi(e) : 0; }(); P.pad0 = stagger; }
   P.adapt_mode = b->adapt_mode;
   P.dt = (double)(float)b->dt;
   P.mu_inv = (double)(1.f / (float)b->mu);

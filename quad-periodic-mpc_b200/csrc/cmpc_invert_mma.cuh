@@ -278,9 +278,6 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
 
   // ---------------- main: tiles in registers, DMMA ----------------
   asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
-  // The two CTAs of an SM start together and every instance takes the same time, so their main warps would run their
-  // DMMA phases in lockstep (pipe saturated, then idle).  The second wave of CTAs starts half a block step late.
-  if (P.pad0 > 0 && blockIdx.x >= (gridDim.x + 1) / 2) __nanosleep((unsigned)P.pad0);
   const int count = P.count;
   unsigned flops_acc = 0u;
   const int fo = q * PS + r;  // fragment offset: element (k = q, row/col = r)

@@ -127,20 +127,8 @@ size_t cmpc_condense_smem_bytes(int horizon, int nmax, int cshape, bool adapt) {
   return (size_t)make_ccarve(horizon, nmax, cmpc_rec_stride(horizon), cnpad_of(cshape), adapt).total;
 }
 
-namespace {
-int asm_minb() {  // resident CTAs per SM the assembly kernel is compiled for (register cap 80 / 72)
-  static int v = [] {
-    const char* e = std::getenv("CMPC_ASM_MINB");
-    return (e && std::atoi(e) == 7) ? 7 : 6;
-  }();
-  return v;
-}
-}  // namespace
 int cmpc_condense_max_ctas_per_sm(int cshape, size_t smem, bool adapt) {
-  if (cshape == CMPC_CSHAPE_MMA64) {
-    if (asm_minb() == 7) return adapt ? occ_mma_t<true, 7>(smem) : occ_mma_t<false, 7>(smem);
-    return adapt ? occ_mma_t<true, 6>(smem) : occ_mma_t<false, 6>(smem);
-  }
+  if (cshape == CMPC_CSHAPE_MMA64) return adapt ? occ_mma_t<true, 6>(smem) : occ_mma_t<false, 6>(smem);
   CMPC_CDISPATCH(occ_condense_t, smem)
 }
 
@@ -150,10 +138,8 @@ int cmpc_launch_condense(const CmpcParams& P, int cshape, int grid, void* stream
   const bool adapt = P.adapt_mode >= 0;
   const size_t smem = cmpc_condense_smem_bytes(P.horizon, P.nmax, cshape, adapt);
   cudaStream_t st = (cudaStream_t)stream;
-  if (cshape == CMPC_CSHAPE_MMA64) {
-    if (asm_minb() == 7) return adapt ? launch_mma_t<true, 7>(P, grid, smem, st) : launch_mma_t<false, 7>(P, grid, smem, st);
+  if (cshape == CMPC_CSHAPE_MMA64)
     return adapt ? launch_mma_t<true, 6>(P, grid, smem, st) : launch_mma_t<false, 6>(P, grid, smem, st);
-  }
   CMPC_CDISPATCH(launch_condense_t, P, grid, smem, st)
 }
 
