@@ -28,22 +28,49 @@ __device__ __forceinline__ void estimate_disturbance_impl(const CmpcParams& P, i
   double* tim = work + 2 * N;
   const float* wd = P.win_d + (size_t)inst * N;
   const float* wt = P.win_t + (size_t)inst * N;
-  for (int i = tid; i < N; i += NT) tre[i] = (double)wd[i];
+  // band-pass: difference of the two blurs, edge samples repeated (SolverMPC.cpp:425-434).  The window is staged with
+  // its edges already repeated (no index clamping in the tap loops) next to the taps as doubles; a thread forms four
+  // consecutive outputs, so a tap and a sample are fetched once per four FMAs.  Every output is still the same
+  // left-to-right FMA chain over its taps.
+  constexpr int R1 = CMPC_GK_R1, R2 = CMPC_GK_R2;
+  double* xe = work + N;                  // [N + 2 R2], overlays tre / tim (dead until the DFT)
+  double* tap1 = work + 2 * N + 2 * R2;   // [2 R1 + 1]
+  double* tap2 = tap1 + 2 * R1 + 1;       // [2 R2 + 1]
+  static_assert(3 * CMPC_ADAPT_WINDOW >= 2 * CMPC_ADAPT_WINDOW + 2 * CMPC_GK_R2 + CMPC_GK_TOTAL, "estimator scratch");
+  for (int i = tid; i < N + 2 * R2; i += NT) xe[i] = (double)wd[min(max(i - R2, 0), N - 1)];
+  for (int i = tid; i < CMPC_GK_TOTAL; i += NT) tap1[i] = (double)__ldg(P.gk + i);
   sync();
-  // band-pass: difference of the two blurs, edge samples repeated (SolverMPC.cpp:425-434)
-  const float* g1 = P.gk;
-  const float* g2 = P.gk + 2 * CMPC_GK_R1 + 1;
-  for (int i = tid; i < N; i += NT) {
-    double a1 = 0.0, a2 = 0.0;
-    for (int j = -CMPC_GK_R1; j <= CMPC_GK_R1; j++) {
-      int idx = min(max(i + j, 0), N - 1);
-      a1 += tre[idx] * (double)__ldg(g1 + j + CMPC_GK_R1);
+  for (int o = tid; o < N / 4; o += NT) {
+    const int i0 = 4 * o;
+    double a2[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+      const double* x = xe + i0;  // output i0 + c, tap j reads sample index (i0 + c) + j - R2, i.e. xe[i0 + c + j]
+      double x0 = x[0], x1 = x[1], x2 = x[2];
+#pragma unroll 4
+      for (int j = 0; j <= 2 * R2; j++) {
+        const double x3 = x[j + 3], g = tap2[j];
+        a2[0] = fma(x0, g, a2[0]);
+        a2[1] = fma(x1, g, a2[1]);
+        a2[2] = fma(x2, g, a2[2]);
+        a2[3] = fma(x3, g, a2[3]);
+        x0 = x1; x1 = x2; x2 = x3;
+      }
     }
-    for (int j = -CMPC_GK_R2; j <= CMPC_GK_R2; j++) {
-      int idx = min(max(i + j, 0), N - 1);
-      a2 += tre[idx] * (double)__ldg(g2 + j + CMPC_GK_R2);
+    {
+      const double* x = xe + i0 + (R2 - R1);
+      double x0 = x[0], x1 = x[1], x2 = x[2];
+#pragma unroll 4
+      for (int j = 0; j <= 2 * R1; j++) {
+        const double x3 = x[j + 3], g = tap1[j];
+        a1[0] = fma(x0, g, a1[0]);
+        a1[1] = fma(x1, g, a1[1]);
+        a1[2] = fma(x2, g, a1[2]);
+        a1[3] = fma(x3, g, a1[3]);
+        x0 = x1; x1 = x2; x2 = x3;
+      }
     }
-    y[i] = a1 - a2;
+#pragma unroll
+    for (int c = 0; c < 4; c++) y[i0 + c] = a1[c] - a2[c];
   }
   sync();
   // mean and (population) standard deviation
