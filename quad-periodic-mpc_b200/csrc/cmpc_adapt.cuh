@@ -39,6 +39,8 @@ __device__ __forceinline__ void estimate_disturbance_impl(const CmpcParams& P, i
   static_assert(3 * CMPC_ADAPT_WINDOW >= 2 * CMPC_ADAPT_WINDOW + 2 * CMPC_GK_R2 + CMPC_GK_TOTAL, "estimator scratch");
   for (int i = tid; i < N + 2 * R2; i += NT) xe[i] = (double)wd[min(max(i - R2, 0), N - 1)];
   for (int i = tid; i < CMPC_GK_TOTAL; i += NT) tap1[i] = (double)__ldg(P.gk + i);
+  double* w20 = work + 3 * N;             // W20^m = W400^(20 m), m = 0..19: (cos, -sin) pairs for both DFT passes
+  for (int i = tid; i < 40; i += NT) w20[i] = __ldg(P.twiddle + 2 * (20 * (i >> 1)) + (i & 1));
   sync();
   for (int o = tid; o < N / 4; o += NT) {
     const int i0 = 4 * o;
@@ -88,8 +90,8 @@ __device__ __forceinline__ void estimate_disturbance_impl(const CmpcParams& P, i
     int m = 0;  // (n1 * k1) mod 20
     for (int n1 = 0; n1 < 20; n1++) {
       const double yv = y[20 * n1 + n2];
-      re = fma(yv, __ldg(P.twiddle + 2 * (20 * m)), re);
-      im = fma(yv, __ldg(P.twiddle + 2 * (20 * m) + 1), im);
+      re = fma(yv, w20[2 * m], re);
+      im = fma(yv, w20[2 * m + 1], im);
       m += k1;
       if (m >= 20) m -= 20;
     }
@@ -107,7 +109,7 @@ __device__ __forceinline__ void estimate_disturbance_impl(const CmpcParams& P, i
     double re = 0.0, im = 0.0;
     int m = 0;  // (n2 * k2) mod 20
     for (int n2 = 0; n2 < 20; n2++) {
-      const double c = __ldg(P.twiddle + 2 * (20 * m)), s = __ldg(P.twiddle + 2 * (20 * m) + 1);
+      const double c = w20[2 * m], s = w20[2 * m + 1];
       const double a = tre[20 * n2 + k1], b = tim[20 * n2 + k1];
       re += a * c - b * s;
       im += a * s + b * c;

@@ -52,7 +52,7 @@ __host__ __device__ inline CCarve make_ccarve(int h, int nmax, int rec_stride, i
   c.g = o; o += align16(8 * npad);
   {
     int hb = 8 * nmax * nmax;  // H staging; the estimator stage borrows it for 3 x 400 doubles
-    if (adapt && hb < 8 * 3 * CMPC_ADAPT_WINDOW) hb = 8 * 3 * CMPC_ADAPT_WINDOW;
+    if (adapt && hb < 8 * CMPC_ADAPT_SCRATCH) hb = 8 * CMPC_ADAPT_SCRATCH;
     c.hs = o; o += align16(hb);
   }
   c.pan = o; o += align16(8 * 8 * (npad + 4));

@@ -60,7 +60,7 @@ __host__ __device__ inline MCarve make_mcarve(int h, int rec_stride, bool adapt)
   c.pan = o; o += 8 * 8 * MMA_PS;
   c.mm = o; o += 8 * 8 * MMA_PS;
   c.dv = o; o += 8 * 64;
-  if (adapt && o - c.pan < 8 * 3 * CMPC_ADAPT_WINDOW) o = c.pan + 8 * 3 * CMPC_ADAPT_WINDOW;
+  if (adapt && o - c.pan < 8 * CMPC_ADAPT_SCRATCH) o = c.pan + 8 * CMPC_ADAPT_SCRATCH;
   c.red = o; o += 512;
   c.total = o;
   return c;

@@ -70,7 +70,7 @@ __host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_s
   c.cbuf = o; o += align16(8 * (2 * (npad + 2) + 2 * npad));  // pivot rows (x2) + diagonal copies (x2)
   {
     int kb = gmem ? 0 : 8 * nmax * nmax;  // the estimator stage borrows this region for 3 x 400 doubles of work space
-    if (adapt && kb < 8 * 3 * CMPC_ADAPT_WINDOW) kb = 8 * 3 * CMPC_ADAPT_WINDOW;
+    if (adapt && kb < 8 * CMPC_ADAPT_SCRATCH) kb = 8 * CMPC_ADAPT_SCRATCH;
     c.K = o; o += align16(kb);
   }
   c.g = o; o += align16(8 * nmax);
