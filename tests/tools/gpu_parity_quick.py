@@ -1,6 +1,6 @@
 """Quick GPU parity run: CUDA path vs the oracle (real qpOASES) on seeded batches."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "quad-periodic-mpc_b200")); sys.path.insert(0, ROOT)
 import numpy as np
 from cmpc_b200 import synth, engine

@@ -1,7 +1,7 @@
 """Large-sample parity of the CUDA path against the reference's qpOASES (oracle/_ref, fp64 condensation, all host
 threads): forces, and the count of instances on which qpOASES itself gave up (nWSR cap of 100)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "quad-periodic-mpc_b200")); sys.path.insert(0, ROOT)
 import numpy as np
 from cmpc_b200 import synth, engine
