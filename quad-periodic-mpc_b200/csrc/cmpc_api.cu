@@ -249,8 +249,9 @@ struct cmpc_batch {
   int* d_sched[kMaxStreams] = {};
   int sched_ints[kMaxStreams] = {};
   int* d_resume[kMaxStreams] = {};    // per stream: working sets of the instances in d_overflow, for the full-capacity launch
-  int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [capacity] keys, [capacity] hardest-first worklist
+  int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [CMPC_SM_SLOTS] SM arrival counters, [capacity] keys, [capacity] worklist
   bool lpt = true;                    // CMPC_LPT=0: natural instance order in the active-set kernel
+  int inv_stagger = 2000;             // start offset (cycles) between the inversion CTAs of an SM (CMPC_INV_STAGGER, 0 = off)
   bool resume = true;                 // CMPC_RESUME=0: overflowed instances restart from scratch in the full-capacity launch
   std::vector<PipePlan> plans;        // launch plans by (reduced size bound, horizon, adaptive)
   HostBinding bound;                  // cmpc_batch_bind_host
@@ -615,10 +616,13 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.lpt_hist = nullptr;
     Q.lpt_key = nullptr;
     if (tiled) {  // the assembly kernel left H tiles: invert them in place on the FP64 tensor cores
+      // one memset zeroes the key histogram and the SM arrival counters of the stagger
+      CK(cudaMemsetAsync(b->d_lpt[si], 0, sizeof(int) * (64 + CMPC_SM_SLOTS), st));
+      Q.sm_slots = b->d_lpt[si] + 64;
+      Q.inv_stagger = b->inv_stagger;
       if (lpt) {
         Q.lpt_hist = b->d_lpt[si];
-        Q.lpt_key = b->d_lpt[si] + 64;
-        CK(cudaMemsetAsync(Q.lpt_hist, 0, sizeof(int) * 64, st));
+        Q.lpt_key = b->d_lpt[si] + 64 + CMPC_SM_SLOTS;
       }
       Q.sched = b->d_sched[si] + 4 * c + 3;
       const int ipc2 = cmpc_invert_instances_per_cta();
@@ -641,10 +645,10 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       Q.overflow_list = nullptr;
     }
     if (lpt) {  // hardest instances first: the makespan of the kernel is its longest active-set run
-      rc = cmpc_launch_lpt_order(Q.lpt_hist, Q.lpt_key, b->d_lpt[si] + 64 + b->capacity, cnt, st);
+      rc = cmpc_launch_lpt_order(Q.lpt_hist, Q.lpt_key, b->d_lpt[si] + 64 + CMPC_SM_SLOTS + b->capacity, cnt, st);
       if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_lpt_order_kernel launch");
       b->launches++;
-      Q.worklist = b->d_lpt[si] + 64 + b->capacity;
+      Q.worklist = b->d_lpt[si] + 64 + CMPC_SM_SLOTS + b->capacity;
     }
     if (fast) rc = cmpc_launch_dual_fast(Q, std::min(cnt, b->sm_count * per_sm_fast), st);
     else rc = cmpc_launch_dual(Q, wpc1, std::min((cnt + wpc1 - 1) / wpc1, b->sm_count * per_sm2), st);
@@ -837,7 +841,8 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMalloc(&b->d_iters, sizeof(int) * cap));
   CK(cudaMalloc(&b->d_active, cap * 20 * hm));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
-  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_lpt[i], sizeof(int) * (64 + 2 * cap)));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_lpt[i], sizeof(int) * (64 + CMPC_SM_SLOTS + 2 * cap)));
+  if (const char* e = std::getenv("CMPC_INV_STAGGER")) b->inv_stagger = std::max(0, std::atoi(e));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume[i], sizeof(int) * CMPC_RESUME_INTS * cap));
   if (const char* e = std::getenv("CMPC_RESUME")) b->resume = std::atoi(e) != 0;
   if (const char* e = std::getenv("CMPC_LPT")) b->lpt = std::atoi(e) != 0;

@@ -6,6 +6,7 @@
 #include "../../include/cmpc_b200.h"
 
 #define CMPC_MAX_FS 80 /* 4 * CMPC_MAX_HORIZON rounded up */
+#define CMPC_SM_SLOTS 1024 /* >= the largest %smid + 1 */
 #define CMPC_RESUME_INTS 20 /* q, iterations, 32 working-set rows as 16-bit ids */
 
 // ---------------------------------------------------------------------------
@@ -56,7 +57,7 @@ struct CmpcParams {
   int qcap;         // working-set capacity of this launch
   int max_iter;
   int adapt_mode;   // -1 off, 0 estimate only, 1 estimate and apply, 2 apply the stored estimate
-  int pad0;
+  int inv_stagger;  // inversion kernel: start offset (SM cycles) between the CTAs that share an SM; 0 = none
   double dt;        // (double)(float)dt
   double mu_inv;    // (double)(1.f/(float)mu)   SolverMPC.cpp:657
   double f_max;     // (double)(float)f_max
@@ -101,6 +102,7 @@ struct CmpcParams {
   // constraint rows its unconstrained optimum violates (a good predictor of the active-set iterations)
   int* lpt_hist;              // [64] instances per key, zeroed per launch; null = natural order
   int* lpt_key;               // [count] key << 24 | position within the key's bucket
+  int* sm_slots;              // [CMPC_SM_SLOTS] arrival counters per SM (%smid), zeroed per launch; null = no stagger
   // optional phase clocks (profiling aid): CMPC_PH_COUNT counters of SM cycles summed over CTAs, thread 0 only
   unsigned long long* phase_cycles;
 };

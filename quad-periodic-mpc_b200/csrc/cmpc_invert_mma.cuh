@@ -257,6 +257,20 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
   double* tbuf = dtile + 66;                                     // 36 tiles, filled by one cp.async.bulk
   const int BAR_TILE = 1 + 2 * pair, BAR_DV = 2 + 2 * pair;
 
+  // The CTAs of an SM start together and every instance takes the same time, so the main warps that share a
+  // sub-partition would run their DMMA phases in LOCKSTEP for the whole launch — pipe saturated, then idle
+  // (scripts/ubench/dmma_phase_ubench.cu: 37 instead of 22 cycles per DMMA).  The second CTA to arrive on an SM
+  // therefore starts half a block step late.
+  __shared__ int sm_slot;
+  if (P.sm_slots && P.inv_stagger > 0) {
+    if (threadIdx.x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      sm_slot = atomicAdd(P.sm_slots + (smid & (CMPC_SM_SLOTS - 1)), 1);
+    }
+    __syncthreads();
+  }
+
   if (warp >= WS_MAIN) {
     // ---------------- helper: the pivot chains ----------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
@@ -278,6 +292,10 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
 
   // ---------------- main: tiles in registers, DMMA ----------------
   asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
+  if (P.sm_slots && P.inv_stagger > 0 && (sm_slot & 1)) {
+    const long long s0 = clock64();
+    while (clock64() - s0 < (long long)P.inv_stagger) { }
+  }
   const int count = P.count;
   unsigned flops_acc = 0u;
   const int fo = q * PS + r;  // fragment offset: element (k = q, row/col = r)
