@@ -251,6 +251,8 @@ struct cmpc_batch {
   int* d_resume[kMaxStreams] = {};    // per stream: working sets of the instances in d_overflow, for the full-capacity launch
   int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [CMPC_SM_SLOTS] SM arrival counters, [capacity] keys, [capacity] worklist
   bool lpt = true;                    // CMPC_LPT=0: natural instance order in the active-set kernel
+  bool sweep_dmma = false;            // CMPC_SWEEP=dmma: tensor-core sweep in the 96 / 128 condensation shapes (measured:
+                                      // +5 % on mixed gaits at h = 16, rounding error 50x the DFMA sweep's -> not the default)
   int inv_stagger = 2000;             // start offset (cycles) between the inversion CTAs of an SM (CMPC_INV_STAGGER, 0 = off)
   bool resume = true;                 // CMPC_RESUME=0: overflowed instances restart from scratch in the full-capacity launch
   std::vector<PipePlan> plans;        // launch plans by (reduced size bound, horizon, adaptive)
@@ -602,6 +604,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.qws = b->d_qws[si];
     Q.qws_stride = slot;
     Q.k_tiled = tiled;
+    Q.sweep_dmma = (!tiled && cshape != CMPC_CSHAPE_64 && b->sweep_dmma) ? 1 : 0;
     Q.qws_goff = cmpc_qws_goff(nmax, tiled);
     Q.worklist = nullptr;
     Q.count_ptr = nullptr;
@@ -846,6 +849,7 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume[i], sizeof(int) * CMPC_RESUME_INTS * cap));
   if (const char* e = std::getenv("CMPC_RESUME")) b->resume = std::atoi(e) != 0;
   if (const char* e = std::getenv("CMPC_LPT")) b->lpt = std::atoi(e) != 0;
+  if (const char* e = std::getenv("CMPC_SWEEP")) b->sweep_dmma = std::strcmp(e, "dmma") == 0;
   CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMallocHost(&b->h_forces, sizeof(double) * cap * 12 * hm));

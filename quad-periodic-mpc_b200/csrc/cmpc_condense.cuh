@@ -157,6 +157,110 @@ __device__ __forceinline__ void sweep_blocked(double (&A)[S::TM][S::TN], int n, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same blocked sweep on the FP64 tensor cores (DMMA m8n8k4) for the 96 / 128 shapes: the padded symmetric matrix
+// is held as its lower-triangular 8 x 8 tiles in accumulator layout (lane l: row l >> 2, columns 2 (l & 3), +1),
+// dealt round-robin to the eight warps of the CTA (10 / 17 tiles per warp).  Block step s:
+//   1. the owners publish the pivot rows as an 8 x NPAD panel C (tiles (s, J <= s) as they are, tiles (I > s, s)
+//      transposed — the matrix is symmetric), D - I in the diagonal block;
+//   2. warp 0 inverts D (Gauss-Jordan over shuffles) and leaves -D^-1;
+//   3. M = -D^-1 C, the column tiles dealt to the warps (two DMMAs each);
+//   4. every tile (I, J) += C_I' M_J (two DMMAs per tile).
+// Same algebra as sweep_blocked / cmpc_invert_mma.cuh: a swept diagonal entry carries a constant +2.
+// ---------------------------------------------------------------------------------------------------------------
+template <class S>
+struct DSweep {
+  static constexpr int NBLK = S::NPAD / 8, NTILE = NBLK * (NBLK + 1) / 2, NW = S::NT / 32, TPW = (NTILE + NW - 1) / NW;
+};
+
+__device__ __forceinline__ void cdmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// 8 x 8 inverse of a tile in accumulator layout (lane (r, q): D[r][2q], D[r][2q+1]), Gauss-Jordan without pivoting
+__device__ __forceinline__ void cinv8_acc(double& a0, double& a1, int r, int q) {
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const int pq = p >> 1;
+    const double mine = (p & 1) ? a1 : a0;
+    const double arp = __shfl_sync(0xffffffffu, mine, r * 4 + pq);  // D[r][p]
+    const double dpp = __shfl_sync(0xffffffffu, mine, p * 4 + pq);  // D[p][p]
+    const double ap0 = __shfl_sync(0xffffffffu, a0, p * 4 + q);     // D[p][2q]
+    const double ap1 = __shfl_sync(0xffffffffu, a1, p * 4 + q);     // D[p][2q+1]
+    const double dinv = fast_rcp(dpp);
+    const double t = arp * dinv;
+    double n0 = fma(-t, ap0, a0), n1 = fma(-t, ap1, a1);
+    if (r == p) { n0 = ap0 * dinv; n1 = ap1 * dinv; }
+    if (q == pq) {
+      if (p & 1) n1 = (r == p) ? dinv : -t;
+      else n0 = (r == p) ? dinv : -t;
+    }
+    a0 = n0;
+    a1 = n1;
+  }
+}
+
+template <class S>
+__device__ __forceinline__ void sweep_dmma(double (&t)[DSweep<S>::TPW][2], const int (&tI)[DSweep<S>::TPW],
+                                           const int (&tJ)[DSweep<S>::TPW], int n, int tid, double* pan, double* mm,
+                                           double* dv) {
+  constexpr int PS = S::PS, TPW = DSweep<S>::TPW, NW = DSweep<S>::NW;
+  const int lane = tid & 31, w = tid >> 5, r = lane >> 2, q = lane & 3;
+  const int fo = q * PS + r;  // fragment offset: element (k = q, row / column = r)
+  const int nblk = (n + 7) >> 3;
+#pragma unroll 1
+  for (int s = 0; s < nblk; s++) {
+    // 1. panel
+#pragma unroll
+    for (int i = 0; i < TPW; i++) {
+      const int I = tI[i], J = tJ[i];
+      if (I == s) {
+        double v0 = t[i][0], v1 = t[i][1];
+        if (J == s) {
+          // the pivot block itself goes to warp 0 as it is: (d - 1) + 1 would cost the small pivots their low bits
+          *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(v0, v1);
+          if (r == 2 * q) v0 -= 1.0;
+          if (r == 2 * q + 1) v1 -= 1.0;
+        }
+        *reinterpret_cast<double2*>(pan + r * PS + 8 * J + 2 * q) = make_double2(v0, v1);
+      } else if (J == s && I > s && I < nblk) {
+        pan[(2 * q) * PS + 8 * I + r] = t[i][0];
+        pan[(2 * q + 1) * PS + 8 * I + r] = t[i][1];
+      }
+    }
+    __syncthreads();
+    // 2. -D^-1 by warp 0
+    if (w == 0) {
+      const double2 d = *reinterpret_cast<const double2*>(dv + r * 8 + 2 * q);
+      double d0 = d.x, d1 = d.y;
+      cinv8_acc(d0, d1, r, q);
+      *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
+    }
+    __syncthreads();
+    // 3. M = -D^-1 C
+    {
+      const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
+      for (int J = w; J < nblk; J += NW) {
+        double m0 = 0.0, m1 = 0.0;
+        cdmma(m0, m1, a0, pan[fo + 8 * J]);
+        cdmma(m0, m1, a1, pan[fo + 4 * PS + 8 * J]);
+        *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(m0, m1);
+      }
+    }
+    __syncthreads();
+    // 4. every tile (I, J) += C_I' M_J
+#pragma unroll
+    for (int i = 0; i < TPW; i++) {
+      const int I = tI[i], J = tJ[i];
+      if (I >= 0 && I < nblk) {
+        cdmma(t[i][0], t[i][1], pan[fo + 8 * I], mm[fo + 8 * J]);
+        cdmma(t[i][0], t[i][1], pan[fo + 4 * PS + 8 * I], mm[fo + 4 * PS + 8 * J]);
+      }
+    }
+    __syncthreads();  // the next publish overwrites pan
+  }
+}
+
 }  // namespace
 
 template <class S, bool ADAPT>
@@ -470,6 +574,62 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
       int e2;
       frexp(dmax, &e2);
       const double scale = ldexp(1.0, -e2);  // exact; scaled diagonal < 1
+      if (P.sweep_dmma) {
+        // ---- FP64 tensor-core sweep: tiles from the staged H, K back into the staging area, x0 = -K g, one
+        //      coalesced copy to the workspace slot ----
+        constexpr int TPW = DSweep<S>::TPW, NWARP = DSweep<S>::NW, NTILE = DSweep<S>::NTILE;
+        const int lane = tid & 31, w = tid >> 5, r = lane >> 2, q = lane & 3;
+        int tI[TPW], tJ[TPW];
+        double t[TPW][2];
+#pragma unroll
+        for (int i = 0; i < TPW; i++) {
+          const int k = w + NWARP * i;
+          int I = -1, J = 0;
+          if (k < NTILE) {
+            I = 0;
+            while ((I + 1) * (I + 2) / 2 <= k) I++;
+            J = k - I * (I + 1) / 2;
+          }
+          tI[i] = I;
+          tJ[i] = J;
+          t[i][0] = 0.0;
+          t[i][1] = 0.0;
+          if (I >= 0) {
+            const int ii = 8 * I + r, j0 = 8 * J + 2 * q;
+            t[i][0] = (ii < n && j0 < n) ? Hs[ii * n + j0] * scale : (ii == j0 ? 0.5 : 0.0);
+            t[i][1] = (ii < n && j0 + 1 < n) ? Hs[ii * n + j0 + 1] * scale : (ii == j0 + 1 ? 0.5 : 0.0);
+          }
+        }
+        pc.tick(CMPC_PH_LOAD);
+        __syncthreads();  // every tile is in registers before the staging area is reused
+        sweep_dmma<S>(t, tI, tJ, n, tid, pan, mm, dinvs);
+        pc.tick(CMPC_PH_SWEEP);
+        // K_ij = -(A_ij - 2 d_ij) scale, both triangles, into the staging area
+#pragma unroll
+        for (int i = 0; i < TPW; i++) {
+          const int I = tI[i], J = tJ[i];
+          if (I < 0) continue;
+          const int ii = 8 * I + r, j0 = 8 * J + 2 * q;
+          const double k0 = -(t[i][0] - (ii == j0 ? 2.0 : 0.0)) * scale;
+          const double k1 = -(t[i][1] - (ii == j0 + 1 ? 2.0 : 0.0)) * scale;
+          if (ii < n && j0 < n) {
+            Hs[ii * n + j0] = k0;
+            if (I != J) Hs[j0 * n + ii] = k0;  // a diagonal tile holds both triangles itself
+          }
+          if (ii < n && j0 + 1 < n) {
+            Hs[ii * n + j0 + 1] = k1;
+            if (I != J) Hs[(j0 + 1) * n + ii] = k1;
+          }
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += NT) {
+          double acc = 0.0;
+          for (int i = 0; i < n; i++) acc = fma(Hs[i * n + j], g[i], acc);
+          slot[P.qws_goff + j] = g[j];
+          slot[P.qws_goff + P.nmax + j] = -acc;
+        }
+        for (int idx = tid; idx < n * n; idx += NT) slot[idx] = Hs[idx];
+      } else {
       double A[TM][TN];
 #pragma unroll
       for (int a = 0; a < TM; a++)
@@ -511,6 +671,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
         const double gj = g[j];
         slot[P.qws_goff + j] = gj;
         slot[P.qws_goff + P.nmax + j] = scale * (acc - 2.0 * gj);
+      }
       }
       flops_acc += 2.0 * (double)n * n * n * 0.5 + 12.0 * (double)n * n + 2.0 * (double)n * n;
     }

@@ -96,6 +96,7 @@ struct CmpcParams {
   double* qws;                // [count][qws_stride]: K (nmax x nmax, row stride n), g, x0, header
   size_t qws_stride;          // doubles per slot, >= cmpc_qws_slot_doubles(nmax)
   int* sched;                 // work counter of THIS launch (zeroed by the host)
+  int sweep_dmma;             // condensation kernel of the 96 / 128 shapes: sweep on the FP64 tensor cores (else DFMA register tiles)
   int k_tiled;                // K is stored as 36 lower-triangular 8x8 tiles (cmpc_condense_mma.cuh), else row-major n x n
   int qws_goff;               // offset (doubles) of g in a slot; x0 follows at +nmax, the header at +2 nmax
   // hardest-first order of the active-set kernel: the inversion kernel files every instance under the number of

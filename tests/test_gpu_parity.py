@@ -401,3 +401,15 @@ def test_submit_wait_overlaps_two_batches(built_lib):
                 assert (res[key] == want[k][key]).all(), (rep, k, key)
     for b in bs:
         b.close()
+
+
+def test_tensor_core_sweep_of_the_large_shapes(built_lib):
+    """CMPC_SWEEP=dmma: the 96 / 128-variable condensation shapes with the blocked sweep on the FP64 tensor cores
+    (opt-in) against the default DFMA sweep: same optimum within 1e-5 N (its rounding error is larger), same masks."""
+    for h, gaits, nseg in ((16, ("trot", "bound", "pace", "gallop"), 10), (10, ("stand",), None)):
+        inst = synth.make_batch(192, horizon=h, seed=77, gaits=gaits, n_segment=nseg, spread=1.5)
+        ref = _solve_env(inst, {})
+        res = _solve_env(inst, {"CMPC_SWEEP": "dmma"})
+        assert (res["status"] == ref["status"]).all()
+        assert np.abs(res["forces"] - ref["forces"]).max() <= 1e-5
+        assert (res["active"] == ref["active"]).all()
