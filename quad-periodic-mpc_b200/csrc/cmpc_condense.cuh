@@ -623,10 +623,18 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
         }
         __syncthreads();
         for (int j = tid; j < n; j += NT) {
-          double acc = 0.0;
-          for (int i = 0; i < n; i++) acc = fma(Hs[i * n + j], g[i], acc);
+          // x0 = -K g as a compensated dot product (TwoProduct / TwoSum): the terms are ~1e8 times the result, a plain
+          // FMA chain would leave its rounding error in the forces
+          double hi = 0.0, lo = 0.0;
+          for (int i = 0; i < n; i++) {
+            const double a = Hs[i * n + j], b = g[i];
+            const double p = a * b, pe = fma(a, b, -p);
+            const double sum = hi + p, bp = sum - hi;
+            lo += ((hi - (sum - bp)) + (p - bp)) + pe;
+            hi = sum;
+          }
           slot[P.qws_goff + j] = g[j];
-          slot[P.qws_goff + P.nmax + j] = -acc;
+          slot[P.qws_goff + P.nmax + j] = -(hi + lo);
         }
         for (int idx = tid; idx < n * n; idx += NT) slot[idx] = Hs[idx];
       } else {
