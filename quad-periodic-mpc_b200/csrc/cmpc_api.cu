@@ -1082,7 +1082,7 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
   CK(cudaSetDevice(b->device));
   int nchunks = 1;
   if (const char* e = std::getenv("CMPC_CHUNKS")) nchunks = std::atoi(e);
-  else if (count >= 2048) nchunks = std::min(kMaxChunks, std::max(2, count / 16384));  // measured: scripts/e2e_probe.py
+  else nchunks = std::max(1, std::min(4, count / 4096));  // measured (scripts/e2e_chunks.py): one chunk up to 8191, four from 16384
   nchunks = std::max(1, std::min(nchunks, kMaxChunks));
   const int direct = hb.direct;
   const SoaView& soa = hb.soa;
@@ -1109,8 +1109,6 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
       const int first = c * per, n = std::min(per, count - first);
       if (n <= 0) break;
       const auto tq0 = std::chrono::steady_clock::now();
-      chunk_maxc[c] = max_contact_scan(b, in->gait, first, n);
-      if (trace) tr_scan += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
       const size_t f = (size_t)first;
       auto at = [&](int i, size_t bytes_per_instance) -> const void* { return soa.p[i] ? soa.p[i] + f * bytes_per_instance : nullptr; };
       const int rcp = cmpc_launch_pack(at(0, 12), at(1, 12), at(2, 16), at(3, 12), at(4, 48), at(5, 48), at(6, 48 * (size_t)h),
@@ -1124,6 +1122,15 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
         CK(cudaEventRecord(tr_ev[2 * c], ps));
         tr_pack += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
       }
+    }
+    // the host's only pass over the inputs (the contact bound that sizes the solve kernels) runs while the device is
+    // already reading the arrays
+    for (int c = 0; c < nchunks; c++) {
+      const int first = c * per, n = std::min(per, count - first);
+      if (n <= 0) break;
+      const auto tq0 = std::chrono::steady_clock::now();
+      chunk_maxc[c] = max_contact_scan(b, in->gait, first, n);
+      if (trace) tr_scan += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
     }
   }
   for (int c = 0; c < nchunks; c++) {
