@@ -171,7 +171,7 @@ namespace {
 // Launch plan of the pipeline for one (reduced size bound, horizon, adaptive) combination: kernel shapes, shared
 // memory, CTAs per SM.  The occupancy queries behind it cost tens of microseconds, so a batch keeps its plans.
 struct PipePlan {
-  int nmax = 0, h = 0, adapt = 0;
+  int nmax = 0, h = 0, adapt = 0, qcap_pref = 0;
   int cshape = 0, tiled = 0;
   size_t slot = 0;
   int chunk_cap = 0;  // instances whose workspace stays L2-sized
@@ -251,6 +251,7 @@ struct cmpc_batch {
   int* d_resume[kMaxStreams] = {};    // per stream: working sets of the instances in d_overflow, for the full-capacity launch
   int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [CMPC_SM_SLOTS] SM arrival counters, [capacity] keys, [capacity] worklist
   bool lpt = true;                    // CMPC_LPT=0: natural instance order in the active-set kernel
+  bool throughput_mode = false;       // set by solve_range (batches pipelined over the streams), cleared by the end-to-end calls
   bool sweep_dmma = false;            // CMPC_SWEEP=dmma: tensor-core sweep in the 96 / 128 condensation shapes (measured:
                                       // +5 % on mixed gaits at h = 16, rounding error 50x the DFMA sweep's -> not the default)
   int inv_stagger = 2000;             // start offset (cycles) between the inversion CTAs of an SM (CMPC_INV_STAGGER, 0 = off)
@@ -464,7 +465,7 @@ int fork_streams(cmpc_batch* b, int only = -1) {
 // Two-kernel pipeline (cmpc_pipeline.cu) over the instances P describes, in chunks whose workspace stays
 // L2-sized: condensation + K = H^-1 (one CTA per instance), then the dual active set (one warp per
 // instance) with a small working-set capacity, then the few instances that outgrew it at full capacity.
-int make_pipe_plan(const CmpcParams& P, PipePlan& pl) {
+int make_pipe_plan(const CmpcParams& P, int qcap_pref, PipePlan& pl) {
   const bool adapt = P.adapt_mode >= 0;
   const int nmax = P.nmax;
   pl.nmax = nmax;
@@ -495,7 +496,7 @@ int make_pipe_plan(const CmpcParams& P, PipePlan& pl) {
     return CMPC_E_NODEVICE;
   }
   // kernel 2, two working-set capacity tiers
-  int qcap1 = 32;
+  int qcap1 = qcap_pref;
   if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
   if (qcap1 < 1 || qcap1 > nmax) qcap1 = nmax;
   bool fast = qcap1 <= 32;  // tier 1 on the register-resident kernel (cmpc_dual_fast.cuh)
@@ -529,11 +530,16 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
   const bool adapt = P.adapt_mode >= 0;
   const int nmax = P.nmax;
   const PipePlan* plp = nullptr;
+  // first-tier working-set capacity: 32 rows for one batch at a time (the shortest active-set kernel), 24 when
+  // batches are pipelined over the streams (ten instead of seven warps per SM; the ~1 % of instances beyond 24 rows
+  // are resumed by the any-capacity launch, off the critical path of the following batches) — measured, profiles/
+  const int qcap_pref = (b->throughput_mode && nmax < 64) ? 24 : 32;
   for (const PipePlan& c : b->plans)
-    if (c.nmax == nmax && c.h == P.horizon && c.adapt == (int)adapt) plp = &c;
+    if (c.nmax == nmax && c.h == P.horizon && c.adapt == (int)adapt && c.qcap_pref == qcap_pref) plp = &c;
   if (!plp) {
     PipePlan pl;
-    if (int e = make_pipe_plan(P, pl)) return e;
+    pl.qcap_pref = qcap_pref;
+    if (int e = make_pipe_plan(P, qcap_pref, pl)) return e;
     b->plans.push_back(pl);
     plp = &b->plans.back();
   }
@@ -952,6 +958,7 @@ int cmpc_batch_solve_range(cmpc_batch* b, int first, int count) {
   CK(cudaSetDevice(b->device));
   // a large range is cut into `split` parts on successive streams: kernels of different parts (assembly,
   // inversion, active set) then share the SMs instead of each waiting for the previous kernel's tail
+  b->throughput_mode = !b->serial;
   const int parts = (b->serial || count < 512 * b->split) ? 1 : b->split;
   const int per = (count + parts - 1) / parts;
   for (int part = 0; part < parts; part++) {
@@ -1079,6 +1086,7 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
   const cmpc_inputs* in = &hb.in;
   const cmpc_outputs* out = &hb.out;
   int rc = CMPC_OK;
+  b->throughput_mode = false;
   CK(cudaSetDevice(b->device));
   int nchunks = 1;
   if (const char* e = std::getenv("CMPC_CHUNKS")) nchunks = std::atoi(e);
@@ -1395,6 +1403,7 @@ int cmpc_batch_solve_commands(cmpc_batch* b, int count, const cmpc_command* comm
   }
   if (b->hist_len < (1 << 30)) b->hist_len++;
   b->adapt_mode = b->hist_len < CMPC_ADAPT_WINDOW ? -1 : (b->hist_len <= 500 ? 0 : 2);
+  b->throughput_mode = false;
   b->count = count;
   b->max_contact = maxc;
   rc = launch_range(b, 0, count, maxc, 0);
@@ -1538,6 +1547,7 @@ int cmpc_batch_profile_range(cmpc_batch* b, int first, int count, float ms[4]) {
     for (int i = 0; i < CMPC_K_COUNT + 1; i++) CK(cudaEventCreate(&b->prof_ev[i]));
   for (int i = 0; i < CMPC_K_COUNT; i++) { ms[i] = 0.f; b->prof_ms[i] = 0.f; }
   b->profiling = true;
+  b->throughput_mode = !b->serial;  // the kernels as solve_range configures them
   int rc = launch_range(b, first, count, b->max_contact, 0);
   b->profiling = false;
   if (rc) return rc;

@@ -330,8 +330,17 @@ def test_interleaved_uploads_and_solves_stay_ordered(built_lib):
     for i in range(ring):
         b.solve_range(i * B, B)
     full = b.download()
-    whole = solve(inst)
+    # the reference: the same instances solved as ONE range on one stream (same kernels, same capacity tiers)
+    ref_b = engine.Batch(B * ring)
+    ref_b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    ref_b.upload(inst)
+    ref_b.solve_range(0, B * ring)
+    whole = ref_b.download()
+    ref_b.close()
     assert (full["forces"] == whole["forces"]).all() and (full["status"] == 0).all()
+    # and the end-to-end call (first capacity tier of 32 rows instead of 24: a few working sets take the other tier)
+    host = solve(inst)
+    assert np.abs(full["forces"] - host["forces"]).max() <= 1e-7 and (full["active"] == host["active"]).all()
     # overwrite the records while solves are in flight, solve again: results follow the new records
     perm = np.random.default_rng(1).permutation(B * ring)
     inst2 = {k: (v[perm] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
