@@ -177,6 +177,7 @@ struct PipePlan {
   int chunk_cap = 0;  // instances whose workspace stays L2-sized
   int per_sm1 = 0, per_sm_inv = 0;
   int qcap1 = 0, fast = 0, per_sm_fast = 0, wpc1 = 0, per_sm2 = 0, wpc2 = 0, per_sm3 = 0;
+  int qcap_mid = 0, wpc_mid = 0, per_sm_mid = 0;  // middle capacity tier (0: none)
 };
 
 }  // namespace
@@ -248,7 +249,9 @@ struct cmpc_batch {
   size_t qws_bytes[kMaxStreams] = {};
   int* d_sched[kMaxStreams] = {};
   int sched_ints[kMaxStreams] = {};
-  int* d_resume[kMaxStreams] = {};    // per stream: working sets of the instances in d_overflow, for the full-capacity launch
+  int* d_resume[kMaxStreams] = {};    // per stream: working sets of the instances in d_overflow, for the next capacity tier
+  int* d_overflow2[kMaxStreams] = {}; // per stream: second overflow list (middle tier -> full capacity) + count
+  int* d_resume2[kMaxStreams] = {};
   int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [CMPC_SM_SLOTS] SM arrival counters, [capacity] keys, [capacity] worklist
   bool lpt = true;                    // CMPC_LPT=0: natural instance order in the active-set kernel
   bool throughput_mode = false;       // set by solve_range (batches pipelined over the streams), cleared by the end-to-end calls
@@ -518,6 +521,18 @@ int make_pipe_plan(const CmpcParams& P, int qcap_pref, PipePlan& pl) {
     g_err = "cmpc_batch_solve: active-set kernel not launchable on this device (no sm_100a image?)";
     return CMPC_E_NODEVICE;
   }
+  // a middle tier for the larger reduced problems: at full capacity one warp's K N and P fill an SM's shared memory
+  pl.qcap_mid = 0;
+  if (nmax > 64 && qcap1 < CMPC_QCAP_MID && !std::getenv("CMPC_NO_MID_TIER")) {
+    int wm = 4;
+    while (wm > 1 && cmpc_dual_smem_bytes_per_warp(nmax, CMPC_QCAP_MID) * wm > 100 * 1024) wm >>= 1;
+    const int pm = cmpc_dual_max_ctas_per_sm(wm, cmpc_dual_smem_bytes_per_warp(nmax, CMPC_QCAP_MID) * wm);
+    if (pm >= 1) {
+      pl.qcap_mid = CMPC_QCAP_MID;
+      pl.wpc_mid = wm;
+      pl.per_sm_mid = pm;
+    }
+  }
   pl.qcap1 = qcap1;
   pl.fast = fast ? 1 : 0;
   pl.wpc1 = wpc1;
@@ -644,11 +659,12 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.sched = b->d_sched[si] + 4 * c + 1;
     Q.qcap = qcap1;
     if (int e = prof_begin()) return e;
-    Q.resume = nullptr;
+    Q.resume_in = nullptr;
+    Q.resume_out = nullptr;
     if (qcap1 < nmax) {
       Q.overflow_list = b->d_overflow[si];
       Q.overflow_count = b->d_overflow[si] + b->capacity;
-      if (fast && b->resume) Q.resume = b->d_resume[si];
+      if (fast && b->resume) Q.resume_out = b->d_resume[si];
       CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
     } else {
       Q.overflow_list = nullptr;
@@ -664,11 +680,32 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel launch");
     b->launches++;
     if (qcap1 < nmax) {
+      // the instances that outgrew the first tier: resumed at a middle capacity (three warps per SM instead of one for
+      // the larger problems), the few that outgrow that too at full capacity
+      const bool mid = pl.qcap_mid > 0 && pl.qcap_mid < nmax && fast && b->resume;
       Q.sched = b->d_sched[si] + 4 * c + 2;
-      Q.qcap = nmax;
       Q.worklist = b->d_overflow[si];
       Q.count_ptr = b->d_overflow[si] + b->capacity;
+      Q.resume_in = Q.resume_out;
+      Q.resume_out = nullptr;
       Q.overflow_list = nullptr;
+      if (mid) {
+        Q.qcap = pl.qcap_mid;
+        Q.overflow_list = b->d_overflow2[si];
+        Q.overflow_count = b->d_overflow2[si] + b->capacity;
+        Q.resume_out = b->d_resume2[si];
+        CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
+        rc = cmpc_launch_dual(Q, pl.wpc_mid, std::min((cnt + pl.wpc_mid - 1) / pl.wpc_mid, b->sm_count * pl.per_sm_mid), st);
+        if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel (middle capacity) launch");
+        b->launches++;
+        Q.worklist = b->d_overflow2[si];
+        Q.count_ptr = b->d_overflow2[si] + b->capacity;
+        Q.resume_in = b->d_resume2[si];
+        Q.resume_out = nullptr;
+        Q.overflow_list = nullptr;
+        Q.sched = b->d_sched[si] + 4 * c + 3;  // the inversion kernel's counter, unused (and zero) on the shapes beyond 63 variables
+      }
+      Q.qcap = nmax;
       rc = cmpc_launch_dual(Q, wpc2, std::min((cnt + wpc2 - 1) / wpc2, b->sm_count * per_sm3), st);
       if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel (full capacity) launch");
       b->launches++;
@@ -853,6 +890,8 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_lpt[i], sizeof(int) * (64 + CMPC_SM_SLOTS + 2 * cap)));
   if (const char* e = std::getenv("CMPC_INV_STAGGER")) b->inv_stagger = std::max(0, std::atoi(e));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume[i], sizeof(int) * CMPC_RESUME_INTS * cap));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow2[i], sizeof(int) * (cap + 1)));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume2[i], sizeof(int) * CMPC_RESUME_INTS * cap));
   if (const char* e = std::getenv("CMPC_RESUME")) b->resume = std::atoi(e) != 0;
   if (const char* e = std::getenv("CMPC_LPT")) b->lpt = std::atoi(e) != 0;
   if (const char* e = std::getenv("CMPC_SWEEP")) b->sweep_dmma = std::strcmp(e, "dmma") == 0;
@@ -877,7 +916,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
   cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops); cudaFree(b->d_phase);
   cudaFree(b->d_gws);
-  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); cudaFree(b->d_lpt[i]); cudaFree(b->d_resume[i]); }
+  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); cudaFree(b->d_lpt[i]); cudaFree(b->d_resume[i]); cudaFree(b->d_overflow2[i]); cudaFree(b->d_resume2[i]); }
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFree(b->d_cmds); cudaFree(b->d_results); cudaFree(b->d_fext);

@@ -7,7 +7,8 @@
 
 #define CMPC_MAX_FS 80 /* 4 * CMPC_MAX_HORIZON rounded up */
 #define CMPC_SM_SLOTS 1024 /* >= the largest %smid + 1 */
-#define CMPC_RESUME_INTS 20 /* q, iterations, 32 working-set rows as 16-bit ids */
+#define CMPC_RESUME_INTS 34 /* q, iterations, up to 64 working-set rows as 16-bit ids */
+#define CMPC_QCAP_MID 56    /* middle capacity tier of the active-set kernel for reduced problems beyond 64 variables */
 
 // ---------------------------------------------------------------------------
 // Instance record (HBM, one per MPC instance, 16-byte aligned, fetched with a
@@ -72,8 +73,9 @@ struct CmpcParams {
   const int* count_ptr;       // optional device-side instance count (tier-2 launch), capped by `count`
   int* overflow_list;         // instances whose working set outgrew qcap
   int* overflow_count;
-  int* resume;                // [overflow entries][CMPC_RESUME_INTS]: the working set an overflowed instance had reached
-                              // (written by the first tier next to overflow_list, read by the full-capacity launch)
+  int* resume_out;            // [overflow entries][CMPC_RESUME_INTS]: the working set an overflowed instance had reached,
+                              // written next to overflow_list by the tier that ran out of capacity
+  const int* resume_in;       // the same records, read by the launch that takes the worklist over (null: restart from x0)
   double* forces;             // [count][12h]
   double* objective;          // [count]
   int* status;                // [count]

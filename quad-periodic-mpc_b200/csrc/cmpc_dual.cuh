@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
       // ---- resume: the first tier ran out of working-set capacity at a valid state of the method (x optimal on the
       //      face of its working set A, multipliers >= 0).  Rebuild that state from A alone: border P and cache K N
       //      row by row (no line searches), then u = -P s_A(x0), x = x0 + K N u ----
-      if (P.resume && P.worklist) {
-        const int* rs = P.resume + (size_t)slot_i * CMPC_RESUME_INTS;
+      if (P.resume_in && P.worklist) {
+        const int* rs = P.resume_in + (size_t)slot_i * CMPC_RESUME_INTS;
         const int rq = min(rs[0], qcap);
         for (int k = 0; k < rq; k++) {
           const int w2 = rs[2 + (k >> 1)];
@@ -335,10 +335,21 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
       }
     }
     if (status == CMPC_ST_WSOVERFLOW && P.overflow_list) {
-      // left for the full-capacity launch
+      // left for the next capacity tier, with the working set reached here (up to 64 rows travel as 16-bit ids)
+      int pos = 0;
       if (lane == 0) {
-        const int pos = atomicAdd(P.overflow_count, 1);
+        pos = atomicAdd(P.overflow_count, 1);
         P.overflow_list[pos] = inst;
+      }
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (P.resume_out) {
+        int* rs = P.resume_out + (size_t)pos * CMPC_RESUME_INTS;
+        const int qs = min(q, 2 * (CMPC_RESUME_INTS - 2));
+        for (int k = lane; 2 * k < qs; k += 32) {
+          const int lo = (unsigned short)act[2 * k], hi = (2 * k + 1 < qs) ? (unsigned short)act[2 * k + 1] : 0;
+          rs[2 + k] = lo | (hi << 16);
+        }
+        if (lane == 0) { rs[0] = qs; rs[1] = iters - 1; }
       }
       __syncwarp();
       continue;

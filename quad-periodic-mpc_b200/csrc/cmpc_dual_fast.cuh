@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
         P.overflow_list[pos] = inst;
       }
       pos = __shfl_sync(0xffffffffu, pos, 0);
-      if (P.resume) {
-        int* rs = P.resume + (size_t)pos * CMPC_RESUME_INTS;
+      if (P.resume_out) {
+        int* rs = P.resume_out + (size_t)pos * CMPC_RESUME_INTS;
         const int mine = (lane < q) ? sact : 0;
         const int nb = __shfl_down_sync(0xffffffffu, mine, 1);
         if (!(lane & 1)) rs[2 + (lane >> 1)] = (mine & 0xffff) | (nb << 16);
