@@ -95,6 +95,8 @@ void build_adapt_tables(std::vector<double>& tw, std::vector<float>& gk) {
 
 constexpr int kMaxChunks = 8;
 constexpr int kMaxStreams = 8;
+constexpr int kRstateStride = 32 * 32;                                   // P of a 32-row working set, full rows
+constexpr int kRstate2Stride = CMPC_QCAP_MID * (CMPC_QCAP_MID + 1) / 2;  // P of a middle-tier working set, packed
 constexpr int kPackStream = 2;  // end-to-end call: the record-packing kernels of all chunks, in order
 
 // Small persistent worker pool for the host side of the end-to-end call (record packing, result unpacking):
@@ -252,6 +254,9 @@ struct cmpc_batch {
   int* d_resume[kMaxStreams] = {};    // per stream: working sets of the instances in d_overflow, for the next capacity tier
   int* d_overflow2[kMaxStreams] = {}; // per stream: second overflow list (middle tier -> full capacity) + count
   int* d_resume2[kMaxStreams] = {};
+  double* d_rstate[kMaxStreams] = {};   // per stream: P of the overflowed working sets, first tier -> next ([rstate_cap][1024])
+  double* d_rstate2[kMaxStreams] = {};  // middle tier -> full capacity ([rstate2_cap][1600], packed)
+  int rstate_cap = 0, rstate2_cap = 0;
   int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [CMPC_SM_SLOTS] SM arrival counters, [capacity] keys, [capacity] worklist
   bool lpt = true;                    // CMPC_LPT=0: natural instance order in the active-set kernel
   bool throughput_mode = false;       // set by solve_range (batches pipelined over the streams), cleared by the end-to-end calls
@@ -664,7 +669,14 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     if (qcap1 < nmax) {
       Q.overflow_list = b->d_overflow[si];
       Q.overflow_count = b->d_overflow[si] + b->capacity;
-      if (fast && b->resume) Q.resume_out = b->d_resume[si];
+      Q.rstate_out = nullptr;
+      Q.rstate_in = nullptr;
+      if (fast && b->resume) {
+        Q.resume_out = b->d_resume[si];
+        Q.rstate_out = b->d_rstate[si];
+        Q.rstate_out_stride = kRstateStride;
+        Q.rstate_out_cap = b->rstate_cap;
+      }
       CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
     } else {
       Q.overflow_list = nullptr;
@@ -688,12 +700,19 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       Q.count_ptr = b->d_overflow[si] + b->capacity;
       Q.resume_in = Q.resume_out;
       Q.resume_out = nullptr;
+      Q.rstate_in = Q.rstate_out;
+      Q.rstate_in_stride = Q.rstate_out_stride;
+      Q.rstate_in_cap = Q.rstate_out_cap;
+      Q.rstate_out = nullptr;
       Q.overflow_list = nullptr;
       if (mid) {
         Q.qcap = pl.qcap_mid;
         Q.overflow_list = b->d_overflow2[si];
         Q.overflow_count = b->d_overflow2[si] + b->capacity;
         Q.resume_out = b->d_resume2[si];
+        Q.rstate_out = b->d_rstate2[si];
+        Q.rstate_out_stride = kRstate2Stride;
+        Q.rstate_out_cap = b->rstate2_cap;
         CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
         rc = cmpc_launch_dual(Q, pl.wpc_mid, std::min((cnt + pl.wpc_mid - 1) / pl.wpc_mid, b->sm_count * pl.per_sm_mid), st);
         if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel (middle capacity) launch");
@@ -702,6 +721,10 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
         Q.count_ptr = b->d_overflow2[si] + b->capacity;
         Q.resume_in = b->d_resume2[si];
         Q.resume_out = nullptr;
+        Q.rstate_in = b->d_rstate2[si];
+        Q.rstate_in_stride = kRstate2Stride;
+        Q.rstate_in_cap = b->rstate2_cap;
+        Q.rstate_out = nullptr;
         Q.overflow_list = nullptr;
         Q.sched = b->d_sched[si] + 4 * c + 3;  // the inversion kernel's counter, unused (and zero) on the shapes beyond 63 variables
       }
@@ -892,6 +915,10 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume[i], sizeof(int) * CMPC_RESUME_INTS * cap));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow2[i], sizeof(int) * (cap + 1)));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume2[i], sizeof(int) * CMPC_RESUME_INTS * cap));
+  b->rstate_cap = (int)std::min<size_t>(cap, std::max<size_t>(1024, cap / 4));
+  b->rstate2_cap = (int)std::min<size_t>(cap, std::max<size_t>(256, cap / 16));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_rstate[i], sizeof(double) * kRstateStride * (size_t)b->rstate_cap));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_rstate2[i], sizeof(double) * kRstate2Stride * (size_t)b->rstate2_cap));
   if (const char* e = std::getenv("CMPC_RESUME")) b->resume = std::atoi(e) != 0;
   if (const char* e = std::getenv("CMPC_LPT")) b->lpt = std::atoi(e) != 0;
   if (const char* e = std::getenv("CMPC_SWEEP")) b->sweep_dmma = std::strcmp(e, "dmma") == 0;
@@ -916,7 +943,7 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
   cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops); cudaFree(b->d_phase);
   cudaFree(b->d_gws);
-  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); cudaFree(b->d_lpt[i]); cudaFree(b->d_resume[i]); cudaFree(b->d_overflow2[i]); cudaFree(b->d_resume2[i]); }
+  for (int i = 0; i < kMaxStreams; i++) { cudaFree(b->d_overflow[i]); cudaFree(b->d_qws[i]); cudaFree(b->d_sched[i]); cudaFree(b->d_lpt[i]); cudaFree(b->d_resume[i]); cudaFree(b->d_overflow2[i]); cudaFree(b->d_resume2[i]); cudaFree(b->d_rstate[i]); cudaFree(b->d_rstate2[i]); }
   cudaFree(b->d_twiddle); cudaFree(b->d_gk); cudaFree(b->d_win_t); cudaFree(b->d_win_d); cudaFree(b->d_simtime);
   cudaFree(b->d_est); cudaFree(b->d_fest);
   cudaFree(b->d_cmds); cudaFree(b->d_results); cudaFree(b->d_fext);

@@ -76,6 +76,13 @@ struct CmpcParams {
   int* resume_out;            // [overflow entries][CMPC_RESUME_INTS]: the working set an overflowed instance had reached,
                               // written next to overflow_list by the tier that ran out of capacity
   const int* resume_in;       // the same records, read by the launch that takes the worklist over (null: restart from x0)
+  // the iterate that goes with a resume record, so that the next tier continues without re-bordering the working set:
+  // per overflow entry [x (nmax)] [u (q)] [P = (N'KN)^-1: q x q full rows from the fast tier, packed lower triangle from
+  // the any-capacity tier]; entries beyond rstate_*_cap carry the row ids only
+  double* rstate_out;
+  const double* rstate_in;
+  int rstate_out_stride, rstate_in_stride;  // doubles per entry
+  int rstate_out_cap, rstate_in_cap;        // entries
   double* forces;             // [count][12h]
   double* objective;          // [count]
   int* status;                // [count]

@@ -144,8 +144,36 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
       //      row by row (no line searches), then u = -P s_A(x0), x = x0 + K N u ----
       if (P.resume_in && P.worklist) {
         const int* rs = P.resume_in + (size_t)slot_i * CMPC_RESUME_INTS;
-        const int rq = min(rs[0], qcap);
-        for (int k = 0; k < rq; k++) {
+        const int rq = min(rs[0] & 0xffff, qcap);
+        const int pfmt = (rs[0] >> 16) & 3;  // 0: row ids only, 1: P as q x q rows, 2: P packed (lower triangle)
+        const bool have_p = pfmt != 0 && P.rstate_in && slot_i < P.rstate_in_cap && rq == (rs[0] & 0xffff);
+        if (have_p) {
+          // the working set with its P: cache K N for every row (independent row fetches), copy P, done
+          const double* stp = P.rstate_in + (size_t)slot_i * P.rstate_in_stride;
+          for (int k = lane; k < rq; k += 32) {
+            const int w2 = rs[2 + (k >> 1)];
+            const int p = (k & 1) ? ((w2 >> 16) & 0xffff) : (w2 & 0xffff);
+            act[k] = (short)p;
+            isact[p] = 1;
+          }
+          __syncwarp();
+          for (int k = 0; k < rq; k++) {
+            int pia, piz;
+            double pva, pvz;
+            cons_of(act[k], mu_inv, pia, pva, piz, pvz);
+            for (int i = lane; i < n; i += 32)
+              KN[k * nmax + i] = pva * k_entry(slot, n, tiled, pia, i) + pvz * k_entry(slot, n, tiled, piz, i);
+          }
+          if (pfmt == 1) {
+            for (int k = 0; k < rq; k++)
+              for (int l = lane; l <= k; l += 32) Pp[k * (k + 1) / 2 + l] = stp[k * rq + l];
+          } else {
+            for (int e = lane; e < rq * (rq + 1) / 2; e += 32) Pp[e] = stp[e];
+          }
+          q = rq;
+          __syncwarp();
+        }
+        for (int k = have_p ? rq : 0; k < rq; k++) {  // row ids only: border P and cache K N row by row
           const int w2 = rs[2 + (k >> 1)];
           const int p = (k & 1) ? ((w2 >> 16) & 0xffff) : (w2 & 0xffff);
           int pia, piz;
@@ -349,7 +377,13 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
           const int lo = (unsigned short)act[2 * k], hi = (2 * k + 1 < qs) ? (unsigned short)act[2 * k + 1] : 0;
           rs[2 + k] = lo | (hi << 16);
         }
-        if (lane == 0) { rs[0] = qs; rs[1] = iters - 1; }
+        bool with_p = false;
+        if (P.rstate_out && pos < P.rstate_out_cap && qs == q && q * (q + 1) / 2 <= P.rstate_out_stride) {
+          double* stp = P.rstate_out + (size_t)pos * P.rstate_out_stride;
+          for (int e = lane; e < q * (q + 1) / 2; e += 32) stp[e] = Pp[e];
+          with_p = true;
+        }
+        if (lane == 0) { rs[0] = qs | (with_p ? (2 << 16) : 0); rs[1] = iters - 1; }
       }
       __syncwarp();
       continue;

@@ -386,7 +386,17 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
         const int mine = (lane < q) ? sact : 0;
         const int nb = __shfl_down_sync(0xffffffffu, mine, 1);
         if (!(lane & 1)) rs[2 + (lane >> 1)] = (mine & 0xffff) | (nb << 16);
-        if (lane == 0) { rs[0] = q; rs[1] = iters - 1; }
+        // P = (N'KN)^-1 of the working set travels too when there is room for it (it depends on the rows only and has
+        // not been bordered with the candidate): the next tier then derives u = -P s_A(x0) and x = x0 + K N u directly
+        // instead of re-bordering row by row
+        bool with_p = false;
+        if (P.rstate_out && pos < P.rstate_out_cap && q * q <= P.rstate_out_stride) {
+          double* st = P.rstate_out + (size_t)pos * P.rstate_out_stride;
+          for (int k = 0; k < q; k++)
+            if (lane < q) st[k * q + lane] = Pm[k * PSQ + lane];
+          with_p = true;
+        }
+        if (lane == 0) { rs[0] = q | (with_p ? (1 << 16) : 0); rs[1] = iters - 1; }
       }
       __syncwarp();
       continue;
