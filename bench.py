@@ -270,8 +270,8 @@ def run_b200(args, rank, world, local_rank):
         peaks, peak_kind = measured_peaks()
         fp64 = engine.measure_fp64_peak(local_rank)
         step_ms = region_ms / args.steps
-        names = {"assemble": "cmpc_assemble_mma_kernel", "invert": "cmpc_invert_mma_kernel",
-                 "dual": "cmpc_dual_fast_kernel (+ cmpc_dual_kernel for overflowed working sets)", "fused": "cmpc_solve_kernel"}
+        names = {"assemble": "cmpc_assemble_mma_kernel", "invert": "cmpc_invert_ws_kernel",
+                 "dual": "cmpc_lpt_order_kernel + cmpc_dual_fast_kernel + cmpc_dual_kernel (resumed working sets beyond the first tier)", "fused": "cmpc_solve_kernel"}
         bounds = {"assemble": "latency / issue (FP64 FMA + shared memory)", "invert": "tensor (FP64 DMMA)",
                   "dual": "latency (dependent chain per active-set iteration)", "fused": "latency"}
         kernels = []
@@ -319,7 +319,7 @@ def run_b200(args, rank, world, local_rank):
                                         "MEASURED_PEAKS.json holds no FP64 figure",
                          "flops_per_launch": fl_dom,
                          "flops_note": "algorithmic: n^3 + 2 n^2 per instance (symmetric inverse + x0 = -K g), n = 60; "
-                                       "the kernel executes 1.7x that (padding to 64, full diagonal tiles, D^-1 C)",
+                                       "the kernel executes 1.6x that (padding to 64, full diagonal tiles, D^-1 C)",
                          "timing": "CUDA events around each kernel class of %d serial solves of cold ring batches" % prof_n,
                          "traffic_note": "dram bytes of one ncu --set full launch (profiles/); ncu flushes L2 between "
                                          "kernels, in the pipeline the tiles written by the assembly kernel are L2 hits",
