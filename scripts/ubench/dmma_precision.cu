@@ -1,5 +1,6 @@
 // Rounding behaviour of DMMA m8n8k4 against an FMA chain: C = sum over many k-steps of A_k B_k with random data,
-// compared with a double-double (error-free) reference on the host.  Is the tensor-core accumulation round-to-nearest?
+// compared with a long-double reference on the host.  Is the tensor-core accumulation round-to-nearest?
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o dmma_precision dmma_precision.cu
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
