@@ -97,6 +97,9 @@ constexpr int kMaxChunks = 8;
 constexpr int kMaxStreams = 8;
 constexpr int kRstateStride = 32 * 32;                                   // P of a 32-row working set, full rows
 constexpr int kRstate2Stride = CMPC_QCAP_MID * (CMPC_QCAP_MID + 1) / 2;  // P of a middle-tier working set, packed
+// control block of one chunk of a pipeline launch, zeroed by ONE memset per launch: work counters of the kernels,
+// overflow counts of the two capacity hand-overs, the hardest-first histogram, the SM arrival counters of the stagger
+constexpr int kCtlSched = 0, kCtlOvf = 4, kCtlOvf2 = 5, kCtlHist = 8, kCtlSlots = 8 + 64, kCtlInts = 8 + 64 + CMPC_SM_SLOTS;
 constexpr int kPackStream = 2;  // end-to-end call: the record-packing kernels of all chunks, in order
 
 // Small persistent worker pool for the host side of the end-to-end call (record packing, result unpacking):
@@ -249,7 +252,7 @@ struct cmpc_batch {
   // two-kernel pipeline: per-stream workspace slots (K, g, x0 per instance of a chunk) and work counters
   double* d_qws[kMaxStreams] = {};
   size_t qws_bytes[kMaxStreams] = {};
-  int* d_sched[kMaxStreams] = {};
+  int* d_sched[kMaxStreams] = {};     // per stream: control blocks (kCtlInts ints per chunk of a pipeline launch)
   int sched_ints[kMaxStreams] = {};
   int* d_resume[kMaxStreams] = {};    // per stream: working sets of the instances in d_overflow, for the next capacity tier
   int* d_overflow2[kMaxStreams] = {}; // per stream: second overflow list (middle tier -> full capacity) + count
@@ -257,7 +260,7 @@ struct cmpc_batch {
   double* d_rstate[kMaxStreams] = {};   // per stream: P of the overflowed working sets, first tier -> next ([rstate_cap][1024])
   double* d_rstate2[kMaxStreams] = {};  // middle tier -> full capacity ([rstate2_cap][1600], packed)
   int rstate_cap = 0, rstate2_cap = 0;
-  int* d_lpt[kMaxStreams] = {};       // per stream: [64] key histogram, [CMPC_SM_SLOTS] SM arrival counters, [capacity] keys, [capacity] worklist
+  int* d_lpt[kMaxStreams] = {};       // per stream: [capacity] hardest-first keys, [capacity] worklist
   bool lpt = true;                    // CMPC_LPT=0: natural instance order in the active-set kernel
   bool throughput_mode = false;       // set by solve_range (batches pipelined over the streams), cleared by the end-to-end calls
   bool sweep_dmma = false;            // CMPC_SWEEP=dmma: tensor-core sweep in the 96 / 128 condensation shapes (measured:
@@ -572,7 +575,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
   const int chunk = std::min(count, pl.chunk_cap);
   const int nchunks = (count + chunk - 1) / chunk;
   const size_t need = (size_t)chunk * slot * sizeof(double);
-  if (need > b->qws_bytes[si] || 4 * nchunks > b->sched_ints[si]) {
+  if (need > b->qws_bytes[si] || kCtlInts * nchunks > b->sched_ints[si]) {
     // grow the workspaces of every stream in use at once: the first solves of the other streams then find theirs
     { int rcs = sync_all(b); if (rcs) return rcs; }
     for (int k = 0; k < kMaxStreams; k++) {
@@ -584,17 +587,17 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
         CK(cudaMalloc(&b->d_qws[k], need));
         b->qws_bytes[k] = need;
       }
-      if (4 * nchunks > b->sched_ints[k]) {
+      if (kCtlInts * nchunks > b->sched_ints[k]) {
         if (b->d_sched[k]) CK(cudaFree(b->d_sched[k]));
         b->d_sched[k] = nullptr;
         b->sched_ints[k] = 0;
-        const int ints = std::max(4 * nchunks, 1024);
+        const int ints = kCtlInts * std::max(nchunks, 4);
         CK(cudaMalloc(&b->d_sched[k], sizeof(int) * ints));
         b->sched_ints[k] = ints;
       }
     }
   }
-  CK(cudaMemsetAsync(b->d_sched[si], 0, sizeof(int) * 4 * nchunks, st));
+  CK(cudaMemsetAsync(b->d_sched[si], 0, sizeof(int) * kCtlInts * nchunks, st));
   const CmpcParams base = P;
   // cmpc_batch_profile_range: CUDA events between the kernel classes (the stream is drained per class)
   auto prof_begin = [&]() -> int {
@@ -634,7 +637,8 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.qws_goff = cmpc_qws_goff(nmax, tiled);
     Q.worklist = nullptr;
     Q.count_ptr = nullptr;
-    Q.sched = b->d_sched[si] + 4 * c;
+    int* const ctl = b->d_sched[si] + kCtlInts * c;
+    Q.sched = ctl + kCtlSched;
     const int ipc = cmpc_condense_instances_per_cta(cshape);
     if (int e = prof_begin()) return e;
     int rc = cmpc_launch_condense(Q, cshape, std::min((cnt + ipc - 1) / ipc, b->sm_count * per_sm1), st);
@@ -645,15 +649,13 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.lpt_hist = nullptr;
     Q.lpt_key = nullptr;
     if (tiled) {  // the assembly kernel left H tiles: invert them in place on the FP64 tensor cores
-      // one memset zeroes the key histogram and the SM arrival counters of the stagger
-      CK(cudaMemsetAsync(b->d_lpt[si], 0, sizeof(int) * (64 + CMPC_SM_SLOTS), st));
-      Q.sm_slots = b->d_lpt[si] + 64;
+      Q.sm_slots = ctl + kCtlSlots;
       Q.inv_stagger = b->inv_stagger;
       if (lpt) {
-        Q.lpt_hist = b->d_lpt[si];
-        Q.lpt_key = b->d_lpt[si] + 64 + CMPC_SM_SLOTS;
+        Q.lpt_hist = ctl + kCtlHist;
+        Q.lpt_key = b->d_lpt[si];
       }
-      Q.sched = b->d_sched[si] + 4 * c + 3;
+      Q.sched = ctl + kCtlSched + 3;
       const int ipc2 = cmpc_invert_instances_per_cta();
       if (int e = prof_begin()) return e;
       rc = cmpc_launch_invert(Q, std::min((cnt + ipc2 - 1) / ipc2, b->sm_count * per_sm_inv), st);
@@ -661,14 +663,14 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       b->launches++;
       if (int e = prof_end(CMPC_K_INVERT)) return e;
     }
-    Q.sched = b->d_sched[si] + 4 * c + 1;
+    Q.sched = ctl + kCtlSched + 1;
     Q.qcap = qcap1;
     if (int e = prof_begin()) return e;
     Q.resume_in = nullptr;
     Q.resume_out = nullptr;
     if (qcap1 < nmax) {
       Q.overflow_list = b->d_overflow[si];
-      Q.overflow_count = b->d_overflow[si] + b->capacity;
+      Q.overflow_count = ctl + kCtlOvf;
       Q.rstate_out = nullptr;
       Q.rstate_in = nullptr;
       if (fast && b->resume) {
@@ -677,15 +679,14 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
         Q.rstate_out_stride = kRstateStride;
         Q.rstate_out_cap = b->rstate_cap;
       }
-      CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
     } else {
       Q.overflow_list = nullptr;
     }
     if (lpt) {  // hardest instances first: the makespan of the kernel is its longest active-set run
-      rc = cmpc_launch_lpt_order(Q.lpt_hist, Q.lpt_key, b->d_lpt[si] + 64 + CMPC_SM_SLOTS + b->capacity, cnt, st);
+      rc = cmpc_launch_lpt_order(Q.lpt_hist, Q.lpt_key, b->d_lpt[si] + b->capacity, cnt, st);
       if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_lpt_order_kernel launch");
       b->launches++;
-      Q.worklist = b->d_lpt[si] + 64 + CMPC_SM_SLOTS + b->capacity;
+      Q.worklist = b->d_lpt[si] + b->capacity;
     }
     if (fast) rc = cmpc_launch_dual_fast(Q, std::min(cnt, b->sm_count * per_sm_fast), st);
     else rc = cmpc_launch_dual(Q, wpc1, std::min((cnt + wpc1 - 1) / wpc1, b->sm_count * per_sm2), st);
@@ -695,9 +696,9 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       // the instances that outgrew the first tier: resumed at a middle capacity (three warps per SM instead of one for
       // the larger problems), the few that outgrow that too at full capacity
       const bool mid = pl.qcap_mid > 0 && pl.qcap_mid < nmax && fast && b->resume;
-      Q.sched = b->d_sched[si] + 4 * c + 2;
+      Q.sched = ctl + kCtlSched + 2;
       Q.worklist = b->d_overflow[si];
-      Q.count_ptr = b->d_overflow[si] + b->capacity;
+      Q.count_ptr = ctl + kCtlOvf;
       Q.resume_in = Q.resume_out;
       Q.resume_out = nullptr;
       Q.rstate_in = Q.rstate_out;
@@ -708,17 +709,16 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       if (mid) {
         Q.qcap = pl.qcap_mid;
         Q.overflow_list = b->d_overflow2[si];
-        Q.overflow_count = b->d_overflow2[si] + b->capacity;
+        Q.overflow_count = ctl + kCtlOvf2;
         Q.resume_out = b->d_resume2[si];
         Q.rstate_out = b->d_rstate2[si];
         Q.rstate_out_stride = kRstate2Stride;
         Q.rstate_out_cap = b->rstate2_cap;
-        CK(cudaMemsetAsync(Q.overflow_count, 0, sizeof(int), st));
         rc = cmpc_launch_dual(Q, pl.wpc_mid, std::min((cnt + pl.wpc_mid - 1) / pl.wpc_mid, b->sm_count * pl.per_sm_mid), st);
         if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel (middle capacity) launch");
         b->launches++;
         Q.worklist = b->d_overflow2[si];
-        Q.count_ptr = b->d_overflow2[si] + b->capacity;
+        Q.count_ptr = ctl + kCtlOvf2;
         Q.resume_in = b->d_resume2[si];
         Q.resume_out = nullptr;
         Q.rstate_in = b->d_rstate2[si];
@@ -726,7 +726,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
         Q.rstate_in_cap = b->rstate2_cap;
         Q.rstate_out = nullptr;
         Q.overflow_list = nullptr;
-        Q.sched = b->d_sched[si] + 4 * c + 3;  // the inversion kernel's counter, unused (and zero) on the shapes beyond 63 variables
+        Q.sched = ctl + kCtlSched + 3;  // the inversion kernel's counter, unused (and zero) on the shapes beyond 63 variables
       }
       Q.qcap = nmax;
       rc = cmpc_launch_dual(Q, wpc2, std::min((cnt + wpc2 - 1) / wpc2, b->sm_count * per_sm3), st);
@@ -910,7 +910,7 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMalloc(&b->d_iters, sizeof(int) * cap));
   CK(cudaMalloc(&b->d_active, cap * 20 * hm));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
-  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_lpt[i], sizeof(int) * (64 + CMPC_SM_SLOTS + 2 * cap)));
+  for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_lpt[i], sizeof(int) * 2 * cap));
   if (const char* e = std::getenv("CMPC_INV_STAGGER")) b->inv_stagger = std::max(0, std::atoi(e));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume[i], sizeof(int) * CMPC_RESUME_INTS * cap));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow2[i], sizeof(int) * (cap + 1)));
