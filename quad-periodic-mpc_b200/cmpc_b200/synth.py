@@ -183,7 +183,7 @@ def make_commands(batch, dtype, horizon=10, gaits=("trot",), seed=0, spread=1.0,
     c["gait_iteration"] = rng.integers(0, h, B)
     mixed = rng.random(B) < mixed_fraction
     c["gait_kind"] = mixed.astype(np.int32)
-    periods = rng.integers(3, h + 1, (B, 4))
+    periods = rng.integers(min(3, h), h + 1, (B, 4))
     c["gait_offsets"][mixed] = periods[mixed]
     c["gait_duty"] = rng.uniform(0.35, 0.65, B)
     c["omni_mode"] = rng.random(B) < 0.25
