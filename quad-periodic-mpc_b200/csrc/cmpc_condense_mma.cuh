@@ -55,7 +55,7 @@ __host__ __device__ inline MCarve make_mcarve(int h, int rec_stride, bool adapt)
   c.rowinfo = o; o += 4 * MMA_NPAD;
   c.g = o; o += 8 * MMA_NPAD;
   c.pq = o; o += 16 * MMA_PQ;
-  c.xtab = o; o += align16(24 * h * h);  // x_drag couplings: XA[ab], X0[ab], XA[ba]
+  c.xtab = o; o += align16(32 * h * h);  // x_drag couplings: XA[ab], X0[ab], XA[ba], and a table of zeros
   // pan, mm, dv are contiguous: the estimator (3 x 400 doubles) borrows them
   c.pan = o; o += 8 * 8 * MMA_PS;
   c.mm = o; o += 8 * 8 * MMA_PS;
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
   for (int i = tid; i < hh; i += NT)
     SS[i] = make_double2(__ldg(P.sigma + CMPC_SIG_22 * hh + i), __ldg(P.sigma + CMPC_SIG_11 * hh + i));
   for (int i = 144 + tid; i < MMA_PQ; i += NT) PQ[i] = make_double2(0.0, 0.0);
+  for (int i = tid; i < hh; i += NT) xtab[3 * hh + i] = 0.0;  // what a component pair without an x_drag coupling adds
   if (tid == 0) {
     const int cur0 = atomicAdd(P.sched, 1);
     redi[2] = cur0;
@@ -440,8 +441,7 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
       const int nblk = (n + 7) >> 3;
       double tl[4][2], th[8][2];  // tile rows ILO (J <= ILO) and IHI (J <= IHI)
       {
-        int rah[2], rpo[2];
-        unsigned rfl = 0;  // bit t: row component is x, bit 2 + t: row component is z (x_drag couplings)
+        int rah[2], rpo[2], xs0[2], xs2[2];
 #pragma unroll
         for (int t = 0; t < 2; t++) {
           const int info = rowinfo[8 * (t ? IHI : ILO) + r];
@@ -449,8 +449,9 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
           const int c1 = info >> 16;
           rah[t] = ok ? (info & 0xff) * h : 0;
           rpo[t] = ok ? ((info >> 8) & 3) * 36 + c1 * 3 : 144;
-          if (ok && c1 == 0) rfl |= 1u << t;
-          if (ok && c1 == 2) rfl |= 4u << t;
+          // table of the x_drag coupling this row has with an x column / a z column
+          xs0[t] = (ok && c1 == 0) ? hh : ((ok && c1 == 2) ? 0 : 3 * hh);
+          xs2[t] = (ok && c1 == 0) ? 2 * hh : 3 * hh;
         }
         const double alpha2s = C.alpha2 * scale;
         const bool brow = (w == 0 && r == 7);  // row 63 lives in warp 0's tile row 7
@@ -474,12 +475,9 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
                 const double2 pq = PQ[rpo[t] + cpo];
                 double v = fma(ss.x, pq.x, ss.y * pq.y);
                 if (drag) {
-                  // (c1, c2) = (x, x): X0[ab]; (z, x): XA[ab]; (x, z): XA[ba]
-                  const bool r0 = (rfl >> t) & 1u, r2 = (rfl >> (2 + t)) & 1u;
-                  const int ab = rah[t] + cb;
-                  if (r0 && k0) v += xtab[hh + ab];
-                  if (r2 && k0) v += xtab[ab];
-                  if (r0 && k2) v += xtab[2 * hh + ab];
+                  // (c1, c2) = (x, x): X0[ab]; (z, x): XA[ab]; (x, z): XA[ba]; every other pair: the zero table
+                  const int tsel = k0 ? xs0[t] : (k2 ? xs2[t] : 3 * hh);
+                  v += xtab[tsel + rah[t] + cb];
                 }
                 const int i = 8 * I + r, j = 8 * J + 2 * q + e;
                 if (I == J && i == j) v += (i < n) ? alpha2s : 0.5;  // alpha; 1/2 on the padding diagonal
