@@ -210,29 +210,36 @@ def run_b200(args, rank, world, local_rank):
     h2d = int(sum(a.nbytes for a in be._prepared_inputs.values()))   # the eleven input arrays the device reads over PCIe
     d2h = int(sum(a.nbytes for a in res.values()))                    # forces, objective, status, iterations
 
-    # ---- the same call with two batches in flight (submit / wait): step k+1 is submitted before step k is waited for ----
-    pipe = []
-    for k in range(2):
-        sk = {kk: (v[(k + 1) * BATCH:(k + 2) * BATCH] if isinstance(v, np.ndarray) else v) for kk, v in inst.items()}
-        bk = engine.Batch(BATCH, device=local_rank)
-        bk.setup(DT, h, inst["mu"], inst["f_max"])
-        bk.prepare_host(sk, want_active=False)
-        pipe.append(bk)
-    for k in range(2 * max(1, args.warmup)):
-        pipe[k % 2].solve_prepared()
-    barrier()
-    t0 = time.perf_counter()
-    pipe[0].submit_prepared()
-    for k in range(1, args.steps):
-        pipe[k % 2].submit_prepared()
-        rp = pipe[(k - 1) % 2].wait_prepared()
-    rp = pipe[(args.steps - 1) % 2].wait_prepared()
-    barrier()
-    pipe_wall = time.perf_counter() - t0
-    pipe_units, pipe_seconds = allreduce_sum_max(float(args.steps * BATCH), pipe_wall)
-    assert (rp["status"] == 0).all()
-    for bk in pipe:
-        bk.close()
+    # ---- the same call with D batches in flight (submit / wait): step k is submitted before step k-D+1 is waited for ----
+    def in_flight(depth):
+        pipe = []
+        for k in range(depth):
+            sk = {kk: (v[(k + 1) * BATCH:(k + 2) * BATCH] if isinstance(v, np.ndarray) else v) for kk, v in inst.items()}
+            bk = engine.Batch(BATCH, device=local_rank)
+            bk.setup(DT, h, inst["mu"], inst["f_max"])
+            bk.prepare_host(sk, want_active=False)
+            pipe.append(bk)
+        for k in range(depth * max(1, args.warmup)):
+            pipe[k % depth].solve_prepared()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            if k >= depth:
+                rp = pipe[k % depth].wait_prepared()
+            pipe[k % depth].submit_prepared()
+        for k in range(max(args.steps, depth), max(args.steps, depth) + min(depth, args.steps)):
+            rp = pipe[k % depth].wait_prepared()
+        barrier()
+        wall = time.perf_counter() - t0
+        units, secs = allreduce_sum_max(float(args.steps * BATCH), wall)
+        assert (rp["status"] == 0).all()
+        for bk in pipe:
+            bk.close()
+        return units, secs
+
+    pipe_units, pipe_seconds = in_flight(2)
+    deep = min(8, ring - 1)
+    deep_units, deep_seconds = in_flight(deep)
 
     # ---- end to end one level up: the controller-level call (updateMPCIfNeeded / solveDenseMPC on the device) ----
     cmds = synth.make_commands(BATCH, engine.COMMAND_DTYPE, horizon=h, gaits=("trot",), seed=2000 + rank)
@@ -340,6 +347,9 @@ def run_b200(args, rank, world, local_rank):
                                       "ms_per_step": 1e3 * pipe_seconds / args.steps,
                                       "call": "cmpc_batch_submit_bound / cmpc_batch_wait_bound on two batches: every step "
                                               "still reads its inputs from and writes its results to pinned host arrays"},
+                    "deep_in_flight": {"value": deep_units / deep_seconds, "unit": "solves/s", "batches_in_flight": deep,
+                                       "ms_per_step": 1e3 * deep_seconds / args.steps,
+                                       "call": "the same submit / wait calls on %d engine handles (scripts/e2e_depth.py)" % deep},
                     "commands": {"value": cmd_units / cmd_seconds, "unit": "solves/s", "steps": csteps,
                                  "h2d_bytes_per_step": int(cmds.nbytes), "d2h_bytes_per_step": int(cres.nbytes),
                                  "ms_per_step": 1e3 * cmd_seconds / csteps,

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "cmpc_device.h"
 
 namespace {
@@ -27,25 +29,44 @@ struct PackArgs {
   int tail_words;  // zero padding after the gait bytes
 };
 
-__global__ void __launch_bounds__(256) cmpc_pack_records_kernel(const __grid_constant__ PackArgs A) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// Each thread keeps PACK_UNROLL independent loads in flight per pass: the source is host memory behind PCIe
+// (~2 us per request), so the bytes in flight decide the rate, not the thread count — few CTAs then read as fast
+// as many and leave the SMs' register files to the solve kernels of other batches (scripts/e2e_depth.py).
+constexpr int PACK_UNROLL = 8;
+constexpr int PACK_THREADS = 512;
+
+__global__ void __launch_bounds__(PACK_THREADS) cmpc_pack_records_kernel(const __grid_constant__ PackArgs A) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll 1
   for (int s = 0; s < PACK_SEGS; s++) {
     const Seg sg = A.seg[s];
     if (sg.width == 0) continue;
-    const long long total = (long long)A.count * sg.width;
-    for (long long j = t0; j < total; j += stride) {
-      const int inst = (int)(j / sg.width), k = (int)(j - (long long)inst * sg.width);
-      const uint32_t v = sg.src ? __ldcs(sg.src + j) : 0u;
-      A.records[(size_t)inst * A.rec_words + sg.dst + k] = v;
+    const unsigned width = (unsigned)sg.width;
+    const unsigned total = (unsigned)A.count * width;  // < 2^31: the launcher cuts larger batches
+#pragma unroll 1
+    for (unsigned base = t0; base < total; base += stride * PACK_UNROLL) {
+      uint32_t v[PACK_UNROLL];
+#pragma unroll
+      for (int u = 0; u < PACK_UNROLL; u++) {
+        const unsigned j = base + u * stride;
+        v[u] = (sg.src && j < total) ? __ldcs(sg.src + j) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < PACK_UNROLL; u++) {
+        const unsigned j = base + u * stride;
+        if (j < total) {
+          const unsigned inst = j / width, k = j - inst * width;
+          A.records[(size_t)inst * A.rec_words + sg.dst + k] = v[u];
+        }
+      }
     }
   }
   // reserved words and the padding behind the gait bytes
-  const int zw = 3 + A.tail_words;
-  for (long long j = t0; j < (long long)A.count * zw; j += stride) {
-    const int inst = (int)(j / zw), k = (int)(j - (long long)inst * zw);
-    const int dst = k < 3 ? CMPC_REC_SIMTIME + k : A.tail_dst + (k - 3);
+  const unsigned zw = 3 + A.tail_words;
+  for (unsigned j = t0; j < (unsigned)A.count * zw; j += stride) {
+    const unsigned inst = j / zw, k = j - inst * zw;
+    const int dst = k < 3 ? CMPC_REC_SIMTIME + (int)k : A.tail_dst + ((int)k - 3);
     A.records[(size_t)inst * A.rec_words + dst] = 0u;
   }
 }
@@ -57,13 +78,23 @@ int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w,
                      const void* traj, const void* alpha, const void* gait, const void* x_drag, const void* f_dist,
                      unsigned char* records, int rec_stride, int horizon, int count, int sm_count, void* stream) {
   if (count <= 0) return 0;
+  const int h = horizon;
+  // 32-bit word indices inside the kernel: larger batches go out in pieces
+  const int piece = (int)(0x7fffffffLL / (12LL * h + 64));
+  if (count > piece) {
+    auto adv = [&](const void* a, size_t bytes) -> const void* { return a ? static_cast<const char*>(a) + (size_t)piece * bytes : nullptr; };
+    int rc = cmpc_launch_pack(p, v, q, w, r, weights, traj, alpha, gait, x_drag, f_dist, records, rec_stride, horizon, piece, sm_count, stream);
+    if (rc) return rc;
+    return cmpc_launch_pack(adv(p, 12), adv(v, 12), adv(q, 16), adv(w, 12), adv(r, 48), adv(weights, 48), adv(traj, 48 * (size_t)h),
+                            adv(alpha, 4), adv(gait, 4 * (size_t)h), adv(x_drag, 4), adv(f_dist, 24),
+                            records + (size_t)piece * rec_stride, rec_stride, horizon, count - piece, sm_count, stream);
+  }
   PackArgs A;
   auto set = [&](int i, const void* src, int width, int dst) {
     A.seg[i].src = static_cast<const uint32_t*>(src);
     A.seg[i].width = width;
     A.seg[i].dst = dst;
   };
-  const int h = horizon;
   set(0, traj, 12 * h, CMPC_REC_TRAJ);  // the largest array first: its loads are in flight while the rest is issued
   set(1, gait, h, CMPC_REC_TRAJ + 12 * h);
   set(2, r, 12, CMPC_REC_R);
@@ -82,9 +113,12 @@ int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w,
   A.tail_dst = CMPC_REC_TRAJ + 13 * h;
   A.tail_words = A.rec_words - A.tail_dst;
   const long long words = (long long)count * (12 * h);
-  int grid = (int)((words + 255) / 256);
-  if (grid > sm_count * 2) grid = sm_count * 2;  // few, fat CTAs: they also have to find room beside resident solve kernels
+  const long long per_cta = (long long)PACK_THREADS * PACK_UNROLL;
+  int grid = (int)((words + per_cta - 1) / per_cta);
+  static const int grid_cap = [] { const char* e = std::getenv("CMPC_PACK_GRID"); return e ? std::atoi(e) : 0; }();  // experiments
+  const int cap = grid_cap > 0 ? grid_cap : (sm_count + 7) / 8;  // few, fat CTAs (measured: profiles/r1_s4_pack_grid.txt): they have to find room beside resident solve kernels
+  if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  cmpc_pack_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+  cmpc_pack_records_kernel<<<grid, PACK_THREADS, 0, (cudaStream_t)stream>>>(A);
   return (int)cudaGetLastError();
 }
