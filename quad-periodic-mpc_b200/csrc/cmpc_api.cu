@@ -217,6 +217,10 @@ struct cmpc_batch {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, mark0 = nullptr, mark1 = nullptr;
   cudaEvent_t chunk_done[kMaxChunks] = {};
   cudaEvent_t packed[kMaxChunks] = {};    // end-to-end call: chunk c's records are in HBM
+  cudaStream_t copy_stream = nullptr;     // end-to-end call: the copy engine brings the reference trajectories (71 % of the input bytes) ...
+  cudaEvent_t traj_copied[kMaxChunks] = {};
+  float* d_traj_stage = nullptr;          // ... here, while the packing kernel reads the ten small arrays over PCIe itself
+  bool traj_copy = true;                  // CMPC_TRAJ_COPY=0: the packing kernel reads every array itself
   // successive solve_range calls rotate through the streams so that the latency-bound tails of a batch's kernels
   // overlap the kernels of the following batches; these events carry the cross-stream ordering
   cudaEvent_t join_ev = nullptr;      // scratch: "stream i has reached this point"
@@ -896,6 +900,9 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaEventCreate(&b->mark1));
   for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->chunk_done[i], cudaEventDisableTiming));
   for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->packed[i], cudaEventDisableTiming));
+  for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->traj_copied[i], cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+  if (const char* e = std::getenv("CMPC_TRAJ_COPY")) b->traj_copy = std::atoi(e) != 0;
   CK(cudaEventCreateWithFlags(&b->join_ev, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming));
   const size_t cap = (size_t)capacity;
@@ -903,6 +910,7 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   const size_t rec_max = (size_t)cmpc_rec_stride(hm);
   CK(cudaMallocHost(&b->h_rec, cap * rec_max));
   CK(cudaMalloc(&b->d_rec, cap * rec_max));
+  if (b->traj_copy) CK(cudaMalloc(&b->d_traj_stage, sizeof(float) * cap * 12 * hm));
   CK(cudaMalloc(&b->d_sigma, sizeof(double) * CMPC_SIG_COUNT * hm * hm));
   CK(cudaMalloc(&b->d_forces, sizeof(double) * cap * 12 * hm));
   CK(cudaMalloc(&b->d_obj, sizeof(double) * cap));
@@ -952,6 +960,9 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); cudaEventDestroy(b->mark0); cudaEventDestroy(b->mark1);
   for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->chunk_done[i]);
   for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->packed[i]);
+  for (int i = 0; i < kMaxChunks; i++) cudaEventDestroy(b->traj_copied[i]);
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+  cudaFree(b->d_traj_stage);
   for (int i = 0; i < CMPC_K_COUNT + 1; i++) if (b->prof_ev[i]) cudaEventDestroy(b->prof_ev[i]);
   cudaEventDestroy(b->join_ev); cudaEventDestroy(b->fork_ev);
   for (int i = 0; i < kMaxStreams; i++) cudaStreamDestroy(b->stream[i]);
@@ -1179,15 +1190,37 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
   if (soa.ok) {
     cudaStream_t ps = b->stream[kPackStream];
     CK(cudaStreamWaitEvent(ps, b->ev0, 0));
+    // The reference trajectories are 71 % of the input bytes: the copy engine moves them (52 GB/s against ~35 GB/s for
+    // loads issued by SMs, scripts/pcie_copy_rate.py) while the packing kernel reads the ten small arrays over PCIe
+    // itself; a second launch then scatters the staged trajectories from HBM.
+    const bool tcopy = b->traj_copy && b->d_traj_stage && soa.p[6];
+    if (tcopy) {
+      CK(cudaStreamWaitEvent(b->copy_stream, b->ev0, 0));
+      for (int c = 0; c < nchunks; c++) {
+        const int first = c * per, n = std::min(per, count - first);
+        if (n <= 0) break;
+        const size_t off = (size_t)first * 12 * h;
+        CK(cudaMemcpyAsync(b->d_traj_stage + off, soa.p[6] + off * sizeof(float), sizeof(float) * (size_t)n * 12 * h, cudaMemcpyDefault, b->copy_stream));
+        CK(cudaEventRecord(b->traj_copied[c], b->copy_stream));
+      }
+    }
     for (int c = 0; c < nchunks; c++) {
       const int first = c * per, n = std::min(per, count - first);
       if (n <= 0) break;
       const auto tq0 = std::chrono::steady_clock::now();
       const size_t f = (size_t)first;
       auto at = [&](int i, size_t bytes_per_instance) -> const void* { return soa.p[i] ? soa.p[i] + f * bytes_per_instance : nullptr; };
-      const int rcp = cmpc_launch_pack(at(0, 12), at(1, 12), at(2, 16), at(3, 12), at(4, 48), at(5, 48), at(6, 48 * (size_t)h),
-                                       at(7, 4), at(8, 4 * (size_t)h), at(9, 4), at(10, 24),
-                                       b->d_rec + f * b->rec_stride, b->rec_stride, h, n, b->sm_count, ps);
+      const void* traj_src = tcopy ? static_cast<const void*>(b->d_traj_stage + f * 12 * h) : at(6, 48 * (size_t)h);
+      int rcp = cmpc_launch_pack(at(0, 12), at(1, 12), at(2, 16), at(3, 12), at(4, 48), at(5, 48), traj_src,
+                                 at(7, 4), at(8, 4 * (size_t)h), at(9, 4), at(10, 24),
+                                 b->d_rec + f * b->rec_stride, b->rec_stride, h, n, b->sm_count, ps, tcopy ? CMPC_PACK_REST : CMPC_PACK_ALL);
+      if (rcp == 0 && tcopy) {
+        CK(cudaStreamWaitEvent(ps, b->traj_copied[c], 0));
+        rcp = cmpc_launch_pack(at(0, 12), at(1, 12), at(2, 16), at(3, 12), at(4, 48), at(5, 48), traj_src,
+                               at(7, 4), at(8, 4 * (size_t)h), at(9, 4), at(10, 24),
+                               b->d_rec + f * b->rec_stride, b->rec_stride, h, n, b->sm_count, ps, CMPC_PACK_TRAJ);
+        b->launches++;
+      }
       if (rcp != 0) return fail_cuda((cudaError_t)rcp, "cmpc_pack_records_kernel launch");
       b->launches++;
       CK(cudaEventRecord(b->packed[c], ps));

@@ -196,4 +196,6 @@ int cmpc_launch_epilogue(const void* cmds, const double* forces, const int* stat
 /* cmpc_pack.cu: instance records from structure-of-arrays inputs (device-accessible pointers, e.g. pinned host memory) */
 int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w, const void* r, const void* weights,
                      const void* traj, const void* alpha, const void* gait, const void* x_drag, const void* f_dist,
-                     unsigned char* records, int rec_stride, int horizon, int count, int sm_count, void* stream);
+                     unsigned char* records, int rec_stride, int horizon, int count, int sm_count, void* stream,
+                     int which /* CMPC_PACK_ALL, or the two halves of a split call: _REST (all but traj), _TRAJ (traj only) */);
+enum { CMPC_PACK_ALL = 0, CMPC_PACK_REST = 1, CMPC_PACK_TRAJ = 2 };

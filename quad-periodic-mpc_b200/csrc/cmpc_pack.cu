@@ -27,6 +27,8 @@ struct PackArgs {
   int gait_words;  // h: words of gait bytes per instance
   int tail_dst;    // first word after the gait bytes
   int tail_words;  // zero padding after the gait bytes
+  int vec;         // 16-byte source loads where the array is aligned
+  int zero_tail;   // write the reserved words and the padding (once per record)
 };
 
 // Each thread keeps PACK_UNROLL independent loads in flight per pass: the source is host memory behind PCIe
@@ -34,6 +36,7 @@ struct PackArgs {
 // as many and leave the SMs' register files to the solve kernels of other batches (scripts/e2e_depth.py).
 constexpr int PACK_UNROLL = 8;
 constexpr int PACK_THREADS = 512;
+constexpr int PACK_VUNROLL = 4;
 
 __global__ void __launch_bounds__(PACK_THREADS) cmpc_pack_records_kernel(const __grid_constant__ PackArgs A) {
   const unsigned stride = gridDim.x * blockDim.x;
@@ -44,8 +47,37 @@ __global__ void __launch_bounds__(PACK_THREADS) cmpc_pack_records_kernel(const _
     if (sg.width == 0) continue;
     const unsigned width = (unsigned)sg.width;
     const unsigned total = (unsigned)A.count * width;  // < 2^31: the launcher cuts larger batches
+    // 16-byte loads where the source allows: a warp then asks for 512 contiguous bytes per request
+    unsigned done = 0;
+    if (A.vec && sg.src && (reinterpret_cast<uintptr_t>(sg.src) & 15) == 0) {
+      const unsigned nvec = total >> 2;
+      const uint4* src4 = reinterpret_cast<const uint4*>(sg.src);
 #pragma unroll 1
-    for (unsigned base = t0; base < total; base += stride * PACK_UNROLL) {
+      for (unsigned base = t0; base < nvec; base += stride * PACK_VUNROLL) {
+        uint4 v[PACK_VUNROLL];
+#pragma unroll
+        for (int u = 0; u < PACK_VUNROLL; u++) {
+          const unsigned j = base + u * stride;
+          v[u] = (j < nvec) ? __ldcs(src4 + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < PACK_VUNROLL; u++) {
+          const unsigned j = base + u * stride;
+          if (j < nvec) {
+            unsigned inst = (4u * j) / width, k = 4u * j - inst * width;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              A.records[(size_t)inst * A.rec_words + sg.dst + k] = w[e];
+              if (++k == width) { k = 0; inst++; }
+            }
+          }
+        }
+      }
+      done = nvec << 2;
+    }
+#pragma unroll 1
+    for (unsigned base = done + t0; base < total; base += stride * PACK_UNROLL) {
       uint32_t v[PACK_UNROLL];
 #pragma unroll
       for (int u = 0; u < PACK_UNROLL; u++) {
@@ -63,6 +95,7 @@ __global__ void __launch_bounds__(PACK_THREADS) cmpc_pack_records_kernel(const _
     }
   }
   // reserved words and the padding behind the gait bytes
+  if (!A.zero_tail) return;
   const unsigned zw = 3 + A.tail_words;
   for (unsigned j = t0; j < (unsigned)A.count * zw; j += stride) {
     const unsigned inst = j / zw, k = j - inst * zw;
@@ -76,18 +109,18 @@ __global__ void __launch_bounds__(PACK_THREADS) cmpc_pack_records_kernel(const _
 // in: the eleven arrays of cmpc_inputs as device-accessible pointers, already offset to the first instance
 int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w, const void* r, const void* weights,
                      const void* traj, const void* alpha, const void* gait, const void* x_drag, const void* f_dist,
-                     unsigned char* records, int rec_stride, int horizon, int count, int sm_count, void* stream) {
+                     unsigned char* records, int rec_stride, int horizon, int count, int sm_count, void* stream, int which) {
   if (count <= 0) return 0;
   const int h = horizon;
   // 32-bit word indices inside the kernel: larger batches go out in pieces
   const int piece = (int)(0x7fffffffLL / (12LL * h + 64));
   if (count > piece) {
     auto adv = [&](const void* a, size_t bytes) -> const void* { return a ? static_cast<const char*>(a) + (size_t)piece * bytes : nullptr; };
-    int rc = cmpc_launch_pack(p, v, q, w, r, weights, traj, alpha, gait, x_drag, f_dist, records, rec_stride, horizon, piece, sm_count, stream);
+    int rc = cmpc_launch_pack(p, v, q, w, r, weights, traj, alpha, gait, x_drag, f_dist, records, rec_stride, horizon, piece, sm_count, stream, which);
     if (rc) return rc;
     return cmpc_launch_pack(adv(p, 12), adv(v, 12), adv(q, 16), adv(w, 12), adv(r, 48), adv(weights, 48), adv(traj, 48 * (size_t)h),
                             adv(alpha, 4), adv(gait, 4 * (size_t)h), adv(x_drag, 4), adv(f_dist, 24),
-                            records + (size_t)piece * rec_stride, rec_stride, horizon, count - piece, sm_count, stream);
+                            records + (size_t)piece * rec_stride, rec_stride, horizon, count - piece, sm_count, stream, which);
   }
   PackArgs A;
   auto set = [&](int i, const void* src, int width, int dst) {
@@ -106,18 +139,25 @@ int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w,
   set(8, alpha, 1, CMPC_REC_ALPHA);
   set(9, x_drag, 1, CMPC_REC_XDRAG);
   set(10, f_dist, 6, CMPC_REC_FDIST);  // nullptr: zeros (SolverMPC.cpp:813)
+  if (which == CMPC_PACK_REST) A.seg[0].width = 0;
+  if (which == CMPC_PACK_TRAJ)
+    for (int i = 1; i < PACK_SEGS; i++) A.seg[i].width = 0;
+  A.zero_tail = which != CMPC_PACK_TRAJ;
   A.records = reinterpret_cast<uint32_t*>(records);
   A.rec_words = rec_stride / 4;
   A.count = count;
   A.gait_words = h;
   A.tail_dst = CMPC_REC_TRAJ + 13 * h;
   A.tail_words = A.rec_words - A.tail_dst;
+  static const int vec = [] { const char* e = std::getenv("CMPC_PACK_VEC"); return e ? std::atoi(e) : 1; }();  // experiments
+  A.vec = vec;
   const long long words = (long long)count * (12 * h);
   const long long per_cta = (long long)PACK_THREADS * PACK_UNROLL;
   int grid = (int)((words + per_cta - 1) / per_cta);
   static const int grid_cap = [] { const char* e = std::getenv("CMPC_PACK_GRID"); return e ? std::atoi(e) : 0; }();  // experiments
   const int cap = grid_cap > 0 ? grid_cap : (sm_count + 7) / 8;  // few, fat CTAs (measured: profiles/r1_s4_pack_grid.txt): they have to find room beside resident solve kernels
-  if (grid > cap) grid = cap;
+  if (which == CMPC_PACK_TRAJ) { if (grid > sm_count) grid = sm_count; }  // staged in HBM: latency is short, more CTAs finish sooner
+  else if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   cmpc_pack_records_kernel<<<grid, PACK_THREADS, 0, (cudaStream_t)stream>>>(A);
   return (int)cudaGetLastError();
