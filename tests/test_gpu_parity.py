@@ -422,3 +422,23 @@ def test_tensor_core_sweep_of_the_large_shapes(built_lib):
         assert (res["status"] == ref["status"]).all()
         assert np.abs(res["forces"] - ref["forces"]).max() <= 1e-5
         assert (res["active"] == ref["active"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 7, 4097, 16389])
+def test_device_packed_inputs_match_host_packed(built_lib, B):
+    """Pinned inputs take the device-side path of the end-to-end call (csrc/cmpc_pack.cu: the copy engine stages the
+    reference trajectories, the packing kernel reads the other ten arrays over PCIe with 16-byte loads where a chunk's
+    offset allows, scalar loads elsewhere; 16389 instances are four ragged chunks whose 12-byte-per-instance arrays
+    start off a 16-byte boundary); pageable inputs are packed by the host.  Same records, so bit-identical results."""
+    h = 10
+    inst = synth.make_batch(B, horizon=h, seed=4242, spread=1.5)
+    want = solve(inst)                                   # pageable arrays: host packing
+    b = engine.Batch(B)
+    b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    b.prepare_host(inst)                                 # arrays registered: device packing
+    for rep in range(2):
+        res = b.solve_prepared()
+        for key in ("forces", "objective", "status", "iterations", "active"):
+            assert (res[key] == want[key]).all(), (rep, key)
+    b.close()
