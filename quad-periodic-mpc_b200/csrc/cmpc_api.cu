@@ -25,6 +25,9 @@ thread_local std::string g_err;
 
 int fail_cuda(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  // the failure has been reported: do not leave it in the runtime's last-error slot, where the next kernel-launch check
+  // (cudaGetLastError) would find it and blame the launch — e.g. cmpc_host_register on memory that is pinned already
+  (void)cudaGetLastError();
   return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice ||
           e == cudaErrorInvalidDeviceFunction)
              ? CMPC_E_NODEVICE

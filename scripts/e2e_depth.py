@@ -31,6 +31,15 @@ for D in depths:
             bk.wait_prepared = bk.sync
             bk.solve_prepared = lambda bk=bk: (bk.solve(), bk.sync())
         else:
+            if os.environ.get("PINNED") == "hostalloc":  # inputs in cudaHostAlloc memory instead of cudaHostRegister-ed numpy arrays
+                import torch
+                keep = []
+                for kk, v in list(sk.items()):
+                    if isinstance(v, np.ndarray):
+                        t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.uint8 if kk == "gait" else np.float32)).pin_memory()
+                        keep.append(t)
+                        sk[kk] = t.numpy()
+                bk._hostalloc_keep = keep
             bk.prepare_host(sk, want_active=False)
         pipe.append(bk)
     for k in range(3 * D):

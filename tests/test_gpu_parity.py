@@ -442,3 +442,27 @@ def test_device_packed_inputs_match_host_packed(built_lib, B):
         for key in ("forces", "objective", "status", "iterations", "active"):
             assert (res[key] == want[key]).all(), (rep, key)
     b.close()
+
+
+@pytest.mark.gpu
+def test_inputs_in_cudahostalloc_memory(built_lib):
+    """Input arrays that are pinned already (cudaHostAlloc, here through torch) cannot be registered again: the failed
+    cmpc_host_register must not poison the next kernel-launch check, and the arrays take the device-packing path."""
+    h, B = 10, 2048
+    inst = synth.make_batch(B, horizon=h, seed=77, spread=1.5)
+    want = solve(inst)
+    keep = []
+    pinned = dict(inst)
+    for k, v in inst.items():
+        if isinstance(v, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.uint8 if k == "gait" else np.float32)).pin_memory()
+            keep.append(t)
+            pinned[k] = t.numpy()
+    assert engine.lib().cmpc_host_register(pinned["traj"].ctypes.data, pinned["traj"].nbytes) != 0   # already pinned
+    b = engine.Batch(B)
+    b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    b.prepare_host(pinned)
+    res = b.solve_prepared()
+    for key in ("forces", "objective", "status", "iterations", "active"):
+        assert (res[key] == want[key]).all(), key
+    b.close()
