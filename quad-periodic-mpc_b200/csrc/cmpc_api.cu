@@ -1175,7 +1175,10 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
   nchunks = std::max(1, std::min(nchunks, kMaxChunks));
   const int direct = hb.direct;
   const SoaView& soa = hb.soa;
-  const bool zc_out = hb.zc_out;
+  // submit / wait (batches in flight): results written over PCIe by the active-set kernel's own warps hold those warps
+  // while other batches want the SMs (profiles/r1_s4_skip_pack.txt), so CMPC_SUBMIT_COPY=1 hands them to the copy engine
+  static const bool submit_copy = [] { const char* e = std::getenv("CMPC_SUBMIT_COPY"); return e && std::atoi(e) != 0; }();
+  const bool zc_out = hb.zc_out && !(submit_copy && !wait);
   void* const* vo = hb.vo;
   const int per = (count + nchunks - 1) / nchunks;
   { int rcs = sync_aux(b); if (rcs) return rcs; }
