@@ -31,10 +31,15 @@ def test_oracle_float_mode_stays_within_force_bar(golden):
     inst = golden_case(golden, "trot10")
     st = O.make_setup(inst["dt"], 10, inst["mu"], inst["f_max"])
     worst = 0.0
-    for i in range(8):
+    for i in range(len(inst["p"])):
         u = O.make_update(inst, i, 10)
-        worst = max(worst, np.abs(O.solve(st, u, use_float=True)["x"] - O.solve(st, u)["x"]).max())
-    assert worst < 5e-3, worst
+        r32, r64 = O.solve(st, u, use_float=True), O.solve(st, u)
+        worst = max(worst, np.abs(r32["x"] - r64["x"]).max())
+        # no constraint flips between the two arithmetics
+        keep = N.contact_vars(inst["gait"][i], 10)
+        assert (N.active_mask(r32["x"][keep], inst["mu"], inst["f_max"]) ==
+                N.active_mask(r64["x"][keep], inst["mu"], inst["f_max"])).all()
+    assert worst < 1e-3, worst     # measured 7.6e-4 N over the 24 golden trot instances
 
 
 @needs_ref
