@@ -43,8 +43,10 @@ enum {
   CMPC_ST_INFEASIBLE = 3, /* cannot happen for this constraint set; kept for diagnostics */
   CMPC_ST_WSOVERFLOW = 4, /* working set outgrew the launch's capacity tier; the engine re-solves
                              these with the full-capacity kernel before returning */
-  CMPC_ST_CAPACITY = 5    /* instance has more contact foot-steps than the launch was sized for
+  CMPC_ST_CAPACITY = 5,   /* instance has more contact foot-steps than the launch was sized for
                              (only reachable through cmpc_batch_set_count with a wrong bound) */
+  CMPC_ST_NONFINITE = 6   /* NaN / Inf in the inputs, the disturbance estimate or the iterate: the forces of this
+                             instance are all zero and must not be used (qpOASES would return garbage here) */
 };
 
 /* ------------------------------------------------------------------------
@@ -65,7 +67,8 @@ double get_solution(int index);
  * active-set optimum that the use_jcqp == 0 (qpOASES) branch computes. */
 void update_solver_settings(int max_iter, double rho, double sigma, double solver_alpha, double terminate,
                             double use_jcqp);
-/* convexMPC_interface.h:52 / convexMPC_interface.cpp:151 */
+/* convexMPC_interface.h:52 / convexMPC_interface.cpp:151.  The reference declares this one WITHOUT extern "C", so an
+ * unmodified reference translation unit looks for the C++ symbol _Z13update_x_dragf: the library exports both. */
 void update_x_drag(float x_drag);
 /* The reference hands the adaptive hook its inputs through two globals,
  * `Eigen::Matrix<float,6,1> f_ext` (convexMPC_interface.h:54, written at
@@ -76,6 +79,19 @@ void cmpc_set_external_force(const float f_ext[6]);
 void cmpc_set_simulation_time(float t);
 /* f_est after the last solve (SolverMPC.h:76 `extern f_est`) */
 void cmpc_get_disturbance_estimate(float f_est[6]);
+/* the two filtered estimates solve_mpc keeps next to it (SolverMPC.h:73-74):
+ * f_est_smoothed = 0.95 f_est_smoothed + 0.05 f_est (SolverMPC.cpp:783), f_est_static[3] = 0.97 f_est_static[3] +
+ * 0.03 f_ext[3] (SolverMPC.cpp:798), both updated once per solve */
+void cmpc_get_disturbance_estimate_smoothed(float f_est_smoothed[6]);
+void cmpc_get_disturbance_estimate_static(float f_est_static[6]);
+/* What the reference interface does when a solve does not end in CMPC_ST_SOLVED / CMPC_ST_EMPTY or returns non-finite
+ * forces (the reference prints "failed to solve!" and hands the controller whatever qpOASES left in memory):
+ * CMPC_ON_ERROR_ABORT (default) prints the reason and aborts the process — a controller must not run on garbage;
+ * CMPC_ON_ERROR_HOLD keeps the forces of the last good solve for get_solution() and records the status. */
+enum { CMPC_ON_ERROR_ABORT = 0, CMPC_ON_ERROR_HOLD = 1 };
+void cmpc_set_error_policy(int policy);
+/* CMPC_ST_* of the last update_problem_data* call */
+int cmpc_last_status(void);
 /* Forget the accumulated f_ext / time history (the reference's file-scope vectors, SolverMPC.cpp:398-399,
  * live for the life of the process; a test or a controller restart needs a way to clear them). */
 void cmpc_reset_history(void);
@@ -119,6 +135,10 @@ void cmpc_batch_destroy(cmpc_batch* b);
  * reference's hard-coded 12 kg and diag(.07,.26,.242) (RobotState.h:24, RobotState.cpp:49). */
 int cmpc_batch_setup(cmpc_batch* b, double dt, int horizon, double mu, double f_max);
 int cmpc_batch_set_robot(cmpc_batch* b, double mass, const double inertia_diag[3]);
+/* Diagnostic / test switches (which kernel path, capacity tiers, stream count ...; the keys are listed next to
+ * cmpc_batch_set_option in csrc/cmpc_api.cu).  The library reads NO environment variable on any solve path: a
+ * switch exists only through this call.  Drains the batch and drops its cached launch plans. */
+int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value);
 /* Pack `count` host instances into pinned records and copy them to the device (async on the batch stream). */
 int cmpc_batch_upload(cmpc_batch* b, int count, const cmpc_inputs* in);
 /* Launch the fused condensation + QP kernel over the uploaded instances (async). */
@@ -210,7 +230,10 @@ typedef struct {
 /* Q and alpha of solveDenseMPC (:627, :634); defaults are the reference's hard-coded values. */
 int cmpc_batch_set_weights(cmpc_batch* b, const float weights[12], float alpha);
 /* One MPC update of `count` robots from host command structs (any host memory; pinned is faster).
- * forces_out may be NULL; when given it receives the full q_soln [count][12*horizon] as well. */
+ * forces_out may be NULL; when given it receives the full q_soln [count][12*horizon] as well.
+ * Instance slot i is robot i for as long as the disturbance histories live: the sample count is kept per batch (the
+ * reference keeps one history per process), so every call between two cmpc_batch_reset_history calls must pass the
+ * same `count` (CMPC_E_STATE otherwise). */
 int cmpc_batch_solve_commands(cmpc_batch* b, int count, const cmpc_command* commands, cmpc_command_result* results,
                               double* forces_out);
 /* Forget the per-instance disturbance histories, estimates and f_ext (the reference's file-scope vectors). */

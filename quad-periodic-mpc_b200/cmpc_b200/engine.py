@@ -11,7 +11,22 @@ import numpy as np
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("CMPC_LIB") or os.path.join(_PKG, "libcmpc_b200.so")  # CMPC_LIB: experiment builds
 
-ST_SOLVED, ST_EMPTY, ST_MAXITER, ST_INFEASIBLE, ST_WSOVERFLOW, ST_CAPACITY = range(6)
+ST_SOLVED, ST_EMPTY, ST_MAXITER, ST_INFEASIBLE, ST_WSOVERFLOW, ST_CAPACITY, ST_NONFINITE = range(7)
+ON_ERROR_ABORT, ON_ERROR_HOLD = 0, 1
+
+# The library reads no environment variable on a solve path; its diagnostic / test switches exist only through
+# cmpc_batch_set_option.  For the scripts and tests that select kernel paths from the shell, THIS test-side binding
+# maps the historical variable names onto options when a Batch is created.
+_ENV_OPTIONS = {
+    "CMPC_NSTREAMS": ("nstreams", int), "CMPC_SPLIT": ("split", int), "CMPC_SERIAL": ("serial", int),
+    "CMPC_LPT": ("lpt", int), "CMPC_RESUME": ("resume", int), "CMPC_INV_STAGGER": ("inv_stagger", int),
+    "CMPC_TRAJ_COPY": ("traj_copy", int), "CMPC_CSHAPE": ("cshape", int), "CMPC_WS_MB": ("ws_mb", int),
+    "CMPC_QCAP1": ("qcap1", int), "CMPC_WPC": ("wpc", int), "CMPC_NO_MID_TIER": ("no_mid_tier", lambda v: 1),
+    "CMPC_SHAPE": ("shape", int), "CMPC_HOST_PACK": ("host_pack", int), "CMPC_D2H_COPY": ("d2h_copy", int),
+    "CMPC_CHUNKS": ("chunks", int), "CMPC_SUBMIT_COPY": ("submit_copy", int), "CMPC_HOST_THREADS": ("host_threads", int),
+    "CMPC_PATH": ("path_fused", lambda v: int(v == "fused")), "CMPC_DUAL": ("dual_generic", lambda v: int(v == "generic")),
+    "CMPC_SWEEP": ("sweep_dmma", lambda v: int(v == "dmma")), "CMPC_EXP_SKIP_PACK": ("exp_skip_pack", lambda v: 1),
+}
 
 
 class Inputs(C.Structure):
@@ -55,6 +70,7 @@ def lib():
         L.cmpc_batch_destroy.argtypes = [C.c_void_p]
         L.cmpc_batch_setup.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double]
         L.cmpc_batch_set_robot.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+        L.cmpc_batch_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.cmpc_batch_upload.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs)]
         L.cmpc_batch_solve.argtypes = [C.c_void_p]
         L.cmpc_batch_sync.argtypes = [C.c_void_p]
@@ -99,6 +115,9 @@ def lib():
         L.cmpc_set_external_force.argtypes = [C.c_void_p]
         L.cmpc_set_simulation_time.argtypes = [C.c_float]
         L.cmpc_get_disturbance_estimate.argtypes = [C.c_void_p]
+        L.cmpc_get_disturbance_estimate_smoothed.argtypes = [C.c_void_p]
+        L.cmpc_get_disturbance_estimate_static.argtypes = [C.c_void_p]
+        L.cmpc_set_error_policy.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -121,13 +140,21 @@ def _ptr(a):
 class Batch:
     """Batched engine handle; mirrors setup_problem / update_problem_data / get_solution for many instances."""
 
-    def __init__(self, capacity, device=0):
+    def __init__(self, capacity, device=0, options=None):
         self._h = C.c_void_p()
         self.capacity = capacity
         _check(lib().cmpc_batch_create(C.byref(self._h), device, capacity), "cmpc_batch_create")
         self.horizon = 0
         self.count = 0
         self._keep = None
+        for env, (key, conv) in _ENV_OPTIONS.items():
+            if env in os.environ:
+                self.set_option(key, conv(os.environ[env]))
+        for key, value in (options or {}).items():
+            self.set_option(key, value)
+
+    def set_option(self, key, value):
+        _check(lib().cmpc_batch_set_option(self._h, key.encode(), int(value)), "cmpc_batch_set_option(%s)" % key)
 
     def close(self):
         if self._h:

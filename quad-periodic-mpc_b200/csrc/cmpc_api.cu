@@ -210,8 +210,26 @@ struct HostBinding {
 
 }  // namespace
 
+// Diagnostic / test switches of a batch (cmpc_batch_set_option).  Nothing here is read from the environment.
+struct Knobs {
+  int cshape = -1;        // "cshape": force a condensation shape that still fits (CMPC_CSHAPE_*)
+  int ws_mb = 160;        // "ws_mb": workspace budget of one pipeline chunk
+  int qcap1 = 0;          // "qcap1": first-tier working-set capacity (0: 32 / 24 by mode)
+  int dual_generic = 0;   // "dual_generic": first tier on the any-capacity kernel
+  int wpc = 4;            // "wpc": warps per CTA of the any-capacity kernel's first tier
+  int no_mid_tier = 0;    // "no_mid_tier"
+  int path_fused = 0;     // "path_fused": single-kernel path for every size
+  int shape = -1;         // "shape": kernel shape of the single-kernel path (CMPC_SHAPE_*)
+  int host_pack = 0;      // "host_pack": pack records on the host even when the inputs are pinned
+  int d2h_copy = 0;       // "d2h_copy": device-side outputs + copy engine instead of zero-copy stores
+  int chunks = 0;         // "chunks": chunks of the end-to-end call (0: by size)
+  int submit_copy = 0;    // "submit_copy": submit / wait hand the results to the copy engine
+  int host_threads = 0;   // "host_threads": host workers of the end-to-end call (0: hardware)
+};
+
 struct cmpc_batch {
   int device = 0;
+  Knobs knobs;
   int capacity = 0;
   int sm_count = 0;
   cudaStream_t stream[kMaxStreams] = {};  // [0] is "the batch stream"; the others only carry pipelined chunks / solves
@@ -224,7 +242,11 @@ struct cmpc_batch {
   cudaEvent_t traj_copied[kMaxChunks] = {};
   float* d_traj_stage = nullptr;          // ... here, while the packing kernel reads the ten small arrays over PCIe itself
   bool traj_copy = true;                  // CMPC_TRAJ_COPY=0: the packing kernel reads every array itself
-  bool exp_packed_once = false;           // CMPC_EXP_SKIP_PACK (experiments): the records of the first call are reused
+#ifdef CMPC_EXPERIMENTS
+  bool exp_skip_pack = false, exp_packed_once = false;  // "exp_skip_pack": the records of the first call are reused
+#endif
+  cudaEvent_t rec_copied = nullptr;       // the last copy out of the pinned record staging (h_rec) has finished
+  bool rec_copy_pending = false;
   // successive solve_range calls rotate through the streams so that the latency-bound tails of a batch's kernels
   // overlap the kernels of the following batches; these events carry the cross-stream ordering
   cudaEvent_t join_ev = nullptr;      // scratch: "stream i has reached this point"
@@ -291,6 +313,7 @@ struct cmpc_batch {
   unsigned char* d_results = nullptr;  // [capacity] cmpc_command_result
   float* d_fext = nullptr;             // [capacity][6] the reference's global f_ext, per instance
   int hist_len = 0;                    // samples pushed into the disturbance histories (time_history.size())
+  int hist_count = 0;                  // instances those histories were built for
   float weights[12] = {0.25f, 0.25f, 10.f, 10.f, 2.f, 50.f, 0.f, 0.f, 0.3f, 0.2f, 0.2f, 0.1f};  // ConvexMPCLocomotion.cpp:627
   float alpha = 4e-5f;                 // :634
   // pinned result staging
@@ -356,7 +379,7 @@ int pack_records(cmpc_batch* b, const cmpc_inputs* in, int first, int count) {
 HostPool* host_pool(cmpc_batch* b) {
   if (!b->pool) {
     int workers = (int)std::thread::hardware_concurrency() - 1;
-    if (const char* e = std::getenv("CMPC_HOST_THREADS")) workers = std::atoi(e) - 1;
+    if (b->knobs.host_threads > 0) workers = b->knobs.host_threads - 1;
     b->pool = new HostPool(std::max(0, std::min(workers, 7)));
   }
   return b->pool;
@@ -449,6 +472,13 @@ int check_inputs(const cmpc_batch* b, int count, const cmpc_inputs* in, const ch
   return CMPC_OK;
 }
 
+// the host waits until the last asynchronous copy out of the pinned record staging has run
+int wait_rec_staging(cmpc_batch* b) {
+  if (!b->rec_copy_pending) return CMPC_OK;
+  CK(cudaEventSynchronize(b->rec_copied));
+  b->rec_copy_pending = false;
+  return CMPC_OK;
+}
 // stream 0 ("the batch stream") waits for everything enqueued on stream 1 so far
 int join_streams(cmpc_batch* b) {
   for (int i = 1; i < kMaxStreams; i++) {
@@ -484,22 +514,21 @@ int fork_streams(cmpc_batch* b, int only = -1) {
 // Two-kernel pipeline (cmpc_pipeline.cu) over the instances P describes, in chunks whose workspace stays
 // L2-sized: condensation + K = H^-1 (one CTA per instance), then the dual active set (one warp per
 // instance) with a small working-set capacity, then the few instances that outgrew it at full capacity.
-int make_pipe_plan(const CmpcParams& P, int qcap_pref, PipePlan& pl) {
+int make_pipe_plan(const Knobs& kn, const CmpcParams& P, int qcap_pref, PipePlan& pl) {
   const bool adapt = P.adapt_mode >= 0;
   const int nmax = P.nmax;
   pl.nmax = nmax;
   pl.h = P.horizon;
   pl.adapt = adapt;
   int cshape = nmax < 64 ? CMPC_CSHAPE_MMA64 : (nmax <= 96 ? CMPC_CSHAPE_96 : CMPC_CSHAPE_128);
-  if (const char* e = std::getenv("CMPC_CSHAPE")) {  // experiments: force a shape that still fits
-    const int sh = std::atoi(e);
+  if (kn.cshape >= 0) {  // forced shape, if it still fits
+    const int sh = kn.cshape;
     if ((sh == CMPC_CSHAPE_64 && nmax <= 64) || (sh == CMPC_CSHAPE_96 && nmax <= 96) || sh == CMPC_CSHAPE_128) cshape = sh;
   }
   pl.cshape = cshape;
   pl.tiled = (cshape == CMPC_CSHAPE_MMA64) ? 1 : 0;
   pl.slot = cmpc_qws_slot_doubles(nmax, pl.tiled);
-  size_t budget = 160;
-  if (const char* e = std::getenv("CMPC_WS_MB")) budget = (size_t)std::max(1, std::atoi(e));
+  size_t budget = (size_t)std::max(1, kn.ws_mb);
   budget <<= 20;
   pl.chunk_cap = (int)std::max<size_t>(1, budget / (pl.slot * sizeof(double)));
   // kernel 1
@@ -515,17 +544,14 @@ int make_pipe_plan(const CmpcParams& P, int qcap_pref, PipePlan& pl) {
     return CMPC_E_NODEVICE;
   }
   // kernel 2, two working-set capacity tiers
-  int qcap1 = qcap_pref;
-  if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
+  int qcap1 = kn.qcap1 > 0 ? kn.qcap1 : qcap_pref;
   if (qcap1 < 1 || qcap1 > nmax) qcap1 = nmax;
-  bool fast = qcap1 <= 32;  // tier 1 on the register-resident kernel (cmpc_dual_fast.cuh)
-  if (const char* e = std::getenv("CMPC_DUAL")) fast = fast && std::strcmp(e, "generic") != 0;
+  bool fast = qcap1 <= 32 && !kn.dual_generic;  // tier 1 on the register-resident kernel (cmpc_dual_fast.cuh)
   if (fast) {
     pl.per_sm_fast = cmpc_dual_fast_max_ctas_per_sm(nmax, cmpc_dual_fast_smem_bytes(nmax, qcap1));
     if (pl.per_sm_fast < 1) fast = false;
   }
-  int wpc1 = 4;
-  if (const char* e = std::getenv("CMPC_WPC")) wpc1 = std::atoi(e);
+  int wpc1 = kn.wpc;
   if (wpc1 != 1 && wpc1 != 2 && wpc1 != 4 && wpc1 != 8) wpc1 = 4;
   const size_t smax = 227 * 1024;
   while (wpc1 > 1 && cmpc_dual_smem_bytes_per_warp(nmax, qcap1) * wpc1 > smax) wpc1 >>= 1;
@@ -539,7 +565,7 @@ int make_pipe_plan(const CmpcParams& P, int qcap_pref, PipePlan& pl) {
   }
   // a middle tier for the larger reduced problems: at full capacity one warp's K N and P fill an SM's shared memory
   pl.qcap_mid = 0;
-  if (nmax > 64 && qcap1 < CMPC_QCAP_MID && !std::getenv("CMPC_NO_MID_TIER")) {
+  if (nmax > 64 && qcap1 < CMPC_QCAP_MID && !kn.no_mid_tier) {
     int wm = 4;
     while (wm > 1 && cmpc_dual_smem_bytes_per_warp(nmax, CMPC_QCAP_MID) * wm > 100 * 1024) wm >>= 1;
     const int pm = cmpc_dual_max_ctas_per_sm(wm, cmpc_dual_smem_bytes_per_warp(nmax, CMPC_QCAP_MID) * wm);
@@ -570,7 +596,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
   if (!plp) {
     PipePlan pl;
     pl.qcap_pref = qcap_pref;
-    if (int e = make_pipe_plan(P, qcap_pref, pl)) return e;
+    if (int e = make_pipe_plan(b->knobs, P, qcap_pref, pl)) return e;
     b->plans.push_back(pl);
     plp = &b->plans.back();
   }
@@ -789,23 +815,18 @@ int launch_range(cmpc_batch* b, int first, int count, int max_contact, int si) {
   }
   // reduced problems of up to 128 variables take the two-kernel pipeline; CMPC_PATH=fused forces the
   // single-kernel path below (kept for larger problems and for A/B measurements)
-  {
-    const char* e = std::getenv("CMPC_PATH");
-    const bool fused = e && std::strcmp(e, "fused") == 0;
-    if (P.nmax <= CMPC_PIPELINE_NMAX && !fused) return launch_pipeline(b, P, count, si);
-  }
-  // kernel shape by reduced problem size; CMPC_SHAPE overrides (0..3) for experiments
+  if (P.nmax <= CMPC_PIPELINE_NMAX && !b->knobs.path_fused) return launch_pipeline(b, P, count, si);
+  // kernel shape by reduced problem size; the "shape" option overrides (0..3)
   int shape = P.nmax <= 64 ? CMPC_SHAPE_64W : (P.nmax <= 128 ? CMPC_SHAPE_128 : CMPC_SHAPE_MEM);
-  if (const char* e = std::getenv("CMPC_SHAPE")) {
-    int sh = std::atoi(e);
+  if (b->knobs.shape >= 0) {
+    int sh = b->knobs.shape;
     if (sh == CMPC_SHAPE_MEM || (sh == CMPC_SHAPE_128 && P.nmax <= 128) ||
         ((sh == CMPC_SHAPE_64 || sh == CMPC_SHAPE_64W) && P.nmax <= 64))
       shape = sh;
   }
   // two working-set capacity tiers: a small first tier keeps shared memory (and so occupancy) low;
   // the few instances that outgrow it are re-solved from scratch by a full-capacity launch
-  int qcap1 = 32;
-  if (const char* e = std::getenv("CMPC_QCAP1")) qcap1 = std::atoi(e);
+  int qcap1 = b->knobs.qcap1 > 0 ? b->knobs.qcap1 : 32;
   if (qcap1 < 1 || qcap1 > P.nmax) qcap1 = P.nmax;
   for (int tier = 0; tier < 2; tier++) {
     if (tier == 0) {
@@ -879,8 +900,11 @@ int cmpc_device_count(void) {
   return n;
 }
 
+static int batch_create_impl(cmpc_batch* b, int device, int capacity);
+
 int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   if (!out || capacity < 1) return fail_arg("cmpc_batch_create: bad arguments");
+  *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -890,14 +914,25 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   if (device < 0 || device >= ndev) return fail_arg("cmpc_batch_create: device out of range");
   CK(cudaSetDevice(device));
   cmpc_batch* b = new cmpc_batch();
+  const int rc = batch_create_impl(b, device, capacity);
+  if (rc != CMPC_OK) {  // release whatever was allocated before the failure (destroy tolerates the nulls)
+    const std::string why = g_err;
+    cmpc_batch_destroy(b);
+    (void)cudaGetLastError();
+    g_err = why;
+    return rc;
+  }
+  *out = b;
+  return CMPC_OK;
+}
+
+static int batch_create_impl(cmpc_batch* b, int device, int capacity) {
   b->device = device;
   b->capacity = capacity;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   b->sm_count = prop.multiProcessorCount;
   for (int i = 0; i < kMaxStreams; i++) CK(cudaStreamCreateWithFlags(&b->stream[i], cudaStreamNonBlocking));
-  if (const char* e = std::getenv("CMPC_NSTREAMS")) b->nstreams = std::max(1, std::min(kMaxStreams, std::atoi(e)));
-  if (const char* e = std::getenv("CMPC_SPLIT")) b->split = std::max(1, std::min(kMaxStreams, std::atoi(e)));
   CK(cudaEventCreate(&b->ev0));
   CK(cudaEventCreate(&b->ev1));
   CK(cudaEventCreate(&b->mark0));
@@ -906,7 +941,7 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->packed[i], cudaEventDisableTiming));
   for (int i = 0; i < kMaxChunks; i++) CK(cudaEventCreateWithFlags(&b->traj_copied[i], cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
-  if (const char* e = std::getenv("CMPC_TRAJ_COPY")) b->traj_copy = std::atoi(e) != 0;
+  CK(cudaEventCreateWithFlags(&b->rec_copied, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&b->join_ev, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming));
   const size_t cap = (size_t)capacity;
@@ -914,7 +949,7 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   const size_t rec_max = (size_t)cmpc_rec_stride(hm);
   CK(cudaMallocHost(&b->h_rec, cap * rec_max));
   CK(cudaMalloc(&b->d_rec, cap * rec_max));
-  if (b->traj_copy) CK(cudaMalloc(&b->d_traj_stage, sizeof(float) * cap * 12 * hm));
+  CK(cudaMalloc(&b->d_traj_stage, sizeof(float) * cap * 12 * hm));
   CK(cudaMalloc(&b->d_sigma, sizeof(double) * CMPC_SIG_COUNT * hm * hm));
   CK(cudaMalloc(&b->d_forces, sizeof(double) * cap * 12 * hm));
   CK(cudaMalloc(&b->d_obj, sizeof(double) * cap));
@@ -923,7 +958,6 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMalloc(&b->d_active, cap * 20 * hm));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow[i], sizeof(int) * (cap + 1)));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_lpt[i], sizeof(int) * 2 * cap));
-  if (const char* e = std::getenv("CMPC_INV_STAGGER")) b->inv_stagger = std::max(0, std::atoi(e));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume[i], sizeof(int) * CMPC_RESUME_INTS * cap));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_overflow2[i], sizeof(int) * (cap + 1)));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_resume2[i], sizeof(int) * CMPC_RESUME_INTS * cap));
@@ -931,9 +965,6 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   b->rstate2_cap = (int)std::min<size_t>(cap, std::max<size_t>(256, cap / 16));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_rstate[i], sizeof(double) * kRstateStride * (size_t)b->rstate_cap));
   for (int i = 0; i < kMaxStreams; i++) CK(cudaMalloc(&b->d_rstate2[i], sizeof(double) * kRstate2Stride * (size_t)b->rstate2_cap));
-  if (const char* e = std::getenv("CMPC_RESUME")) b->resume = std::atoi(e) != 0;
-  if (const char* e = std::getenv("CMPC_LPT")) b->lpt = std::atoi(e) != 0;
-  if (const char* e = std::getenv("CMPC_SWEEP")) b->sweep_dmma = std::strcmp(e, "dmma") == 0;
   CK(cudaMalloc(&b->d_flops, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMemset(b->d_flops, 0, sizeof(unsigned long long) * CMPC_K_COUNT));
   CK(cudaMallocHost(&b->h_forces, sizeof(double) * cap * 12 * hm));
@@ -943,15 +974,13 @@ int cmpc_batch_create(cmpc_batch** out, int device, int capacity) {
   CK(cudaMallocHost(&b->h_active, cap * 20 * hm));
   CK(cudaMallocHost(&b->h_flops, sizeof(unsigned long long) * CMPC_K_COUNT));
   for (int i = 0; i < CMPC_K_COUNT; i++) b->h_flops[i] = 0;
-  if (const char* e = std::getenv("CMPC_SERIAL")) b->serial = std::atoi(e) != 0;
-  *out = b;
   return CMPC_OK;
 }
 
 void cmpc_batch_destroy(cmpc_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  for (int i = 0; i < kMaxStreams; i++) cudaStreamSynchronize(b->stream[i]);
+  for (int i = 0; i < kMaxStreams; i++) if (b->stream[i]) cudaStreamSynchronize(b->stream[i]);
   cudaFreeHost(b->h_rec); cudaFree(b->d_rec); cudaFree(b->d_sigma); cudaFree(b->d_forces); cudaFree(b->d_obj);
   cudaFree(b->d_status); cudaFree(b->d_iters); cudaFree(b->d_active); cudaFree(b->d_flops); cudaFree(b->d_phase);
   cudaFree(b->d_gws);
@@ -968,8 +997,9 @@ void cmpc_batch_destroy(cmpc_batch* b) {
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   cudaFree(b->d_traj_stage);
   for (int i = 0; i < CMPC_K_COUNT + 1; i++) if (b->prof_ev[i]) cudaEventDestroy(b->prof_ev[i]);
-  cudaEventDestroy(b->join_ev); cudaEventDestroy(b->fork_ev);
+  cudaEventDestroy(b->join_ev); cudaEventDestroy(b->fork_ev); cudaEventDestroy(b->rec_copied);
   for (int i = 0; i < kMaxStreams; i++) cudaStreamDestroy(b->stream[i]);
+  (void)cudaGetLastError();  // handles that were never created (a create that failed half way)
   delete b->pool;
   delete b;
 }
@@ -1010,11 +1040,17 @@ int cmpc_batch_upload(cmpc_batch* b, int count, const cmpc_inputs* in) {
   int rc = check_inputs(b, count, in, "cmpc_batch_upload");
   if (rc) return rc;
   CK(cudaSetDevice(b->device));
+  // the previous copy out of the pinned staging may still be queued behind solves: the host must not overwrite
+  // the staging before it has run
+  { int rcw = wait_rec_staging(b); if (rcw) return rcw; }
   b->max_contact = pack_records(b, in, 0, count);
   b->count = count;
   { int rcj = join_streams(b); if (rcj) return rcj; }  // solves in flight on stream 1 still read the records
-  if (count > 0)
+  if (count > 0) {
     CK(cudaMemcpyAsync(b->d_rec, b->h_rec, (size_t)count * b->rec_stride, cudaMemcpyHostToDevice, b->stream[0]));
+    CK(cudaEventRecord(b->rec_copied, b->stream[0]));
+    b->rec_copy_pending = true;
+  }
   return CMPC_OK;
 }
 
@@ -1139,9 +1175,8 @@ static int resolve_binding(cmpc_batch* b, const cmpc_inputs* in, const cmpc_outp
   hb.direct = direct_mask(out);
   // pinned input arrays are read by the device itself (cmpc_pack.cu); pageable ones are packed into pinned records on the host
   hb.soa = soa_view(in);
-  if (const char* e = std::getenv("CMPC_HOST_PACK")) hb.soa.ok = hb.soa.ok && std::atoi(e) == 0;
-  hb.zc_out = true;
-  if (const char* e = std::getenv("CMPC_D2H_COPY")) hb.zc_out = std::atoi(e) == 0;
+  if (b->knobs.host_pack) hb.soa.ok = false;
+  hb.zc_out = !b->knobs.d2h_copy;
   for (int i = 0; i < 5; i++) hb.vo[i] = nullptr;
   if (hb.zc_out) {
     auto view = [&](void* user, void* staging, int bit) -> void* {
@@ -1159,7 +1194,11 @@ static int resolve_binding(cmpc_batch* b, const cmpc_inputs* in, const cmpc_outp
 }
 
 static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool wait = true) {
+#ifdef CMPC_EXPERIMENTS
   static const bool trace = std::getenv("CMPC_TRACE") != nullptr;
+#else
+  constexpr bool trace = false;
+#endif
   static double tr_enq = 0, tr_wait = 0, tr_scan = 0, tr_pack = 0, tr_pipe = 0;
   static cudaEvent_t tr_ev[2 * kMaxChunks] = {};
   static int tr_n = 0;
@@ -1170,15 +1209,14 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
   b->throughput_mode = false;
   CK(cudaSetDevice(b->device));
   int nchunks = 1;
-  if (const char* e = std::getenv("CMPC_CHUNKS")) nchunks = std::atoi(e);
+  if (b->knobs.chunks > 0) nchunks = b->knobs.chunks;
   else nchunks = std::max(1, std::min(4, count / 4096));  // measured (scripts/e2e_chunks.py): one chunk up to 8191, four from 16384
   nchunks = std::max(1, std::min(nchunks, kMaxChunks));
   const int direct = hb.direct;
   const SoaView& soa = hb.soa;
   // submit / wait (batches in flight): results written over PCIe by the active-set kernel's own warps hold those warps
   // while other batches want the SMs (profiles/r1_s4_skip_pack.txt), so CMPC_SUBMIT_COPY=1 hands them to the copy engine
-  static const bool submit_copy = [] { const char* e = std::getenv("CMPC_SUBMIT_COPY"); return e && std::atoi(e) != 0; }();
-  const bool zc_out = hb.zc_out && !(submit_copy && !wait);
+  const bool zc_out = hb.zc_out && !(b->knobs.submit_copy && !wait);
   void* const* vo = hb.vo;
   const int per = (count + nchunks - 1) / nchunks;
   { int rcs = sync_aux(b); if (rcs) return rcs; }
@@ -1200,10 +1238,13 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
     // The reference trajectories are 71 % of the input bytes: the copy engine moves them (52 GB/s against ~35 GB/s for
     // loads issued by SMs, scripts/pcie_copy_rate.py) while the packing kernel reads the ten small arrays over PCIe
     // itself; a second launch then scatters the staged trajectories from HBM.
-    // experiments only (scripts/e2e_depth.py): reuse the records of the previous call, to tell the cost of the input side
-    static const bool skip_pack_exp = std::getenv("CMPC_EXP_SKIP_PACK") != nullptr;
-    const bool skip_pack = skip_pack_exp && b->exp_packed_once;
+#ifdef CMPC_EXPERIMENTS
+    // experiments build only (scripts/e2e_depth.py): reuse the records of the previous call, to tell the cost of the input side
+    const bool skip_pack = b->exp_skip_pack && b->exp_packed_once;
     b->exp_packed_once = true;
+#else
+    constexpr bool skip_pack = false;
+#endif
     const bool tcopy = !skip_pack && b->traj_copy && b->d_traj_stage && soa.p[6];
     if (tcopy) {
       CK(cudaStreamWaitEvent(b->copy_stream, b->ev0, 0));
@@ -1263,9 +1304,12 @@ static int solve_host_core(cmpc_batch* b, int count, const HostBinding& hb, bool
       maxc = chunk_maxc[c];
       CK(cudaStreamWaitEvent(st, b->packed[c], 0));
     } else {
+      if (c == 0) { int rcw = wait_rec_staging(b); if (rcw) return rcw; }  // an earlier upload may still be reading the staging
       maxc = pack_records_parallel(b, in, first, n);
       CK(cudaMemcpyAsync(b->d_rec + (size_t)first * b->rec_stride, b->h_rec + (size_t)first * b->rec_stride,
                          (size_t)n * b->rec_stride, cudaMemcpyHostToDevice, st));
+      CK(cudaEventRecord(b->rec_copied, st));
+      b->rec_copy_pending = true;
     }
     maxc_all = std::max(maxc_all, maxc);
     // the staged, word-wide output stores live in the pipeline's active-set kernel (reduced problems of up to 128
@@ -1351,6 +1395,52 @@ int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_output
   if (!out) return fail_arg("cmpc_batch_bind_host: null outputs");
   CK(cudaSetDevice(b->device));
   return resolve_binding(b, in, out, b->bound);
+}
+
+// Diagnostic / test switches.  Keys: nstreams, split, serial, lpt, resume, sweep_dmma, inv_stagger, traj_copy, cshape,
+// ws_mb, qcap1, dual_generic, wpc, no_mid_tier, path_fused, shape, host_pack, d2h_copy, chunks, submit_copy,
+// host_threads (and exp_skip_pack in a -DCMPC_EXPERIMENTS build).
+int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
+  if (!b || !key) return fail_arg("cmpc_batch_set_option: null argument");
+  CK(cudaSetDevice(b->device));
+  { int rcs = sync_all(b); if (rcs) return rcs; }
+  const std::string k(key);
+  Knobs& kn = b->knobs;
+  if (k == "nstreams") b->nstreams = std::max(1, std::min(kMaxStreams, value));
+  else if (k == "split") b->split = std::max(1, std::min(kMaxStreams, value));
+  else if (k == "serial") b->serial = value != 0;
+  else if (k == "lpt") b->lpt = value != 0;
+  else if (k == "resume") b->resume = value != 0;
+  else if (k == "sweep_dmma") b->sweep_dmma = value != 0;
+  else if (k == "inv_stagger") b->inv_stagger = std::max(0, value);
+  else if (k == "traj_copy") b->traj_copy = value != 0;
+  else if (k == "cshape") kn.cshape = value;
+  else if (k == "ws_mb") kn.ws_mb = std::max(1, value);
+  else if (k == "qcap1") kn.qcap1 = std::max(0, value);
+  else if (k == "dual_generic") kn.dual_generic = value != 0;
+  else if (k == "wpc") kn.wpc = value;
+  else if (k == "no_mid_tier") kn.no_mid_tier = value != 0;
+  else if (k == "path_fused") kn.path_fused = value != 0;
+  else if (k == "shape") kn.shape = value;
+  else if (k == "host_pack") kn.host_pack = value != 0;
+  else if (k == "d2h_copy") kn.d2h_copy = value != 0;
+  else if (k == "chunks") kn.chunks = std::max(0, value);
+  else if (k == "submit_copy") kn.submit_copy = value != 0;
+  else if (k == "host_threads") kn.host_threads = std::max(0, value);
+#ifdef CMPC_EXPERIMENTS
+  else if (k == "exp_skip_pack") b->exp_skip_pack = value != 0;
+#endif
+  else {
+    g_err = "cmpc_batch_set_option: unknown key '" + k + "'";
+    return CMPC_E_ARG;
+  }
+  b->plans.clear();
+  if (b->bound.valid) {  // the binding caches host_pack / d2h_copy
+    HostBinding hb = b->bound;
+    int rc = resolve_binding(b, &hb.in, &hb.out, b->bound);
+    if (rc) return rc;
+  }
+  return CMPC_OK;
 }
 
 int cmpc_batch_submit_bound(cmpc_batch* b, int count) {
@@ -1491,6 +1581,12 @@ int cmpc_batch_solve_commands(cmpc_batch* b, int count, const cmpc_command* comm
   }
   { int rca = ensure_adapt_buffers(b); if (rca) return rca; }
   if (count == 0) return CMPC_OK;
+  if (b->hist_len > 0 && count != b->hist_count) {
+    g_err = "cmpc_batch_solve_commands: count differs from the count the disturbance histories were built with "
+            "(one sample counter per batch); call cmpc_batch_reset_history first";
+    return CMPC_E_STATE;
+  }
+  b->hist_count = count;
   cudaStream_t st = b->stream[0];
   const int h = b->h;
   CK(cudaEventRecord(b->ev0, st));
@@ -1536,6 +1632,7 @@ int cmpc_batch_reset_history(cmpc_batch* b) {
   CK(cudaSetDevice(b->device));
   { int rcs = sync_all(b); if (rcs) return rcs; }
   b->hist_len = 0;
+  b->hist_count = 0;
   b->adapt_mode = -1;
   const size_t cap = (size_t)b->capacity;
   if (b->d_fext) CK(cudaMemset(b->d_fext, 0, cap * 6 * sizeof(float)));
@@ -1739,9 +1836,13 @@ struct Single {
   float f_ext[6] = {0, 0, 0, 0, 0, 0};
   float sim_time = 0.f;
   float f_est[6] = {0, 0, 0, 0, 0, 0};
+  float f_est_smoothed[6] = {0, 0, 0, 0, 0, 0};  // SolverMPC.cpp:783
+  float f_est_static[6] = {0, 0, 0, 0, 0, 0};    // SolverMPC.cpp:798
   // adaptive bookkeeping of solve_mpc(), SolverMPC.cpp:688-798
   std::vector<float> time_history, diff_history;
-  std::vector<double> q_soln;
+  std::vector<double> q_soln, q_new;
+  int policy = CMPC_ON_ERROR_ABORT;
+  int last_status = CMPC_ST_SOLVED;
 };
 Single& single() {
   static Single s;
@@ -1763,6 +1864,7 @@ void setup_problem(double dt, int horizon, double mu, double f_max) {
   if (cmpc_batch_setup(s.b, dt, horizon, mu, f_max) != CMPC_OK) die("setup_problem");
   s.horizon = horizon;
   s.q_soln.assign(12 * horizon, 0.0);
+  s.q_new.assign(12 * horizon, 0.0);
 }
 
 static void solve_single(Single& s, const float* p, const float* v, const float* q, const float* w, const float* r,
@@ -1797,9 +1899,32 @@ static void solve_single(Single& s, const float* p, const float* v, const float*
   in.alpha = &alpha; in.gait = g8.data(); in.x_drag = &s.x_drag; in.f_dist = fd;
   cmpc_outputs out;
   std::memset(&out, 0, sizeof(out));
-  out.forces = s.q_soln.data();
+  int32_t status = CMPC_ST_SOLVED;
+  out.forces = s.q_new.data();
+  out.status = &status;
   if (cmpc_batch_solve_host(s.b, 1, &in, &out) != CMPC_OK) die("update_problem_data");
   if (mode >= 0 && cmpc_batch_download_disturbance(s.b, nullptr, s.f_est) != CMPC_OK) die("update_problem_data/f_est");
+  // the two filtered estimates solve_mpc keeps up to date on every call (SolverMPC.cpp:783, :798), float arithmetic
+  for (int i = 0; i < 6; i++) s.f_est_smoothed[i] = 0.95f * s.f_est_smoothed[i] + 0.05f * s.f_est[i];
+  s.f_est_static[3] = 0.97f * s.f_est_static[3] + 0.03f * s.f_ext[3];
+  // a solve that did not reach the optimum, or that met NaN / Inf on the way, must not reach the legs: the dual
+  // iterate is primal infeasible before convergence (it can leave the friction cone), NaN is NaN
+  bool finite = true;
+  for (double f : s.q_new) finite = finite && std::isfinite(f);
+  if (!finite && (status == CMPC_ST_SOLVED || status == CMPC_ST_EMPTY)) status = CMPC_ST_NONFINITE;
+  s.last_status = status;
+  if (status != CMPC_ST_SOLVED && status != CMPC_ST_EMPTY) {
+    std::fprintf(stderr, "[cmpc_b200] update_problem_data: solve ended with status %d (%s)\n", (int)status,
+                 status == CMPC_ST_NONFINITE ? "non-finite input, disturbance estimate or iterate"
+                                             : status == CMPC_ST_MAXITER ? "iteration cap" : "see CMPC_ST_*");
+    if (s.policy == CMPC_ON_ERROR_ABORT) {
+      g_err = "solve did not reach the optimum";
+      die("update_problem_data");
+    }
+    s.has_solved = true;  // CMPC_ON_ERROR_HOLD: get_solution() keeps serving the last good forces
+    return;
+  }
+  s.q_soln.swap(s.q_new);
   s.has_solved = true;
 }
 
@@ -1863,12 +1988,36 @@ void cmpc_get_disturbance_estimate(float f_est[6]) {
   for (int i = 0; i < 6; i++) f_est[i] = s.f_est[i];
 }
 
+void cmpc_get_disturbance_estimate_smoothed(float f_est_smoothed[6]) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  for (int i = 0; i < 6; i++) f_est_smoothed[i] = s.f_est_smoothed[i];
+}
+
+void cmpc_get_disturbance_estimate_static(float f_est_static[6]) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  for (int i = 0; i < 6; i++) f_est_static[i] = s.f_est_static[i];
+}
+
+void cmpc_set_error_policy(int policy) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  s.policy = policy == CMPC_ON_ERROR_HOLD ? CMPC_ON_ERROR_HOLD : CMPC_ON_ERROR_ABORT;
+}
+
+int cmpc_last_status(void) {
+  Single& s = single();
+  std::lock_guard<std::mutex> lk(s.mu);
+  return s.last_status;
+}
+
 void cmpc_reset_history(void) {
   Single& s = single();
   std::lock_guard<std::mutex> lk(s.mu);
   s.time_history.clear();
   s.diff_history.clear();
-  for (int i = 0; i < 6; i++) s.f_est[i] = 0.f;
+  for (int i = 0; i < 6; i++) s.f_est[i] = s.f_est_smoothed[i] = s.f_est_static[i] = 0.f;
   if (s.b && s.b->d_fest) {
     cudaSetDevice(s.b->device);
     cudaMemset(s.b->d_fest, 0, sizeof(float) * 6 * (size_t)s.b->capacity);
@@ -1878,3 +2027,8 @@ void cmpc_reset_history(void) {
 }
 
 }  // extern "C"
+
+// convexMPC_interface.h:52 declares update_x_drag WITHOUT extern "C": an unmodified reference translation unit that
+// includes that header references the C++-mangled symbol.  Same function, second name.
+void cmpc_update_x_drag_cxx(float x_drag) __asm__("_Z13update_x_dragf");
+void cmpc_update_x_drag_cxx(float x_drag) { update_x_drag(x_drag); }

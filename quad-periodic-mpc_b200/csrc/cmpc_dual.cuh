@@ -389,7 +389,12 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
       continue;
     }
     // ---- outputs: q_soln scatter (zeros for swing feet), objective, primal activity mask ----
-    const bool have_x = have;
+    bool fin = true;  // a non-finite iterate (NaN / Inf upstream) reports CMPC_ST_NONFINITE and zero forces
+    if (have)
+      for (int i = lane; i < n; i += 32) fin = fin && isfinite(x[i]);
+    fin = __all_sync(0xffffffffu, fin);
+    if (have && !fin) status = CMPC_ST_NONFINITE;
+    const bool have_x = have && fin;
     if (P.forces) {
       double* out = P.forces + (size_t)inst * 12 * h;
       for (int idx = lane; idx < 12 * h; idx += 32) {

@@ -402,7 +402,14 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
       continue;
     }
     // ---- outputs: q_soln scatter (zeros for swing feet), objective, primal activity mask ----
-    const bool have_x = have;
+    // NaN / Inf anywhere upstream (inputs, disturbance estimate) ends here as a non-finite iterate: the violation test
+    // `!(best < -tol)` stops the iterations on NaN.  Such an instance reports CMPC_ST_NONFINITE and zero forces.
+    bool fin = true;
+#pragma unroll
+    for (int e = 0; e < NPL; e++) fin = fin && isfinite(x[e]);
+    fin = __all_sync(0xffffffffu, fin);
+    if (have && !fin) status = CMPC_ST_NONFINITE;
+    const bool have_x = have && fin;
 #pragma unroll
     for (int e = 0; e < NPL; e++) kns[lane + 32 * e] = x[e];
     __syncwarp();

@@ -18,8 +18,7 @@
 #pragma once
 
 namespace {
-// Panel of block step S from the register tiles: rows 8S..8S+7 of the symmetric matrix, tiles (S, J <= S) as
-// they are and tiles (I > S, S) transposed, D - I in the diagonal block; row 63 (the border) is published as 0.
+#ifdef CMPC_EXPERIMENTS
 // -D^-1 of the diagonal tile of block step S (row / column 63, the border, excluded from the pivot block)
 template <int S>
 __device__ __forceinline__ void invert_diag(const double (&t)[36][2], double* dv, int r, int q) {
@@ -31,7 +30,10 @@ __device__ __forceinline__ void invert_diag(const double (&t)[36][2], double* dv
   warp_inv8_acc(d0, d1, r, q);
   *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
 }
+#endif
 
+// Panel of block step S from the register tiles: rows 8S..8S+7 of the symmetric matrix, tiles (S, J <= S) as
+// they are and tiles (I > S, S) transposed, D - I in the diagonal block; row 63 (the border) is published as 0.
 template <int S>
 __device__ __forceinline__ void publish_panel(const double (&t)[36][2], double* pan, int r, int q) {
   constexpr int PS = MMA_PS;
@@ -52,6 +54,9 @@ __device__ __forceinline__ void publish_panel(const double (&t)[36][2], double* 
   }
 }
 
+}  // namespace
+#ifdef CMPC_EXPERIMENTS  // the single-warp kernel (superseded by cmpc_invert_ws_kernel below) is kept for A/B builds only
+namespace {
 // Hardest-first scheduling of the active-set kernel: count the constraint rows that x0 (staged in `xs`, shared
 // memory) violates — five rows per contact foot-step, as cmpc_dual_fast.cuh lays them out — and file the instance.
 // deferred form: the histogram atomic is issued here, its result (lane 0) is written by lpt_store one instance later,
@@ -219,6 +224,7 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
 #undef INV_TICK
   if (lane == 0 && P.flops && flops_acc) atomicAdd(P.flops + CMPC_K_INVERT, (unsigned long long)flops_acc);
 }
+#endif  // CMPC_EXPERIMENTS
 
 // ------------------------------------------------------------------------------------------------------------
 // Warp-specialised variant: the serial part of a block step — the 8-pivot chain that inverts the diagonal tile,

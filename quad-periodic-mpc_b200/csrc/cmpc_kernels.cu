@@ -465,7 +465,14 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
     __syncthreads();
     // ---- F. outputs (an overflowed instance is left for the full-capacity launch) ----
     if (status != CMPC_ST_WSOVERFLOW || !P.overflow_list) {
-      const bool have_x = (nc > 0 && status != CMPC_ST_CAPACITY);
+      bool have_x = (nc > 0 && status != CMPC_ST_CAPACITY);
+      {  // a non-finite iterate (NaN / Inf upstream) reports CMPC_ST_NONFINITE and zero forces
+        int fin = 1;
+        if (have_x)
+          for (int i = tid; i < 3 * nc; i += NT) fin = fin && isfinite(x[i]);
+        fin = __syncthreads_and(fin);
+        if (have_x && !fin) { status = CMPC_ST_NONFINITE; have_x = false; }
+      }
       if (P.forces) {
         double* out = P.forces + (size_t)inst * 12 * h;
         for (int idx = tid; idx < 12 * h; idx += NT) {

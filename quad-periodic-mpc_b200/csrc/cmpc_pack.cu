@@ -149,12 +149,20 @@ int cmpc_launch_pack(const void* p, const void* v, const void* q, const void* w,
   A.gait_words = h;
   A.tail_dst = CMPC_REC_TRAJ + 13 * h;
   A.tail_words = A.rec_words - A.tail_dst;
-  static const int vec = [] { const char* e = std::getenv("CMPC_PACK_VEC"); return e ? std::atoi(e) : 1; }();  // experiments
+#ifdef CMPC_EXPERIMENTS
+  static const int vec = [] { const char* e = std::getenv("CMPC_PACK_VEC"); return e ? std::atoi(e) : 1; }();
+#else
+  constexpr int vec = 1;
+#endif
   A.vec = vec;
   const long long words = (long long)count * (12 * h);
   const long long per_cta = (long long)PACK_THREADS * PACK_UNROLL;
   int grid = (int)((words + per_cta - 1) / per_cta);
-  static const int grid_cap = [] { const char* e = std::getenv("CMPC_PACK_GRID"); return e ? std::atoi(e) : 0; }();  // experiments
+#ifdef CMPC_EXPERIMENTS
+  static const int grid_cap = [] { const char* e = std::getenv("CMPC_PACK_GRID"); return e ? std::atoi(e) : 0; }();
+#else
+  constexpr int grid_cap = 0;
+#endif
   const int cap = grid_cap > 0 ? grid_cap : (sm_count + 7) / 8;  // few, fat CTAs (measured: profiles/r1_s4_pack_grid.txt): they have to find room beside resident solve kernels
   if (which == CMPC_PACK_TRAJ) { if (grid > sm_count) grid = sm_count; }  // staged in HBM: latency is short, more CTAs finish sooner
   else if (grid > cap) grid = cap;

@@ -167,6 +167,7 @@ int cmpc_launch_dual(const CmpcParams& P, int wpc, int grid, void* stream) {
 
 // ---- inversion kernel of the n <= 63 path (cmpc_invert_mma.cuh): one warp per CTA; the register cap decides how
 //      many instances an SM sub-partition holds (16384 registers each): 200 -> two, 168 -> three ----
+#ifdef CMPC_EXPERIMENTS
 namespace {
 int inv_regs() {
   static int v = [] {
@@ -193,6 +194,7 @@ int launch_invert_t(const CmpcParams& P, int grid, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 }  // namespace
+#endif
 // hardest-first order of the active-set kernel: instance -> position from the key histogram the inversion kernel left
 namespace {
 __global__ void __launch_bounds__(256) cmpc_lpt_order_kernel(const int* __restrict__ hist, const int* __restrict__ key,
@@ -216,8 +218,10 @@ int cmpc_launch_lpt_order(const int* hist, const int* key, int* worklist, int co
   return (int)cudaGetLastError();
 }
 
-// warp-specialised variant (default): helper warps carry the pivot chains; CMPC_INV_WS=0 selects the kernel above
+// warp-specialised kernel: helper warps carry the pivot chains (an experiments build can select the single-warp
+// kernel with CMPC_INV_WS=0)
 namespace {
+#ifdef CMPC_EXPERIMENTS
 bool inv_ws() {
   static bool v = [] {
     const char* e = std::getenv("CMPC_INV_WS");
@@ -225,6 +229,9 @@ bool inv_ws() {
   }();
   return v;
 }
+#else
+constexpr bool inv_ws() { return true; }
+#endif
 }  // namespace
 int cmpc_invert_max_ctas_per_sm(void) {
   if (inv_ws()) {
@@ -232,15 +239,28 @@ int cmpc_invert_max_ctas_per_sm(void) {
     const size_t smem = (size_t)WS_MAIN * WS_PAIR_SMEM;
     if (smem_attr<cmpc_invert_ws_kernel<false>>(smem) != cudaSuccess) return -1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_invert_ws_kernel<false>, 64 * WS_MAIN, smem) != cudaSuccess) return -1;
-    if (const char* e = std::getenv("CMPC_INV_CTAS_PER_SM")) nb = std::max(1, std::min(nb, std::atoi(e)));  // experiments
+#ifdef CMPC_EXPERIMENTS
+    if (const char* e = std::getenv("CMPC_INV_CTAS_PER_SM")) nb = std::max(1, std::min(nb, std::atoi(e)));
+#endif
     return nb;
   }
+#ifdef CMPC_EXPERIMENTS
   return inv_regs() == 200 ? occ_invert_t<200, false>() : occ_invert_t<168, false>();
+#else
+  return -1;
+#endif
 }
-int cmpc_invert_instances_per_cta(void) { return inv_ws() ? WS_MAIN : INV_WPC; }
+int cmpc_invert_instances_per_cta(void) {
+#ifdef CMPC_EXPERIMENTS
+  if (!inv_ws()) return INV_WPC;
+#endif
+  return WS_MAIN;
+}
 int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+#ifdef CMPC_EXPERIMENTS
   if (P.phase_cycles && !inv_ws()) return inv_regs() == 200 ? launch_invert_t<200, true>(P, grid, st) : launch_invert_t<168, true>(P, grid, st);
+#endif
   if (P.phase_cycles) {
     const size_t smem = (size_t)WS_MAIN * WS_PAIR_SMEM;
     cudaError_t e = smem_attr<cmpc_invert_ws_kernel<true>>(smem);
@@ -255,7 +275,11 @@ int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
     cmpc_invert_ws_kernel<false><<<grid, 64 * WS_MAIN, smem, st>>>(P);
     return (int)cudaGetLastError();
   }
+#ifdef CMPC_EXPERIMENTS
   return inv_regs() == 200 ? launch_invert_t<200, false>(P, grid, st) : launch_invert_t<168, false>(P, grid, st);
+#else
+  return (int)cudaErrorInvalidDeviceFunction;
+#endif
 }
 
 // ---- fast tier of the dual active-set kernel (cmpc_dual_fast.cuh): working sets of up to 32 rows ----

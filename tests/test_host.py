@@ -31,6 +31,40 @@ def test_library_exports_every_declared_symbol(built_lib):
         getattr(lib, s)
 
 
+def build_reference_caller(built_lib):
+    """g++ translation unit that includes only the reference's declarations, linked against libcmpc_b200.so."""
+    src = os.path.join(ROOT, "tests", "cxx", "reference_caller.cpp")
+    out = os.path.join(ROOT, "build", "reference_caller")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    libdir = os.path.dirname(built_lib)
+    subprocess.run(["g++", "-O1", "-std=c++14", src, "-o", out, "-L" + libdir, "-lcmpc_b200", "-Wl,-rpath," + libdir],
+                   check=True)
+    return out
+
+
+def test_unmodified_cxx_caller_links(built_lib):
+    """convexMPC_interface.h:52 declares update_x_drag with C++ linkage: both names must be exported, and a g++
+    caller that sees only the reference's declarations must link (it is RUN by the gpu tests)."""
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], check=True, capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    assert "update_x_drag" in exported and "_Z13update_x_dragf" in exported
+    exe = build_reference_caller(built_lib)
+    und = subprocess.run(["nm", "-u", exe], check=True, capture_output=True, text=True).stdout
+    assert "_Z13update_x_dragf" in und and "setup_problem" in und
+
+
+def test_library_reads_no_environment_on_solve_paths():
+    """Diagnostic switches exist only through cmpc_batch_set_option; the one getenv left in the default build is
+    CMPC_DEVICE of the single-instance reference interface (read once, at the first setup_problem)."""
+    csrc = os.path.join(ROOT, "quad-periodic-mpc_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        text = open(os.path.join(csrc, f)).read()
+        # drop the -DCMPC_EXPERIMENTS-only regions
+        text = re.sub(r"#ifdef CMPC_EXPERIMENTS.*?#e(?:lse|ndif)", "", text, flags=re.S)
+        for m in re.finditer(r'getenv\("(\w+)"\)', text):
+            assert m.group(1) == "CMPC_DEVICE", (f, m.group(1))
+
+
 def test_kernel_image_is_sm100a_with_bulk_copy(built_lib):
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], check=True, capture_output=True, text=True).stdout
     assert "sm_100a" in sass
