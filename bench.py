@@ -2,7 +2,11 @@
 """bench.py — cMPC QP solves/sec (horizon 10, batched A1 trot) on N B200s, next to the
 reference's qpOASES path on the host cores.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode headline|sweep1m]
+
+  --mode headline (default): weak scaling, 4096 instances per GPU per step (BASELINE.json configs[1]).
+  --mode sweep1m: BASELINE.json configs[4] — ONE fixed batch of 2^20 instances sharded over the N ranks
+             (shard_bounds), a step is one pass over the whole million; strong scaling.
 
 One "step" = one pass of the condensation + inversion + QP kernels over one batch of 4096 synthetic
 randomised A1 trot instances (BASELINE.json configs[1]) per GPU.  Instances are independent, so the
@@ -39,11 +43,21 @@ for _p in (os.path.join(ROOT, "quad-periodic-mpc_b200"), ROOT):
 import numpy as np  # noqa: E402
 
 HORIZON, DT, BATCH = 10, 0.03, 4096
+SWEEP_TOTAL = 1 << 20
 METRIC = "cmpc_qp_solves_per_sec_h10_batched"
 L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (bytes), from the committed ncu --set full capture
 # (profiles/r1_s3_ncu_full_summary.txt; cold cache: ncu flushes L2 between kernels)
 NCU_TRAFFIC = {"assemble": 40.1e6, "invert": 97.2e6, "dual": 28.9e6, "fused": None}
+
+
+WORKLOADS = {
+    "headline": "batch 4096 A1 trot instances, horizon 10, dt 0.03, randomised states (BASELINE.json configs[1]) per GPU per step",
+    "sweep1m": "one fixed batch of 1048576 A1 trot instances, horizon 10, dt 0.03, randomised states, sharded over the "
+               "ranks (BASELINE.json configs[4])",
+}
+# the CPU arm is a port (restated fp32 condensation) around the reference's REAL qpOASES 3.2.0 (compiled from its sources)
+CPU_KIND = "port+reference-qpOASES"
 
 
 def shard_bounds(total, rank, world):
@@ -107,6 +121,44 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def single_solve_latency(device, reps=1000):
+    """BASELINE.json configs[0]: one update_problem_data_floats -> get_solution round trip through the reference's own
+    single-instance interface (convexMPC_interface.h:44-52): pageable inputs, host packing, one instance, the whole
+    kernel chain, the twelve first-step forces read back.  Microseconds, wall clock."""
+    from cmpc_b200 import engine, synth
+    L = engine.lib()
+    os.environ["CMPC_DEVICE"] = str(device)
+    inst = synth.make_batch(64, horizon=HORIZON, dt=DT, seed=77)
+    L.cmpc_reset_history()
+    L.setup_problem(DT, HORIZON, inst["mu"], inst["f_max"])
+    args = []
+    for i in range(64):
+        a = [np.array(inst[k][i], dtype=np.float32) for k in ("p", "v", "q", "w", "r", "weights", "traj")]
+        a.append(np.ascontiguousarray(inst["gait"][i], dtype=np.int32))
+        args.append(a)
+    lat = []
+    fext = np.zeros(6, dtype=np.float32)
+    for k in range(reps + 20):
+        p, v, q, w, r, wt, tr, gait = args[k % 64]
+        # what the controller does before every solve: the two globals of the adaptive hook (f_ext, simulation_time)
+        fext[3] = 0.3 + 0.8 * np.sin(2 * np.pi * 0.7 * DT * k)
+        t0 = time.perf_counter()
+        L.cmpc_set_external_force(fext.ctypes.data)
+        L.cmpc_set_simulation_time(DT * k)
+        L.update_problem_data_floats(p.ctypes.data, v.ctypes.data, q.ctypes.data, w.ctypes.data, r.ctypes.data, 0.0, 0.0,
+                                     0.0, wt.ctypes.data, tr.ctypes.data, float(inst["alpha"][k % 64]), gait.ctypes.data)
+        f = [L.get_solution(j) for j in range(12)]
+        t1 = time.perf_counter()
+        if k >= 20:
+            lat.append(1e6 * (t1 - t0))
+    assert all(np.isfinite(f))
+    L.cmpc_reset_history()
+    lat.sort()
+    return {"median": lat[len(lat) // 2], "p99": lat[int(0.99 * len(lat))], "min": lat[0], "reps": reps,
+            "call": "setup once, then update_problem_data_floats + 12 x get_solution per solve (one A1 trot instance, "
+                    "horizon 10) through the reference's single-instance interface; includes the ctypes call overhead"}
+
+
 def cpu_reference_run(steps, warmup, sample, threads=None):
     """The reference's CPU implementation of the path on the host cores (oracle/_ref)."""
     from cmpc_b200 import synth
@@ -131,21 +183,39 @@ def cpu_reference_run(steps, warmup, sample, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    sample = 1024
+    # the same per-step batch as the GPU arm's headline workload; in sweep1m mode a step of the GPU arm is 2^20 solves,
+    # here a bounded 4096-instance sample of the same distribution (a million qpOASES solves take ~25 s per step)
+    sample = BATCH
     r = cpu_reference_run(args.steps, args.warmup, sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 condensation + f64 qpOASES",
         "data": "synthetic",
-        "config": {"workload": "A1 trot, horizon 10, dt 0.03, randomised states", "batch_per_step": sample},
-        "cpu_baseline": {"value": r["value"], "unit": "solves/s", "cores": r["threads"], "kind": "reference",
+        "config": {"workload": WORKLOADS[args.mode], "batch_per_gpu": sample, "horizon": HORIZON,
+                   "sample": "every step solves %d instances of the workload on the host cores" % sample},
+        "cpu_baseline": {"value": r["value"], "unit": "solves/s", "cores": r["threads"], "kind": CPU_KIND,
                          "sample": "%d instances of the bench workload per step, qpOASES 3.2.0 compiled from the "
                                    "reference's sources + restated fp32 condensation, one solve per thread" % sample},
         "e2e": {"value": r["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def pin_rank_to_cores(local_rank, world):
+    """N ranks on one host: give every rank its own slice of the cores this process may use, so the eight enqueue
+    threads (and each engine's host workers) do not migrate across each other."""
+    if world <= 1:
+        return None
+    cores = sorted(os.sched_getaffinity(0))
+    per = max(1, len(cores) // world)
+    mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return None
+    return mine
 
 
 def run_b200(args, rank, world, local_rank):
@@ -155,12 +225,25 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    cores = pin_rank_to_cores(local_rank, world)
+    sweep = args.mode == "sweep1m"
     h = HORIZON
     rec_bytes = 4 * (48 + 12 * h) + 4 * h
     rec_bytes = (rec_bytes + 15) & ~15
     out_bytes = 12 * h * 8 + 20 * h + 8 + 4 + 4
-    ring = max(2, -(-int(1.25 * L2_BYTES) // (BATCH * (rec_bytes + out_bytes))))
-    total = ring * BATCH
+    if sweep:
+        # ONE fixed batch of 2^20 instances, cut over the ranks; a step is one pass over the whole batch (this rank:
+        # its shard, in launches of 65536 instances that rotate through the engine's streams)
+        lo, hi = shard_bounds(SWEEP_TOTAL, rank, world)
+        total = hi - lo
+        launch = 65536
+        ring = -(-total // launch)
+        per_step_units = float(total)
+    else:
+        ring = max(2, -(-int(1.25 * L2_BYTES) // (BATCH * (rec_bytes + out_bytes))))
+        total = ring * BATCH
+        launch = BATCH
+        per_step_units = float(BATCH)
     inst = synth.make_batch(total, horizon=h, dt=DT, seed=1000 + rank)
     b = engine.Batch(total, device=local_rank)
     b.setup(DT, h, inst["mu"], inst["f_max"])
@@ -173,9 +256,16 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
         b.sync()
 
+    def resident_step(i):
+        if sweep:
+            for k0 in range(0, total, launch):
+                b.solve_range(k0, min(launch, total - k0))
+        else:
+            b.solve_range((i % ring) * BATCH, BATCH)
+
     # ---- device-resident throughput ----
     for i in range(args.warmup):
-        b.solve_range((i % ring) * BATCH, BATCH)
+        resident_step(i)
     b.sync()
     b.reset_counters()
     sampler = ClockSampler(local_rank)
@@ -183,32 +273,45 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     b.mark(0)
     for i in range(args.steps):
-        b.solve_range(((i + args.warmup) % ring) * BATCH, BATCH)
+        resident_step(i + args.warmup)
     b.mark(1)
     barrier()
-    region_ms = b.marked_ms()          # CUDA events on the launching stream around exactly K launches
+    region_ms = b.marked_ms()          # CUDA events on the launching stream around exactly K steps
     launches = b.launches()
     flops_total = b.last_flops()
-    units, seconds = allreduce_sum_max(float(args.steps * BATCH), region_ms / 1e3)
+    units, seconds = allreduce_sum_max(args.steps * per_step_units, region_ms / 1e3)
     value = units / seconds
+    # every instance the timed region touched reached its optimum (the ring covers them all)
+    chk = b.download(want_active=False)
+    touched = total if (sweep or args.steps + args.warmup >= ring) else (args.steps + args.warmup) * BATCH
+    assert (chk["status"][:touched] == engine.ST_SOLVED).all(), "resident loop: %d instances not solved" % (
+        chk["status"][:touched] != engine.ST_SOLVED).sum()
+    f = chk["forces"][:touched].reshape(touched, -1, 3)
+    assert np.isfinite(f).all() and (f[..., 2] >= -1e-8).all() and (f[..., 2] <= inst["f_max"] + 1e-8).all()
+    del chk, f
 
-    # ---- end to end through the host-buffer call ----
-    sub = {k: (v[:BATCH] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
-    be = engine.Batch(BATCH, device=local_rank)
-    be.setup(DT, h, inst["mu"], inst["f_max"])
-    be.prepare_host(sub, want_active=False)   # host arrays bound once; every step below is one C-ABI call
-    for _ in range(max(1, args.warmup)):
+    # ---- end to end through the host-buffer call: forces, objective, status, iterations AND the activity mask ----
+    if sweep:
+        be, sub, e2e_n = b, inst, total     # the shard itself, through the same handle (a second one would double its HBM)
+    else:
+        sub = {k: (v[:BATCH] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
+        be = engine.Batch(BATCH, device=local_rank)
+        be.setup(DT, h, inst["mu"], inst["f_max"])
+        e2e_n = BATCH
+    be.prepare_host(sub, want_active=True)   # host arrays bound once; every step below is one C-ABI call
+    for _ in range(max(1, args.warmup if not sweep else 1)):
         res = be.solve_prepared()
+    e2e_steps = args.steps
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = be.solve_prepared()                # pack -> pinned -> H2D -> kernel -> D2H -> unpack, 4 chunks on 2 streams
+    for _ in range(e2e_steps):
+        res = be.solve_prepared()                # inputs read over PCIe -> records -> kernels -> results in host memory
     barrier()
     e2e_wall = time.perf_counter() - t0
-    e2e_units, e2e_seconds = allreduce_sum_max(float(args.steps * BATCH), e2e_wall)
+    e2e_units, e2e_seconds = allreduce_sum_max(float(e2e_steps * e2e_n), e2e_wall)
     assert (res["status"] == 0).all()
     h2d = int(sum(a.nbytes for a in be._prepared_inputs.values()))   # the eleven input arrays the device reads over PCIe
-    d2h = int(sum(a.nbytes for a in res.values()))                    # forces, objective, status, iterations
+    d2h = int(sum(a.nbytes for a in res.values()))                    # forces, objective, status, iterations, active
 
     # ---- the same call with D batches in flight (submit / wait): step k is submitted before step k-D+1 is waited for ----
     def in_flight(depth):
@@ -217,7 +320,7 @@ def run_b200(args, rank, world, local_rank):
             sk = {kk: (v[(k + 1) * BATCH:(k + 2) * BATCH] if isinstance(v, np.ndarray) else v) for kk, v in inst.items()}
             bk = engine.Batch(BATCH, device=local_rank)
             bk.setup(DT, h, inst["mu"], inst["f_max"])
-            bk.prepare_host(sk, want_active=False)
+            bk.prepare_host(sk, want_active=True)
             pipe.append(bk)
         for k in range(depth * max(1, args.warmup)):
             pipe[k % depth].solve_prepared()
@@ -237,140 +340,170 @@ def run_b200(args, rank, world, local_rank):
             bk.close()
         return units, secs
 
-    pipe_units, pipe_seconds = in_flight(2)
-    deep = min(8, ring - 1)
-    deep_units, deep_seconds = in_flight(deep)
+    extra = {}
+    if not sweep:
+        pipe_units, pipe_seconds = in_flight(2)
+        deep = min(8, ring - 1)
+        deep_units, deep_seconds = in_flight(deep)
+        extra["two_in_flight"] = {"value": pipe_units / pipe_seconds, "unit": "solves/s",
+                                  "ms_per_step": 1e3 * pipe_seconds / args.steps,
+                                  "call": "cmpc_batch_submit_bound / cmpc_batch_wait_bound on two batches: every step "
+                                          "still reads its inputs from and writes its results to pinned host arrays"}
+        extra["deep_in_flight"] = {"value": deep_units / deep_seconds, "unit": "solves/s", "batches_in_flight": deep,
+                                   "ms_per_step": 1e3 * deep_seconds / args.steps,
+                                   "call": "the same submit / wait calls on %d engine handles (scripts/e2e_depth.py)" % deep}
+        # ---- end to end one level up: the controller-level call (updateMPCIfNeeded / solveDenseMPC on the device) ----
+        cmds = synth.make_commands(BATCH, engine.COMMAND_DTYPE, horizon=h, gaits=("trot",), seed=2000 + rank)
+        cres = np.zeros(BATCH, dtype=engine.RESULT_DTYPE)
+        bc = engine.Batch(BATCH, device=local_rank)
+        bc.setup(DT, h, inst["mu"], inst["f_max"])
+        for a in (cmds, cres):
+            engine.lib().cmpc_host_register(a.ctypes.data, a.nbytes)
+        for _ in range(max(1, args.warmup)):
+            bc.solve_commands(cmds, results=cres)
+        csteps = max(1, min(args.steps, 200))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(csteps):
+            bc.solve_commands(cmds, results=cres)
+        barrier()
+        cmd_wall = time.perf_counter() - t0
+        cmd_units, cmd_seconds = allreduce_sum_max(float(csteps * BATCH), cmd_wall)
+        assert (cres["status"] == 0).all()
+        for a in (cmds, cres):
+            engine.lib().cmpc_host_unregister(a.ctypes.data)
+        bc.close()
+        extra["commands"] = {"value": cmd_units / cmd_seconds, "unit": "solves/s", "steps": csteps,
+                             "h2d_bytes_per_step": int(cmds.nbytes), "d2h_bytes_per_step": int(cres.nbytes),
+                             "ms_per_step": 1e3 * cmd_seconds / csteps,
+                             "call": "cmpc_batch_solve_commands: the controller-level call (ConvexMPCLocomotion::"
+                                     "updateMPCIfNeeded + solveDenseMPC + getMpcTable on the device), one cmpc_command "
+                                     "in and one cmpc_command_result out per robot"}
+    clocks = sampler.stop()            # sampled through the timed regions (resident, e2e, e2e commands)
+    if sweep:
+        be.release_prepared()
 
-    # ---- end to end one level up: the controller-level call (updateMPCIfNeeded / solveDenseMPC on the device) ----
-    cmds = synth.make_commands(BATCH, engine.COMMAND_DTYPE, horizon=h, gaits=("trot",), seed=2000 + rank)
-    cres = np.zeros(BATCH, dtype=engine.RESULT_DTYPE)
-    bc = engine.Batch(BATCH, device=local_rank)
-    bc.setup(DT, h, inst["mu"], inst["f_max"])
-    for a in (cmds, cres):
-        engine.lib().cmpc_host_register(a.ctypes.data, a.nbytes)
-    for _ in range(max(1, args.warmup)):
-        bc.solve_commands(cmds, results=cres)
-    csteps = max(1, min(args.steps, 200))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(csteps):
-        bc.solve_commands(cmds, results=cres)
-    barrier()
-    cmd_wall = time.perf_counter() - t0
-    cmd_units, cmd_seconds = allreduce_sum_max(float(csteps * BATCH), cmd_wall)
-    assert (cres["status"] == 0).all()
-    for a in (cmds, cres):
-        engine.lib().cmpc_host_unregister(a.ctypes.data)
-    bc.close()
-    clocks = sampler.stop()            # sampled through the three timed regions (resident, e2e, e2e commands)
-
-    # ---- per-kernel-class device time: serial solves (CUDA events between the classes) on cold ring batches ----
+    # ---- per-kernel-class device time: serial solves (CUDA events between the classes) on cold batches ----
     kflops = b.kernel_flops()                     # algorithmic flops of the timed region, per kernel class
     prof_n = min(8, ring)
     kms = {k: 0.0 for k in engine.Batch.KERNELS}
+    launches_per_step = ring if sweep else 1
     for i in range(prof_n):
-        t = b.profile_range(((i + 3) % ring) * BATCH, BATCH)
+        k0 = ((i + 3) % ring) * launch
+        t = b.profile_range(k0, min(launch, total - k0))
         for k in kms:
             kms[k] += t[k] / prof_n
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         fp64 = engine.measure_fp64_peak(local_rank)
+        dmma = engine.measure_dmma_peak(local_rank)
         step_ms = region_ms / args.steps
         names = {"assemble": "cmpc_assemble_mma_kernel", "invert": "cmpc_invert_ws_kernel",
                  "dual": "cmpc_lpt_order_kernel + cmpc_dual_fast_kernel + cmpc_dual_kernel (resumed working sets beyond the first tier)", "fused": "cmpc_solve_kernel"}
         bounds = {"assemble": "latency / issue (FP64 FMA + shared memory)", "invert": "tensor (FP64 DMMA)",
                   "dual": "latency (dependent chain per active-set iteration)", "fused": "latency"}
+        peak_of = {"assemble": fp64, "invert": dmma, "dual": fp64, "fused": fp64}
         kernels = []
         for k in engine.Batch.KERNELS:
             if kms[k] <= 0.0:
                 continue
-            fl = kflops[k] / args.steps
+            fl = kflops[k] / args.steps / launches_per_step
             ach = fl / (kms[k] * 1e-3) / 1e12
             kernels.append({"kernel": names[k], "ms": kms[k], "flops_per_launch": fl, "achieved_tflops": ach,
-                            "frac_of_fp64_peak": ach / fp64 if fp64 else None, "bound": bounds[k]})
+                            "frac_of_fp64_peak": ach / peak_of[k] if peak_of[k] else None, "bound": bounds[k],
+                            "share_of_serial_time": kms[k] / sum(kms.values())})
         fl_step = sum(kflops.values()) / args.steps
-        dom = "invert" if kms["invert"] > 0 else max(kms, key=kms.get)
-        fl_dom = kflops[dom] / args.steps
+        dom = "invert" if kms["invert"] > 0 else max(kms, key=kms.get)   # the flop-dominant kernel (80 % of the step's flops)
+        tdom = max(kms, key=kms.get)                                       # the time-dominant kernel class
+        fl_dom = kflops[dom] / args.steps / launches_per_step
         achieved = fl_dom / (kms[dom] * 1e-3) / 1e12
-        hbm_bytes = BATCH * (rec_bytes + out_bytes)
+        fl_t = kflops[tdom] / args.steps / launches_per_step
+        hbm_bytes = (total if sweep else BATCH) * (rec_bytes + out_bytes)
         hbm_ach = hbm_bytes / (step_ms * 1e-3) / 1e9
         cpu = None
         try:
             c = cpu_reference_run(10, 1, 4096)
-            cpu = {"value": c["value"], "unit": "solves/s", "cores": c["threads"], "kind": "reference",
+            cpu = {"value": c["value"], "unit": "solves/s", "cores": c["threads"], "kind": CPU_KIND,
                    "sample": "10 x 4096 instances of the bench workload (about 20 core-seconds), qpOASES 3.2.0 built "
                              "from the reference's sources + restated fp32 condensation, one solve per thread on all "
                              "host cores"}
         except Exception as e:  # the checker library did not travel
-            cpu = {"value": None, "unit": "solves/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+            cpu = {"value": None, "unit": "solves/s", "cores": 0, "kind": CPU_KIND, "sample": "unavailable: %s" % e}
+        latency = single_solve_latency(local_rank) if not sweep else None
+        cfg = {"workload": WORKLOADS[args.mode], "batch_per_gpu": total if sweep else BATCH, "horizon": h,
+               "l2": "inputs rotate through a ring of %d distinct resident batches (%.0f MB > L2)"
+                     % (ring, total * (rec_bytes + out_bytes) / 1e6) if not sweep else
+                     "every step reads this rank's whole shard (%.0f MB of records and outputs, > L2 up to 8 ranks)"
+                     % (total * (rec_bytes + out_bytes) / 1e6),
+               "sharding": "independent instances, no data-path collective" +
+                           (" (bench.shard_bounds over %d ranks)" % world if sweep else ""),
+               "pipelining": "successive launches rotate through the engine's eight CUDA streams (a launch is three "
+                             "kernels: assembly, FP64-tensor inversion, dual active set, plus the hardest-first "
+                             "ordering pass and the working-set overflow launch)",
+               "host_cores_per_rank": len(cores) if cores else None}
+        if sweep:
+            cfg["launch_instances"] = launch
+        else:
+            cfg["ring_batches"] = ring
         line = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batch 4096 A1 trot instances, horizon 10, dt 0.03, randomised states "
-                                   "(BASELINE.json configs[1]) per GPU per step",
-                       "batch_per_gpu": BATCH, "horizon": h, "ring_batches": ring,
-                       "l2": "inputs rotate through a ring of %d distinct resident batches (%.0f MB > L2)"
-                             % (ring, total * (rec_bytes + out_bytes) / 1e6),
-                       "sharding": "independent instances, no data-path collective",
-                       "pipelining": "successive steps rotate through the engine's eight CUDA streams (a step is three "
-                                     "kernels: assembly, FP64-tensor inversion, dual active set, plus the hardest-first "
-                                     "ordering pass and the working-set overflow launch)"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64, "unit": "TFLOP/s",
-                         "frac": achieved / fp64 if fp64 else None,
+            "scaling": "strong" if sweep else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": dmma, "unit": "TFLOP/s",
+                         "frac": achieved / dmma if dmma else None,
                          "traffic": NCU_TRAFFIC.get(dom),
                          "kernel": names[dom], "kernel_ms": kms[dom],
-                         "peak_source": "FP64 FMA microbenchmark run in this process (cmpc_measure_fp64_peak); FP64 DMMA "
-                                        "m8n8k4 measures the same rate on B200 (scripts/ubench/fp64_ubench.cu); "
-                                        "MEASURED_PEAKS.json holds no FP64 figure",
+                         "peak_source": "FP64 DMMA m8n8k4 microbenchmark run in this process (cmpc_measure_dmma_peak: "
+                                        "independent accumulators on every SM sub-partition); the FP64 FMA peak measured "
+                                        "the same way is fp64_fma_peak; MEASURED_PEAKS.json holds no FP64 figure",
+                         "fp64_fma_peak": fp64, "fp64_dmma_peak": dmma,
                          "flops_per_launch": fl_dom,
                          "flops_note": "algorithmic: n^3 + 2 n^2 per instance (symmetric inverse + x0 = -K g), n = 60; "
                                        "the kernel executes 1.6x that (padding to 64, full diagonal tiles, D^-1 C)",
-                         "timing": "CUDA events around each kernel class of %d serial solves of cold ring batches" % prof_n,
+                         "timing": "CUDA events around each kernel class of %d serial launches of cold batches" % prof_n,
                          "traffic_note": "dram bytes of one ncu --set full launch (profiles/); ncu flushes L2 between "
                                          "kernels, in the pipeline the tiles written by the assembly kernel are L2 hits",
+                         "time_dominant": {"kernel": names[tdom], "ms": kms[tdom],
+                                           "share_of_serial_time": kms[tdom] / sum(kms.values()),
+                                           "flops_per_launch": fl_t, "achieved": fl_t / (kms[tdom] * 1e-3) / 1e12,
+                                           "frac": fl_t / (kms[tdom] * 1e-3) / 1e12 / peak_of[tdom], "bound": bounds[tdom]},
                          "step": {"flops_per_step": fl_step, "achieved": fl_step / (step_ms * 1e-3) / 1e12,
                                   "frac": (fl_step / (step_ms * 1e-3) / 1e12) / fp64 if fp64 else None,
-                                  "ms": step_ms, "serial_ms": sum(kms.values())},
+                                  "ms": step_ms, "serial_ms": sum(kms.values()) * launches_per_step},
                          "kernels": kernels,
                          "hbm": {"achieved": hbm_ach, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm_ach / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                                  "bytes_per_launch": hbm_bytes, "peak_source": peak_kind}},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_units / e2e_seconds, "unit": "solves/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_seconds / args.steps,
-                    "call": "cmpc_batch_solve_bound: one synchronous call per step, pinned host arrays in the layout of "
-                            "update_problem_data (update_data_t); the device reads the inputs over PCIe and packs the "
-                            "records, the kernels write the results into host memory",
-                    "two_in_flight": {"value": pipe_units / pipe_seconds, "unit": "solves/s",
-                                      "ms_per_step": 1e3 * pipe_seconds / args.steps,
-                                      "call": "cmpc_batch_submit_bound / cmpc_batch_wait_bound on two batches: every step "
-                                              "still reads its inputs from and writes its results to pinned host arrays"},
-                    "deep_in_flight": {"value": deep_units / deep_seconds, "unit": "solves/s", "batches_in_flight": deep,
-                                       "ms_per_step": 1e3 * deep_seconds / args.steps,
-                                       "call": "the same submit / wait calls on %d engine handles (scripts/e2e_depth.py)" % deep},
-                    "commands": {"value": cmd_units / cmd_seconds, "unit": "solves/s", "steps": csteps,
-                                 "h2d_bytes_per_step": int(cmds.nbytes), "d2h_bytes_per_step": int(cres.nbytes),
-                                 "ms_per_step": 1e3 * cmd_seconds / csteps,
-                                 "call": "cmpc_batch_solve_commands: the controller-level call (ConvexMPCLocomotion::"
-                                         "updateMPCIfNeeded + solveDenseMPC + getMpcTable on the device), one cmpc_command "
-                                         "in and one cmpc_command_result out per robot"}},
+            "e2e": dict({"value": e2e_units / e2e_seconds, "unit": "solves/s", "h2d_bytes_per_step": h2d,
+                         "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_seconds / e2e_steps,
+                         "outputs": "forces, objective, status, iterations, active mask",
+                         "call": "cmpc_batch_solve_bound: one synchronous call per step, pinned host arrays in the layout of "
+                                 "update_problem_data (update_data_t); the device reads the inputs over PCIe and packs the "
+                                 "records, the kernels write the results into host memory"}, **extra),
             "gpu_launches": launches, "clocks": clocks,
         }
+        if latency:
+            line["latency_single_us"] = latency
         print(json.dumps(line), flush=True)
     b.close()
-    be.close()
+    if be is not b:
+        be.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--mode", default="headline", choices=["headline", "sweep1m"])
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    if args.steps is None:
+        args.steps = 500 if args.mode == "headline" else 10
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

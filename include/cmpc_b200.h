@@ -288,6 +288,9 @@ int cmpc_batch_phase_cycles(cmpc_batch* b, unsigned long long* cycles, int n);
 /* Measured FP64 FMA throughput of the device (dependent-free DFMA chains on every SM), the
  * denominator of the solve kernel's roofline; TFLOP/s. */
 int cmpc_measure_fp64_peak(int device, double* tflops);
+/* The same for the FP64 tensor pipe (independent DMMA m8n8k4 accumulators on every SM sub-partition): the
+ * denominator of the inversion kernel's roofline; TFLOP/s. */
+int cmpc_measure_dmma_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

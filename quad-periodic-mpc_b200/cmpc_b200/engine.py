@@ -97,6 +97,7 @@ def lib():
         L.cmpc_batch_enable_phase_clocks.argtypes = [C.c_void_p, C.c_int]
         L.cmpc_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
         L.cmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.cmpc_measure_dmma_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.cmpc_batch_set_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         L.cmpc_batch_solve_commands.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cmpc_batch_reset_history.argtypes = [C.c_void_p]
@@ -130,6 +131,12 @@ def _check(rc, what):
 def measure_fp64_peak(device=0):
     t = C.c_double()
     _check(lib().cmpc_measure_fp64_peak(device, C.byref(t)), "cmpc_measure_fp64_peak")
+    return t.value
+
+
+def measure_dmma_peak(device=0):
+    t = C.c_double()
+    _check(lib().cmpc_measure_dmma_peak(device, C.byref(t)), "cmpc_measure_dmma_peak")
     return t.value
 
 

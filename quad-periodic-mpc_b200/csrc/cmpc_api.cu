@@ -1788,7 +1788,11 @@ int cmpc_batch_phase_cycles(cmpc_batch* b, unsigned long long* cycles, int n) {
   return CMPC_OK;
 }
 
-int cmpc_measure_fp64_peak(int device, double* tflops) {
+static int measure_peak(int device, double* tflops, bool tensor);
+int cmpc_measure_fp64_peak(int device, double* tflops) { return measure_peak(device, tflops, false); }
+int cmpc_measure_dmma_peak(int device, double* tflops) { return measure_peak(device, tflops, true); }
+
+static int measure_peak(int device, double* tflops, bool tensor) {
   if (!tflops) return fail_arg("cmpc_measure_fp64_peak: null argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -1807,13 +1811,16 @@ int cmpc_measure_fp64_peak(int device, double* tflops) {
   double best = 0;
   for (int rep = 0; rep < 4; rep++) {
     CK(cudaEventRecord(e0, 0));
-    int rc = cmpc_run_dfma_peak(prop.multiProcessorCount, nullptr, d, iters);
+    int rc = tensor ? cmpc_run_dmma_peak(prop.multiProcessorCount, nullptr, d, iters / 4)
+                    : cmpc_run_dfma_peak(prop.multiProcessorCount, nullptr, d, iters);
     if (rc) return fail_cuda((cudaError_t)rc, "cmpc_dfma_peak_kernel");
     CK(cudaEventRecord(e1, 0));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
-    double fl = 2.0 * 8.0 * iters * 256.0 * 8.0 * prop.multiProcessorCount;
+    // DFMA: 8 chains x 2 flops x 256 threads x 8 CTAs per SM; DMMA: 16 accumulators x 512 flops x 8 warps x 4 CTAs per SM
+    double fl = tensor ? 16.0 * 512.0 * (iters / 4) * 8.0 * 4.0 * prop.multiProcessorCount
+                       : 2.0 * 8.0 * iters * 256.0 * 8.0 * prop.multiProcessorCount;
     best = std::max(best, fl / (ms * 1e-3) / 1e12);
   }
   cudaEventDestroy(e0);

@@ -186,6 +186,7 @@ int cmpc_shape_threads(int shape);
 int cmpc_launch_solve(const CmpcParams& P, int shape, int grid, void* stream);
 int cmpc_max_ctas_per_sm(int shape, size_t smem, bool adapt);
 int cmpc_run_dfma_peak(int sm_count, void* stream, double* out_dev, int iters);
+int cmpc_run_dmma_peak(int sm_count, void* stream, double* out_dev, int iters);
 /* cmpc_frontend.cu: the caller of the path (updateMPCIfNeeded / solveDenseMPC / getMpcTable) on the device */
 int cmpc_launch_frontend(const void* cmds, unsigned char* records, void* results, float* f_ext, float* sim_time, int count,
                          int horizon, int rec_stride, float dt, float alpha, const float weights[12], void* stream);

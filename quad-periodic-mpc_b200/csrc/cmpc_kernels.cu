@@ -590,6 +590,29 @@ __global__ void __launch_bounds__(256) cmpc_dfma_peak_kernel(double* out, int it
   if (s == 123.456) out[0] = s;
 }
 
+// the same for the FP64 tensor pipe: sixteen independent DMMA m8n8k4 accumulators per warp (512 flops each)
+__global__ void __launch_bounds__(256) cmpc_dmma_peak_kernel(double* out, int iters, double seed) {
+  double c[16][2];
+#pragma unroll
+  for (int k = 0; k < 16; k++) { c[k][0] = seed + k; c[k][1] = seed - k; }
+  const double a = 0.999999 + 1e-9 * threadIdx.x, b = 1.0 / 4.0;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) s += c[k][0] + c[k][1];
+  if (s == 123.456) out[0] = s;
+}
+
+int cmpc_run_dmma_peak(int sm_count, void* stream, double* out_dev, int iters) {
+  cmpc_dmma_peak_kernel<<<sm_count * 4, 256, 0, (cudaStream_t)stream>>>(out_dev, iters, 1.0);
+  return (int)cudaGetLastError();
+}
+
 int cmpc_run_dfma_peak(int sm_count, void* stream, double* out_dev, int iters) {
   cmpc_dfma_peak_kernel<<<sm_count * 8, 256, 0, (cudaStream_t)stream>>>(out_dev, iters, 1.0);
   return (int)cudaGetLastError();
