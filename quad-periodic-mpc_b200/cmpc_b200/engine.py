@@ -26,6 +26,7 @@ _ENV_OPTIONS = {
     "CMPC_CHUNKS": ("chunks", int), "CMPC_SUBMIT_COPY": ("submit_copy", int), "CMPC_HOST_THREADS": ("host_threads", int),
     "CMPC_PATH": ("path_fused", lambda v: int(v == "fused")), "CMPC_DUAL": ("dual_generic", lambda v: int(v == "generic")),
     "CMPC_SWEEP": ("sweep_dmma", lambda v: int(v == "dmma")), "CMPC_EXP_SKIP_PACK": ("exp_skip_pack", lambda v: 1),
+    "CMPC_DUAL_TEAM": ("dual_team", int),
 }
 
 

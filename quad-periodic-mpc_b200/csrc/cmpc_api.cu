@@ -99,7 +99,7 @@ void build_adapt_tables(std::vector<double>& tw, std::vector<float>& gk) {
 constexpr int kMaxChunks = 8;
 constexpr int kMaxStreams = 8;
 constexpr int kRstateStride = 32 * 32;                                   // P of a 32-row working set, full rows
-constexpr int kRstate2Stride = CMPC_QCAP_MID * (CMPC_QCAP_MID + 1) / 2;  // P of a middle-tier working set, packed
+constexpr int kRstate2Stride = CMPC_QCAP_TEAM * (CMPC_QCAP_TEAM + 1) / 2;  // P of a team- / middle-tier working set, packed
 // control block of one chunk of a pipeline launch, zeroed by ONE memset per launch: work counters of the kernels,
 // overflow counts of the two capacity hand-overs, the hardest-first histogram, the SM arrival counters of the stagger
 constexpr int kCtlSched = 0, kCtlOvf = 4, kCtlOvf2 = 5, kCtlHist = 8, kCtlSlots = 8 + 64, kCtlInts = 8 + 64 + CMPC_SM_SLOTS;
@@ -186,6 +186,7 @@ struct PipePlan {
   int per_sm1 = 0, per_sm_inv = 0;
   int qcap1 = 0, fast = 0, per_sm_fast = 0, wpc1 = 0, per_sm2 = 0, wpc2 = 0, per_sm3 = 0;
   int qcap_mid = 0, wpc_mid = 0, per_sm_mid = 0;  // middle capacity tier (0: none)
+  int qcap_team = 0, per_sm_team = 0;             // CTA-per-instance tier (0: none)
 };
 
 }  // namespace
@@ -225,6 +226,7 @@ struct Knobs {
   int chunks = 0;         // "chunks": chunks of the end-to-end call (0: by size)
   int submit_copy = 0;    // "submit_copy": submit / wait hand the results to the copy engine
   int host_threads = 0;   // "host_threads": host workers of the end-to-end call (0: hardware)
+  int dual_team = 1;      // "dual_team": working sets beyond the first tier on the CTA-per-instance kernel (0: one warp per instance)
 };
 
 struct cmpc_batch {
@@ -575,6 +577,17 @@ int make_pipe_plan(const Knobs& kn, const CmpcParams& P, int qcap_pref, PipePlan
       pl.per_sm_mid = pm;
     }
   }
+  // the CTA-per-instance tier takes over what outgrows the first tier (it resumes from the working set and P handed over)
+  pl.qcap_team = 0;
+  if (kn.dual_team && fast && qcap1 < nmax) {
+    const int qt = std::min(nmax, CMPC_QCAP_TEAM);
+    const int pt = cmpc_dual_team_max_ctas_per_sm(nmax, cmpc_dual_team_smem_bytes(nmax, qt));
+    if (pt >= 1) {
+      pl.qcap_team = qt;
+      pl.per_sm_team = pt;
+      pl.qcap_mid = 0;
+    }
+  }
   pl.qcap1 = qcap1;
   pl.fast = fast ? 1 : 0;
   pl.wpc1 = wpc1;
@@ -730,6 +743,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       // the instances that outgrew the first tier: resumed at a middle capacity (three warps per SM instead of one for
       // the larger problems), the few that outgrow that too at full capacity
       const bool mid = pl.qcap_mid > 0 && pl.qcap_mid < nmax && fast && b->resume;
+      const bool team = pl.qcap_team > 0 && b->resume;
       Q.sched = ctl + kCtlSched + 2;
       Q.worklist = b->d_overflow[si];
       Q.count_ptr = ctl + kCtlOvf;
@@ -740,17 +754,25 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       Q.rstate_in_cap = Q.rstate_out_cap;
       Q.rstate_out = nullptr;
       Q.overflow_list = nullptr;
-      if (mid) {
-        Q.qcap = pl.qcap_mid;
-        Q.overflow_list = b->d_overflow2[si];
-        Q.overflow_count = ctl + kCtlOvf2;
-        Q.resume_out = b->d_resume2[si];
-        Q.rstate_out = b->d_rstate2[si];
-        Q.rstate_out_stride = kRstate2Stride;
-        Q.rstate_out_cap = b->rstate2_cap;
-        rc = cmpc_launch_dual(Q, pl.wpc_mid, std::min((cnt + pl.wpc_mid - 1) / pl.wpc_mid, b->sm_count * pl.per_sm_mid), st);
+      if (team || mid) {
+        const bool last_tier = team && pl.qcap_team >= nmax;
+        Q.qcap = team ? pl.qcap_team : pl.qcap_mid;
+        if (!last_tier) {
+          Q.overflow_list = b->d_overflow2[si];
+          Q.overflow_count = ctl + kCtlOvf2;
+          Q.resume_out = b->d_resume2[si];
+          Q.rstate_out = b->d_rstate2[si];
+          Q.rstate_out_stride = kRstate2Stride;
+          Q.rstate_out_cap = b->rstate2_cap;
+        }
+        if (team) rc = cmpc_launch_dual_team(Q, std::min(cnt, b->sm_count * pl.per_sm_team), st);
+        else rc = cmpc_launch_dual(Q, pl.wpc_mid, std::min((cnt + pl.wpc_mid - 1) / pl.wpc_mid, b->sm_count * pl.per_sm_mid), st);
         if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_dual_kernel (middle capacity) launch");
         b->launches++;
+        if (last_tier) {
+          if (int e = prof_end(CMPC_K_DUAL)) return e;
+          continue;
+        }
         Q.worklist = b->d_overflow2[si];
         Q.count_ptr = ctl + kCtlOvf2;
         Q.resume_in = b->d_resume2[si];
@@ -1399,7 +1421,7 @@ int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_output
 
 // Diagnostic / test switches.  Keys: nstreams, split, serial, lpt, resume, sweep_dmma, inv_stagger, traj_copy, cshape,
 // ws_mb, qcap1, dual_generic, wpc, no_mid_tier, path_fused, shape, host_pack, d2h_copy, chunks, submit_copy,
-// host_threads (and exp_skip_pack in a -DCMPC_EXPERIMENTS build).
+// host_threads, dual_team (and exp_skip_pack in a -DCMPC_EXPERIMENTS build).
 int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
   if (!b || !key) return fail_arg("cmpc_batch_set_option: null argument");
   CK(cudaSetDevice(b->device));
@@ -1427,6 +1449,7 @@ int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
   else if (k == "chunks") kn.chunks = std::max(0, value);
   else if (k == "submit_copy") kn.submit_copy = value != 0;
   else if (k == "host_threads") kn.host_threads = std::max(0, value);
+  else if (k == "dual_team") kn.dual_team = value != 0;
 #ifdef CMPC_EXPERIMENTS
   else if (k == "exp_skip_pack") b->exp_skip_pack = value != 0;
 #endif

@@ -8,7 +8,8 @@
 #define CMPC_MAX_FS 80 /* 4 * CMPC_MAX_HORIZON rounded up */
 #define CMPC_SM_SLOTS 1024 /* >= the largest %smid + 1 */
 #define CMPC_RESUME_INTS 34 /* q, iterations, up to 64 working-set rows as 16-bit ids */
-#define CMPC_QCAP_MID 56    /* middle capacity tier of the active-set kernel for reduced problems beyond 64 variables */
+#define CMPC_QCAP_MID 56    /* middle capacity tier of the one-warp active-set kernel (reduced problems beyond 64 variables; "dual_team" = 0) */
+#define CMPC_QCAP_TEAM 64   /* capacity of the CTA-per-instance active-set tier (cmpc_dual_team.cuh) */
 
 // ---------------------------------------------------------------------------
 // Instance record (HBM, one per MPC instance, 16-byte aligned, fetched with a
@@ -180,6 +181,9 @@ int cmpc_launch_dual_fast(const CmpcParams& P, int grid, void* stream);
 size_t cmpc_dual_smem_bytes_per_warp(int nmax, int qcap);
 int cmpc_dual_max_ctas_per_sm(int warps_per_cta, size_t smem);
 int cmpc_launch_dual(const CmpcParams& P, int warps_per_cta, int grid, void* stream);
+size_t cmpc_dual_team_smem_bytes(int nmax, int qcap);
+int cmpc_dual_team_max_ctas_per_sm(int nmax, size_t smem);
+int cmpc_launch_dual_team(const CmpcParams& P, int grid, void* stream);
 
 size_t cmpc_smem_bytes(int horizon, int nmax, int qcap, int shape, bool adapt);
 int cmpc_shape_threads(int shape);

@@ -33,6 +33,7 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 #include "cmpc_invert_mma.cuh"
 #include "cmpc_dual.cuh"
 #include "cmpc_dual_fast.cuh"
+#include "cmpc_dual_team.cuh"
 
 namespace {
 
@@ -280,6 +281,31 @@ int cmpc_launch_invert(const CmpcParams& P, int grid, void* stream) {
 #else
   return (int)cudaErrorInvalidDeviceFunction;
 #endif
+}
+
+// ---- CTA-per-instance tier of the dual active-set kernel (cmpc_dual_team.cuh): long working sets ----
+size_t cmpc_dual_team_smem_bytes(int nmax, int qcap) { return (size_t)make_tcarve(nmax, qcap).total; }
+namespace {
+template <int NT>
+int occ_team_t(size_t smem) {
+  int nb = 0;
+  if (smem_attr<cmpc_dual_team_kernel<NT>>(smem) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cmpc_dual_team_kernel<NT>, NT, smem) != cudaSuccess) return -1;
+  return nb;
+}
+template <int NT>
+int launch_team_t(const CmpcParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = smem_attr<cmpc_dual_team_kernel<NT>>(smem);
+  if (e != cudaSuccess) return (int)e;
+  cmpc_dual_team_kernel<NT><<<grid, NT, smem, st>>>(P);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+// four warps per instance up to 64 variables, eight beyond (one variable per thread in the z update either way)
+int cmpc_dual_team_max_ctas_per_sm(int nmax, size_t smem) { return nmax <= 64 ? occ_team_t<128>(smem) : occ_team_t<256>(smem); }
+int cmpc_launch_dual_team(const CmpcParams& P, int grid, void* stream) {
+  const size_t smem = cmpc_dual_team_smem_bytes(P.nmax, P.qcap);
+  return P.nmax <= 64 ? launch_team_t<128>(P, grid, smem, (cudaStream_t)stream) : launch_team_t<256>(P, grid, smem, (cudaStream_t)stream);
 }
 
 // ---- fast tier of the dual active-set kernel (cmpc_dual_fast.cuh): working sets of up to 32 rows ----

@@ -313,7 +313,8 @@ def test_every_kernel_path_agrees(built_lib, h, gaits, nseg, B):
     variants = [{}, {"CMPC_QCAP1": "4"}, {"CMPC_DUAL": "generic"}, {"CMPC_CSHAPE": "2"}, {"CMPC_SERIAL": "1"},
                 {"CMPC_LPT": "0"},                          # natural instance order instead of hardest first
                 {"CMPC_RESUME": "0"},                       # overflowed working sets restart instead of resuming
-                {"CMPC_QCAP1": "4", "CMPC_RESUME": "0"}, {"CMPC_QCAP1": "12"}, {"CMPC_NSTREAMS": "2"}]
+                {"CMPC_QCAP1": "4", "CMPC_RESUME": "0"}, {"CMPC_QCAP1": "12"}, {"CMPC_NSTREAMS": "2"},
+                {"CMPC_DUAL_TEAM": "0"}, {"CMPC_DUAL_TEAM": "0", "CMPC_QCAP1": "4"}]   # one warp per instance beyond the first tier
     for env in variants:
         res = _solve_env(inst, env)
         assert (res["status"] == ref["status"]).all(), env
