@@ -226,6 +226,7 @@ struct Knobs {
   int chunks = 0;         // "chunks": chunks of the end-to-end call (0: by size)
   int submit_copy = 0;    // "submit_copy": submit / wait hand the results to the copy engine
   int host_threads = 0;   // "host_threads": host workers of the end-to-end call (0: hardware)
+  int resume_p = 1;       // "resume_p": a working set handed to the next tier travels with its P (0: row ids only, P is bordered again)
   int dual_team = 1;      // "dual_team": working sets beyond the first tier on the CTA-per-instance kernel (0: one warp per instance)
 };
 
@@ -724,7 +725,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
         Q.resume_out = b->d_resume[si];
         Q.rstate_out = b->d_rstate[si];
         Q.rstate_out_stride = kRstateStride;
-        Q.rstate_out_cap = b->rstate_cap;
+        Q.rstate_out_cap = b->knobs.resume_p ? b->rstate_cap : 0;
       }
     } else {
       Q.overflow_list = nullptr;
@@ -763,7 +764,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
           Q.resume_out = b->d_resume2[si];
           Q.rstate_out = b->d_rstate2[si];
           Q.rstate_out_stride = kRstate2Stride;
-          Q.rstate_out_cap = b->rstate2_cap;
+          Q.rstate_out_cap = b->knobs.resume_p ? b->rstate2_cap : 0;
         }
         if (team) rc = cmpc_launch_dual_team(Q, std::min(cnt, b->sm_count * pl.per_sm_team), st);
         else rc = cmpc_launch_dual(Q, pl.wpc_mid, std::min((cnt + pl.wpc_mid - 1) / pl.wpc_mid, b->sm_count * pl.per_sm_mid), st);
@@ -1421,7 +1422,7 @@ int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_output
 
 // Diagnostic / test switches.  Keys: nstreams, split, serial, lpt, resume, sweep_dmma, inv_stagger, traj_copy, cshape,
 // ws_mb, qcap1, dual_generic, wpc, no_mid_tier, path_fused, shape, host_pack, d2h_copy, chunks, submit_copy,
-// host_threads, dual_team (and exp_skip_pack in a -DCMPC_EXPERIMENTS build).
+// host_threads, dual_team, resume_p (and exp_skip_pack in a -DCMPC_EXPERIMENTS build).
 int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
   if (!b || !key) return fail_arg("cmpc_batch_set_option: null argument");
   CK(cudaSetDevice(b->device));
@@ -1450,6 +1451,7 @@ int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
   else if (k == "submit_copy") kn.submit_copy = value != 0;
   else if (k == "host_threads") kn.host_threads = std::max(0, value);
   else if (k == "dual_team") kn.dual_team = value != 0;
+  else if (k == "resume_p") kn.resume_p = value != 0;
 #ifdef CMPC_EXPERIMENTS
   else if (k == "exp_skip_pack") b->exp_skip_pack = value != 0;
 #endif

@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
               for (int e = 0; e < NPL; e++) KN[kd * NS + lane + 32 * e] = KN[last * NS + lane + 32 * e];
             }
             // row and column `last` leave the matrix: zero them so that the padded loops keep reading zeros
-            Pm[last * PSQ + lane] = 0.0;
+            if (lane < PSQ) Pm[last * PSQ + lane] = 0.0;  // (a row is PSQ wide: with a small capacity PSQ < 32, and row
+                                                          //  qcap - 1 is the last one — lanes beyond it would write past P)
             if (lane < qcap) Pm[lane * PSQ + last] = 0.0;
             if (lane == last) { sact = -1; u = 0.0; }
           }

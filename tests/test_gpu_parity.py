@@ -323,6 +323,21 @@ def test_every_kernel_path_agrees(built_lib, h, gaits, nseg, B):
         assert (res["active"] == ref["active"]).all(), env
 
 
+def test_small_first_tier_with_a_drop_at_full_capacity(built_lib):
+    """A partial step (a row leaves the working set) while the first tier's working set is exactly full: with a
+    capacity below 28 rows the cleared slot's row used to be zeroed 32 entries wide — past the end of P when the slot
+    was the last row.  Instances 56 / 949 (capacity 8) and 2216 (capacity 16) of this batch take that path."""
+    h, B = 16, 2304
+    inst = synth.make_batch(2048 * 4, horizon=h, seed=1000, gaits=("trot", "bound", "pace", "gallop"), n_segment=10, spread=1.5)
+    inst = {k: (v[:B] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
+    ref = _solve_env(inst, {"CMPC_PATH": "fused"})
+    for env in ({"CMPC_QCAP1": "8"}, {"CMPC_QCAP1": "16"}, {"CMPC_QCAP1": "8", "CMPC_DUAL_TEAM": "0"}, {"CMPC_QCAP1": "5"}):
+        res = _solve_env(inst, env)
+        assert (res["status"] == ref["status"]).all(), env
+        assert np.abs(res["forces"] - ref["forces"]).max() <= 1e-7, env
+        assert (res["active"] == ref["active"]).all(), env
+
+
 def test_interleaved_uploads_and_solves_stay_ordered(built_lib):
     """Successive solve_range calls rotate through the engine's streams; uploads, marks and downloads
     must still see them in program order (a stream's first use grows its workspace mid-call)."""
