@@ -602,9 +602,10 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
   const int nmax = P.nmax;
   const PipePlan* plp = nullptr;
   // first-tier working-set capacity: 32 rows for one batch at a time (the shortest active-set kernel), 24 when
-  // batches are pipelined over the streams (ten instead of seven warps per SM; the ~1 % of instances beyond 24 rows
-  // are resumed by the any-capacity launch, off the critical path of the following batches) — measured, profiles/
-  const int qcap_pref = (b->throughput_mode && nmax < 64) ? 24 : 32;
+  // batches are pipelined over the streams (ten instead of seven warps per SM; the instances beyond 24 rows — ~1 % of
+  // a trot batch, most of a mixed-gait h = 16 batch — are resumed by the CTA-per-instance tier, off the critical path
+  // of the following batches) — measured, profiles/r2_qcap1_sweep.txt
+  const int qcap_pref = b->throughput_mode ? 24 : 32;
   for (const PipePlan& c : b->plans)
     if (c.nmax == nmax && c.h == P.horizon && c.adapt == (int)adapt && c.qcap_pref == qcap_pref) plp = &c;
   if (!plp) {
