@@ -47,8 +47,8 @@ SWEEP_TOTAL = 1 << 20
 METRIC = "cmpc_qp_solves_per_sec_h10_batched"
 L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (bytes), from the committed ncu --set full capture
-# (profiles/r1_s3_ncu_full_summary.txt; cold cache: ncu flushes L2 between kernels)
-NCU_TRAFFIC = {"assemble": 40.1e6, "invert": 97.2e6, "dual": 28.9e6, "fused": None}
+# (profiles/r2_ncu_full_summary.txt; cold cache: ncu flushes L2 between kernels)
+NCU_TRAFFIC = {"assemble": 43.1e6, "invert": 97.1e6, "dual": 29.3e6, "fused": None}
 
 
 WORKLOADS = {
@@ -400,7 +400,7 @@ def run_b200(args, rank, world, local_rank):
         dmma = engine.measure_dmma_peak(local_rank)
         step_ms = region_ms / args.steps
         names = {"assemble": "cmpc_assemble_mma_kernel", "invert": "cmpc_invert_ws_kernel",
-                 "dual": "cmpc_lpt_order_kernel + cmpc_dual_fast_kernel + cmpc_dual_kernel (resumed working sets beyond the first tier)", "fused": "cmpc_solve_kernel"}
+                 "dual": "cmpc_lpt_order_kernel + cmpc_dual_fast_kernel + cmpc_dual_team_kernel (working sets beyond the first tier, CTA per instance)", "fused": "cmpc_solve_kernel"}
         bounds = {"assemble": "latency / issue (FP64 FMA + shared memory)", "invert": "tensor (FP64 DMMA)",
                   "dual": "latency (dependent chain per active-set iteration)", "fused": "latency"}
         peak_of = {"assemble": fp64, "invert": dmma, "dual": fp64, "fused": fp64}

@@ -18,5 +18,5 @@ for f in "$CSRC"/*.cu; do
   if [ $stale = 1 ]; then (cd "$CSRC" && nvcc $FLAGS -c "$f" -o "$o") & pids+=($!); fi
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -o "$ROOT/quad-periodic-mpc_b200/libcmpc_b200.so" "$OBJ"/*.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$ROOT/quad-periodic-mpc_b200/libcmpc_b200.so" "$OBJ"/*.o
 echo built
