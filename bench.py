@@ -206,7 +206,10 @@ def run_reference(args, rank, world):
 def pin_rank_to_cores(local_rank, world):
     """N ranks on one host: give every rank its own slice of the cores this process may use, so the eight enqueue
     threads (and each engine's host workers) do not migrate across each other."""
-    if world <= 1:
+    # measured on the 8-GPU box (32 cores, one NUMA node; profiles/r2_e2e_scale_n8.txt): four cores per rank are too few
+    # for a rank's enqueue thread plus the CUDA runtime's own threads — 7.84 M solves/s per GPU pinned against 8.50 M
+    # unpinned — so pinning is opt-in
+    if world <= 1 or os.environ.get("CMPC_BENCH_PIN", "0") != "1":
         return None
     cores = sorted(os.sched_getaffinity(0))
     per = max(1, len(cores) // world)
