@@ -29,50 +29,55 @@ __device__ __forceinline__ void estimate_disturbance_impl(const CmpcParams& P, i
   const float* wd = P.win_d + (size_t)inst * N;
   const float* wt = P.win_t + (size_t)inst * N;
   // band-pass: difference of the two blurs, edge samples repeated (SolverMPC.cpp:425-434).  The window is staged with
-  // its edges already repeated (no index clamping in the tap loops) next to the taps as doubles; a thread forms four
-  // consecutive outputs, so a tap and a sample are fetched once per four FMAs.  Every output is still the same
-  // left-to-right FMA chain over its taps.
+  // its edges already repeated by the larger radius (no index clamping in the tap loop; the clamp does not depend on
+  // the radius, so the narrow blur reads the same staged samples) and the two normalised kernels are folded into ONE
+  // set of 2 R2 + 1 taps, c[j] = g7[j] - g27[j] (g7 zero beyond its radius): 65 k FMAs per instance instead of 82 k.
+  // A thread forms FOUR consecutive outputs (a tap and a sample are fetched once per four FMAs): 100 of the CTA's 128
+  // threads work, on three of the four SM sub-partitions — eight outputs per thread halve the loads but leave the whole
+  // stage to two warps, i.e. to the FP64 pipes of two sub-partitions (measured: no faster).
   constexpr int R1 = CMPC_GK_R1, R2 = CMPC_GK_R2;
-  double* xe = work + N;                  // [N + 2 R2], overlays tre / tim (dead until the DFT)
-  double* tap1 = work + 2 * N + 2 * R2;   // [2 R1 + 1]
-  double* tap2 = tap1 + 2 * R1 + 1;       // [2 R2 + 1]
-  static_assert(3 * CMPC_ADAPT_WINDOW >= 2 * CMPC_ADAPT_WINDOW + 2 * CMPC_GK_R2 + CMPC_GK_TOTAL, "estimator scratch");
-  for (int i = tid; i < N + 2 * R2; i += NT) xe[i] = (double)wd[min(max(i - R2, 0), N - 1)];
-  for (int i = tid; i < CMPC_GK_TOTAL; i += NT) tap1[i] = (double)__ldg(P.gk + i);
+  // thread o reads samples 4 o + t: a stride of four doubles would put a half-warp on four banks, so the staged
+  // window is SKEWED by one slot per four samples (sample e at e + e / 4: lane stride five doubles, conflict-free)
+  constexpr int NE = N + 2 * R2, NES = NE + NE / 4 + 1;
+  double* xe = work + N;                  // [NES], overlays tre / tim (dead until the DFT)
+  double* tapc = work + 3 * N + 40;       // [2 R2 + 1], behind the roots of unity
+  static_assert(CMPC_ADAPT_WINDOW + NES <= 3 * CMPC_ADAPT_WINDOW && 3 * CMPC_ADAPT_WINDOW + 40 + 2 * CMPC_GK_R2 + 1 <= CMPC_ADAPT_SCRATCH, "estimator scratch");
+  for (int i = tid; i < NE; i += NT) xe[i + (i >> 2)] = (double)wd[min(max(i - R2, 0), N - 1)];
+  for (int j = tid; j <= 2 * R2; j += NT) {
+    const int j1 = j - (R2 - R1);  // index into the narrow kernel
+    const double g1 = (j1 >= 0 && j1 <= 2 * R1) ? (double)__ldg(P.gk + j1) : 0.0;
+    tapc[j] = g1 - (double)__ldg(P.gk + (2 * R1 + 1) + j);
+  }
   double* w20 = work + 3 * N;             // W20^m = W400^(20 m), m = 0..19: (cos, -sin) pairs for both DFT passes
   for (int i = tid; i < 40; i += NT) w20[i] = __ldg(P.twiddle + 2 * (20 * (i >> 1)) + (i & 1));
   sync();
+  static_assert(CMPC_ADAPT_WINDOW % 4 == 0, "four outputs per thread");
   for (int o = tid; o < N / 4; o += NT) {
-    const int i0 = 4 * o;
-    double a2[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
-    {
-      const double* x = xe + i0;  // output i0 + c, tap j reads sample index (i0 + c) + j - R2, i.e. xe[i0 + c + j]
-      double x0 = x[0], x1 = x[1], x2 = x[2];
-#pragma unroll 4
-      for (int j = 0; j <= 2 * R2; j++) {
-        const double x3 = x[j + 3], g = tap2[j];
-        a2[0] = fma(x0, g, a2[0]);
-        a2[1] = fma(x1, g, a2[1]);
-        a2[2] = fma(x2, g, a2[2]);
-        a2[3] = fma(x3, g, a2[3]);
-        x0 = x1; x1 = x2; x2 = x3;
-      }
-    }
-    {
-      const double* x = xe + i0 + (R2 - R1);
-      double x0 = x[0], x1 = x[1], x2 = x[2];
-#pragma unroll 4
-      for (int j = 0; j <= 2 * R1; j++) {
-        const double x3 = x[j + 3], g = tap1[j];
-        a1[0] = fma(x0, g, a1[0]);
-        a1[1] = fma(x1, g, a1[1]);
-        a1[2] = fma(x2, g, a1[2]);
-        a1[3] = fma(x3, g, a1[3]);
-        x0 = x1; x1 = x2; x2 = x3;
+    // output 4 o + c, tap j reads sample (4 o + c) + j - R2 of the window, i.e. staged sample 4 o + c + j
+    const double* x = xe + 5 * o;  // staged sample 4 o + t sits at 5 o + t + t / 4
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    double xr[4];
+#pragma unroll
+    for (int c = 0; c < 3; c++) xr[c] = x[c];
+    constexpr int NTAP = 2 * R2 + 1;
+#pragma unroll 2
+    for (int jb = 0; jb < NTAP; jb += 4) {
+      const double* xb = x + 5 * (jb >> 2);
+#pragma unroll
+      for (int uu = 0; uu < 4; uu++) {
+        if (jb + uu < NTAP) {
+          // sample t = jb + uu + 3: slot 5 (jb / 4) + (uu + 3) + (uu + 3) / 4
+          xr[3] = xb[uu + 3 + ((uu + 3) >> 2)];
+          const double g = tapc[jb + uu];
+#pragma unroll
+          for (int c = 0; c < 4; c++) a[c] = fma(xr[c], g, a[c]);
+#pragma unroll
+          for (int c = 0; c < 3; c++) xr[c] = xr[c + 1];
+        }
       }
     }
 #pragma unroll
-    for (int c = 0; c < 4; c++) y[i0 + c] = a1[c] - a2[c];
+    for (int c = 0; c < 4; c++) y[4 * o + c] = a[c];
   }
   sync();
   // mean and (population) standard deviation

@@ -48,8 +48,9 @@ static inline int cmpc_rec_stride(int h) {
 #define CMPC_GK_R1 21
 #define CMPC_GK_R2 81
 #define CMPC_GK_TOTAL (2 * CMPC_GK_R1 + 1 + 2 * CMPC_GK_R2 + 1)
-/* shared-memory scratch of the estimator stage (doubles): three 400-sample arrays + the twenty 20th roots of unity */
-#define CMPC_ADAPT_SCRATCH (3 * CMPC_ADAPT_WINDOW + 40)
+/* shared-memory scratch of the estimator stage (doubles): three 400-sample arrays, the twenty 20th roots of unity,
+ * the folded band-pass taps */
+#define CMPC_ADAPT_SCRATCH (3 * CMPC_ADAPT_WINDOW + 40 + 2 * CMPC_GK_R2 + 2)
 
 struct CmpcParams {
   int horizon;

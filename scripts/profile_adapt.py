@@ -12,3 +12,13 @@ for _ in range(3):
     b.solve()
 b.sync()
 print("kernel ms", b.last_solve_ms())
+# per-phase cycles of the adaptive assembly kernel (thread-0 clocks summed over CTAs)
+b.enable_phase_clocks(True)
+for _ in range(4):
+    b.solve(); b.sync()
+cyc = b.phase_cycles()
+tot = sum(cyc.values())
+for k, v in cyc.items():
+    if v:
+        print("   %-12s %5.1f%%  %8.0f cyc/instance" % (k, 100.0 * v / tot, v / (B * 4)))
+print("class times (ms):", b.profile_range(0, B))
