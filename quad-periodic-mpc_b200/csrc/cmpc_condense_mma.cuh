@@ -56,11 +56,11 @@ __host__ __device__ inline MCarve make_mcarve(int h, int rec_stride, bool adapt)
   c.g = o; o += 8 * MMA_NPAD;
   c.pq = o; o += 16 * MMA_PQ;
   c.xtab = o; o += align16(32 * h * h);  // x_drag couplings: XA[ab], X0[ab], XA[ba], and a table of zeros
-  // pan, mm, dv are contiguous: the estimator (3 x 400 doubles) borrows them
-  c.pan = o; o += 8 * 8 * MMA_PS;
-  c.mm = o; o += 8 * 8 * MMA_PS;
-  c.dv = o; o += 8 * 64;
-  if (adapt && o - c.pan < 8 * CMPC_ADAPT_SCRATCH) o = c.pan + 8 * CMPC_ADAPT_SCRATCH;
+  // scratch of the estimator stage (adaptive launches only)
+  c.pan = o;
+  c.mm = o;
+  c.dv = o;
+  if (adapt) o = c.pan + 8 * CMPC_ADAPT_SCRATCH;
   c.red = o; o += 512;
   c.total = o;
   return c;
