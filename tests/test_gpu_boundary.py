@@ -236,3 +236,30 @@ def test_commands_reject_a_changed_robot_count(built_lib):
     b.reset_history()
     b.solve_commands(cmds[:32])
     b.close()
+
+
+def test_sharded_engine_calls_cover_the_batch_once(built_lib):
+    """What `bench.py --gpus N` / `--mode sweep1m` do, on one device: the batch is cut with bench.shard_bounds, every shard is
+    solved by its own engine handle (as a rank would), and the concatenated results equal the unsharded call bit for bit
+    (instances are independent: no collective, nothing shared between the shards)."""
+    import bench
+    h, B, world = 10, 5000, 3                      # a ragged split: 1667 + 1667 + 1666
+    inst = synth.make_batch(B, horizon=h, seed=61, spread=1.5)
+    whole = engine.Batch(B)
+    whole.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+    want = whole.solve_host(inst)
+    whole.close()
+    covered = np.zeros(B, dtype=np.int32)
+    parts = []
+    for rank in range(world):
+        lo, hi = bench.shard_bounds(B, rank, world)
+        covered[lo:hi] += 1
+        shard = {k: (v[lo:hi] if isinstance(v, np.ndarray) else v) for k, v in inst.items()}
+        b = engine.Batch(hi - lo)
+        b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+        parts.append(b.solve_host(shard))
+        b.close()
+    assert (covered == 1).all()
+    for key in ("forces", "objective", "status", "iterations", "active"):
+        got = np.concatenate([p[key] for p in parts])
+        assert (got == want[key]).all(), key
