@@ -1,5 +1,6 @@
+"""The synchronous end-to-end call (cmpc_batch_solve_bound, 4096 trot, pinned arrays) against WHICH result arrays are read back:\nhow much of the call the result bytes cost.  usage: e2e_outputs.py"""
 import os, sys, time
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "quad-periodic-mpc_b200")); sys.path.insert(0, ROOT)
 import numpy as np, ctypes as C
 from cmpc_b200 import synth, engine
