@@ -7,49 +7,56 @@ import numpy as np
 from cmpc_b200 import synth, engine
 from oracle import cmpc_oracle as O
 
-assert O.available(), "oracle/_ref did not travel"
-threads = len(os.sched_getaffinity(0))
-rng = np.random.default_rng(int(os.environ.get("FUZZ_SEED", "20261018")))
-names = list(synth.GAITS)
-rounds = int(os.environ.get("FUZZ_ROUNDS", "60"))
-worst, bad, total = 0.0, 0, 0
-t0 = time.time()
-for it in range(rounds):
-    h = int(rng.integers(1, 20))
-    k = int(rng.integers(1, 4))
-    gaits = tuple(rng.choice(names, size=k, replace=False))
-    nseg = int(rng.choice([h, 10, 16])) if rng.random() < 0.5 else None
-    spread = float(rng.choice([0.5, 1.0, 1.5, 2.5]))
-    B = int(rng.choice([1, 2, 3, 17, 64, 257, 1024]))
-    inst = synth.make_batch(B, horizon=h, seed=int(rng.integers(1 << 30)), gaits=gaits, n_segment=nseg, spread=spread)
-    b = engine.Batch(B); b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
-    res = b.solve_host(inst)
-    b.upload(inst); b.solve(); res_r = b.download(); b.close()
-    st = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"])
-    ups = (O.Update * B)(*[O.make_update(inst, i, h) for i in range(B)])
-    ref, ok = O.solve_batch(st, ups, threads, use_float=False)
-    good = ok != 0
-    tol = 1e-3 + 1e-5 * np.abs(ref)
-    err = np.maximum(np.abs(res["forces"] - ref), np.abs(res_r["forces"] - ref))
-    fails = (~(err <= tol).all(1)) & good
-    capped = 0
-    if fails.any():
-        # the reference caps qpOASES at nWSR = 100 (SolverMPC.cpp:955) and then returns whatever it has; lift the cap
-        # for the instances that disagree before calling them failures
-        st2 = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"], nwsr=5000)
-        for i in np.flatnonzero(fails):
-            r2 = O.solve(st2, O.make_update(inst, int(i), h))
-            e2 = np.maximum(np.abs(res["forces"][i] - r2["x"]), np.abs(res_r["forces"][i] - r2["x"]))
-            if (e2 <= 1e-3 + 1e-5 * np.abs(r2["x"])).all():
-                fails[i] = False
-                err[i] = e2
-                capped += 1
-    nstat = int(((res["status"] > 1) | (res_r["status"] > 1)).sum())
-    n = 3 * int(inst["gait"].astype(bool).sum(1).max())
-    total += int(good.sum()); bad += int(fails.sum()) + nstat
-    if good.any():
-        worst = max(worst, float(err[good].max()))
-    print("h=%2d gaits=%-28s nseg=%-4s spread=%.1f B=%4d nmax=%3d: qpOASES solved %4d, out of tolerance %d, bad status %d, max |dF| %.2e%s"
-          % (h, ",".join(gaits), nseg, spread, B, n, good.sum(), fails.sum(), nstat, err[good].max() if good.any() else 0.0,
-             (" (%d agreed only once qpOASES' nWSR cap of 100 was lifted)" % capped) if capped else ""), flush=True)
-print("FUZZ: %d instances checked in %d configurations, %d failures, worst |dF| %.2e N, %.0f s" % (total, rounds, bad, worst, time.time() - t0))
+def run(rounds=60, seed=20261018, verbose=True):
+    """Returns (instances checked, failures, worst |dF|)."""
+    assert O.available(), "oracle/_ref did not travel"
+    threads = len(os.sched_getaffinity(0))
+    rng = np.random.default_rng(seed)
+    names = list(synth.GAITS)
+    worst, bad, total = 0.0, 0, 0
+    t0 = time.time()
+    for it in range(rounds):
+        h = int(rng.integers(1, 20))
+        k = int(rng.integers(1, 4))
+        gaits = tuple(rng.choice(names, size=k, replace=False))
+        nseg = int(rng.choice([h, 10, 16])) if rng.random() < 0.5 else None
+        spread = float(rng.choice([0.5, 1.0, 1.5, 2.5]))
+        B = int(rng.choice([1, 2, 3, 17, 64, 257, 1024]))
+        inst = synth.make_batch(B, horizon=h, seed=int(rng.integers(1 << 30)), gaits=gaits, n_segment=nseg, spread=spread)
+        b = engine.Batch(B); b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+        res = b.solve_host(inst)
+        b.upload(inst); b.solve(); res_r = b.download(); b.close()
+        st = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"])
+        ups = (O.Update * B)(*[O.make_update(inst, i, h) for i in range(B)])
+        ref, ok = O.solve_batch(st, ups, threads, use_float=False)
+        good = ok != 0
+        tol = 1e-3 + 1e-5 * np.abs(ref)
+        err = np.maximum(np.abs(res["forces"] - ref), np.abs(res_r["forces"] - ref))
+        fails = (~(err <= tol).all(1)) & good
+        capped = 0
+        if fails.any():
+            # the reference caps qpOASES at nWSR = 100 (SolverMPC.cpp:955) and then returns whatever it has; lift the cap
+            # for the instances that disagree before calling them failures
+            st2 = O.make_setup(inst["dt"], h, inst["mu"], inst["f_max"], nwsr=5000)
+            for i in np.flatnonzero(fails):
+                r2 = O.solve(st2, O.make_update(inst, int(i), h))
+                e2 = np.maximum(np.abs(res["forces"][i] - r2["x"]), np.abs(res_r["forces"][i] - r2["x"]))
+                if (e2 <= 1e-3 + 1e-5 * np.abs(r2["x"])).all():
+                    fails[i] = False
+                    err[i] = e2
+                    capped += 1
+        nstat = int(((res["status"] > 1) | (res_r["status"] > 1)).sum())
+        n = 3 * int(inst["gait"].astype(bool).sum(1).max())
+        total += int(good.sum()); bad += int(fails.sum()) + nstat
+        if good.any():
+            worst = max(worst, float(err[good].max()))
+        if verbose: print("h=%2d gaits=%-28s nseg=%-4s spread=%.1f B=%4d nmax=%3d: qpOASES solved %4d, out of tolerance %d, bad status %d, max |dF| %.2e%s"
+              % (h, ",".join(gaits), nseg, spread, B, n, good.sum(), fails.sum(), nstat, err[good].max() if good.any() else 0.0,
+                 (" (%d agreed only once qpOASES' nWSR cap of 100 was lifted)" % capped) if capped else ""), flush=True)
+    if verbose:
+        print("FUZZ: %d instances checked in %d configurations, %d failures, worst |dF| %.2e N, %.0f s" % (total, rounds, bad, worst, time.time() - t0))
+    return total, bad, worst
+
+
+if __name__ == "__main__":
+    run(int(os.environ.get("FUZZ_ROUNDS", "60")), int(os.environ.get("FUZZ_SEED", "20261018")))
