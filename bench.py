@@ -319,9 +319,12 @@ def run_b200(args, rank, world, local_rank):
     # ---- the same call with D batches in flight (submit / wait): step k is submitted before step k-D+1 is waited for ----
     def in_flight(depth):
         pipe = []
+        # from four batches in flight on, the copy engine carries the results better than the kernels' own PCIe stores
+        # (profiles/r2_submit_copy.txt): the documented option for deep pipelines
+        opts = {"submit_copy": 1} if depth >= 4 else {}
         for k in range(depth):
             sk = {kk: (v[(k + 1) * BATCH:(k + 2) * BATCH] if isinstance(v, np.ndarray) else v) for kk, v in inst.items()}
-            bk = engine.Batch(BATCH, device=local_rank)
+            bk = engine.Batch(BATCH, device=local_rank, options=opts)
             bk.setup(DT, h, inst["mu"], inst["f_max"])
             bk.prepare_host(sk, want_active=True)
             pipe.append(bk)
@@ -354,7 +357,7 @@ def run_b200(args, rank, world, local_rank):
                                           "still reads its inputs from and writes its results to pinned host arrays"}
         extra["deep_in_flight"] = {"value": deep_units / deep_seconds, "unit": "solves/s", "batches_in_flight": deep,
                                    "ms_per_step": 1e3 * deep_seconds / args.steps,
-                                   "call": "the same submit / wait calls on %d engine handles (scripts/e2e_depth.py)" % deep}
+                                   "call": "the same submit / wait calls on %d engine handles, option submit_copy = 1: results by the copy engine (scripts/e2e_depth.py, profiles/r2_submit_copy.txt)" % deep}
         # ---- end to end one level up: the controller-level call (updateMPCIfNeeded / solveDenseMPC on the device) ----
         cmds = synth.make_commands(BATCH, engine.COMMAND_DTYPE, horizon=h, gaits=("trot",), seed=2000 + rank)
         cres = np.zeros(BATCH, dtype=engine.RESULT_DTYPE)
