@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#ifdef CMPC_CANARY
+#include <cstdio>
+#endif
 
 #include "cmpc_device.h"
 
@@ -41,6 +44,34 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
+// Shared-memory canaries (a -DCMPC_CANARY build only; compute-sanitizer is closed on this pool): every region of a
+// kernel's shared-memory carve is followed by 64 guard bytes that the kernel fills when it starts and checks when it
+// ends.  A write past the end of a region — the class of the first-tier defect of round 1 — trips the check: the kernel
+// prints the region and traps, so the test run under this build fails.
+// ---------------------------------------------------------------------------
+#ifdef CMPC_CANARY
+#define CMPC_CANARY_FIELDS int guard[24]; int nguard;
+#define CMPC_GUARD_INIT(c) (c).nguard = 0
+#define CMPC_GUARD(o, c) do { (o) = ((o) + 15) & ~15; (c).guard[(c).nguard++] = (o); (o) += 64; } while (0)
+__device__ __forceinline__ void canary_fill(unsigned char* base, const int* guard, int n, int tid, int nt) {
+  for (int g = 0; g < n; g++)
+    for (int i = tid; i < 16; i += nt) reinterpret_cast<unsigned*>(base + guard[g])[i] = 0xC0FFEE00u + (unsigned)g;
+}
+__device__ __forceinline__ void canary_check(const unsigned char* base, const int* guard, int n, int tid, int nt, const char* kernel) {
+  for (int g = 0; g < n; g++)
+    for (int i = tid; i < 16; i += nt)
+      if (reinterpret_cast<const unsigned*>(base + guard[g])[i] != 0xC0FFEE00u + (unsigned)g) {
+        printf("CMPC_CANARY: %s wrote past the end of shared-memory region %d (guard word %d)\n", kernel, g, i);
+        __trap();
+      }
+}
+#else
+#define CMPC_CANARY_FIELDS
+#define CMPC_GUARD_INIT(c)
+#define CMPC_GUARD(o, c)
+#endif
 
 // ---------------------------------------------------------------------------
 // block reductions

@@ -21,27 +21,44 @@ namespace {
 
 struct DCarve {
   int x, kn, z, s, u, d, r, col, KN, Pp, act, isact, fs, gv, fsinv, total;
+  CMPC_CANARY_FIELDS
 };
 
 __host__ __device__ inline DCarve make_dcarve(int nmax, int qcap) {
   DCarve c;
   int o = 0;
+  CMPC_GUARD_INIT(c);
   const int m = 5 * (nmax / 3);
   c.x = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.kn = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.z = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.s = o; o += align16(8 * m);
+  CMPC_GUARD(o, c);
   c.u = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.d = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.r = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.col = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.KN = o; o += align16(8 * qcap * nmax);
+  CMPC_GUARD(o, c);
   c.Pp = o; o += align16(8 * ((qcap + 1) * (qcap + 2) / 2));
+  CMPC_GUARD(o, c);
   c.act = o; o += align16(2 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.isact = o; o += align16(m);
+  CMPC_GUARD(o, c);
   c.fs = o; o += align16(CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.gv = o; o += align16(CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.fsinv = o; o += align16(CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.total = o;
   return c;
 }
@@ -97,6 +114,10 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
   const int count = P.count_ptr ? min(*P.count_ptr, P.count) : P.count;
   const double mu_inv = P.mu_inv;
   double flops_acc = 0.0;
+#ifdef CMPC_CANARY
+  canary_fill(base, cv.guard, cv.nguard, lane, 32);
+  __syncwarp();
+#endif
 
   while (true) {
     int slot_i = 0;
@@ -438,5 +459,9 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_kernel(const __grid_consta
     }
     __syncwarp();
   }
+#ifdef CMPC_CANARY
+  __syncwarp();
+  canary_check(base, cv.guard, cv.nguard, lane, 32, "cmpc_dual_kernel");
+#endif
   if (lane == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_DUAL, (unsigned long long)flops_acc);
 }

@@ -17,20 +17,30 @@ namespace {
 
 struct FCarve {
   int kn, z, d, r, P, KN, misc, ostage, total;
+  CMPC_CANARY_FIELDS
 };
 
 __host__ __device__ inline FCarve make_fcarve(int npl, int qcap) {
   FCarve c;
   int o = 0;
+  CMPC_GUARD_INIT(c);
   c.kn = o; o += 8 * 32 * npl;
+  CMPC_GUARD(o, c);
   c.z = o; o += 8 * 32 * npl;
+  CMPC_GUARD(o, c);
   c.d = o; o += 8 * 40;
+  CMPC_GUARD(o, c);
   c.r = o; o += 8 * 40;
+  CMPC_GUARD(o, c);
   c.P = o; o += align16(8 * (qcap * ((qcap + 4) | 1) + 8));
+  CMPC_GUARD(o, c);
   c.KN = o; o += 8 * (qcap + 4) * 32 * npl;
+  CMPC_GUARD(o, c);
   c.misc = o; o += 3 * CMPC_MAX_FS + 16;  // fs, gv, fsinv bytes
+  CMPC_GUARD(o, c);
   o = align16(o);
   c.ostage = o; o += 20 * CMPC_MAX_HORIZON + 4;  // activity bytes of one instance, staged for word-wide stores
+  CMPC_GUARD(o, c);
   c.total = align16(o);
   return c;
 }
@@ -91,6 +101,9 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
   const int count = P.count_ptr ? min(*P.count_ptr, P.count) : P.count;
   const double mu_inv = P.mu_inv;
   double flops_acc = 0.0;
+#ifdef CMPC_CANARY
+  canary_fill(base, cv.guard, cv.nguard, lane, 32);
+#endif
   for (int i = lane; i < qcap * PSQ + 8; i += 32) Pm[i] = 0.0;  // the unrolled loops read (finite, zero-weighted) padding
   for (int i = lane; i < (qcap + 4) * NS; i += 32) KN[i] = 0.0;
   for (int i = lane; i < 40; i += 32) { dvec[i] = 0.0; rvec[i] = 0.0; }
@@ -357,7 +370,11 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
               for (int e = 0; e < NPL; e++) KN[kd * NS + lane + 32 * e] = KN[last * NS + lane + 32 * e];
             }
             // row and column `last` leave the matrix: zero them so that the padded loops keep reading zeros
-            if (lane < PSQ) Pm[last * PSQ + lane] = 0.0;  // (a row is PSQ wide: with a small capacity PSQ < 32, and row
+#ifdef CMPC_CANARY_SELFTEST  /* the round-1 defect, to prove that the canaries see it */
+            Pm[last * PSQ + lane] = 0.0;
+#else
+            if (lane < PSQ) Pm[last * PSQ + lane] = 0.0;
+#endif  // (a row is PSQ wide: with a small capacity PSQ < 32, and row
                                                           //  qcap - 1 is the last one — lanes beyond it would write past P)
             if (lane < qcap) Pm[lane * PSQ + last] = 0.0;
             if (lane == last) { sact = -1; u = 0.0; }
@@ -474,5 +491,9 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
       tclk = now;
     }
   }
+#ifdef CMPC_CANARY
+  __syncwarp();
+  canary_check(base, cv.guard, cv.nguard, lane, 32, "cmpc_dual_fast_kernel");
+#endif
   if (lane == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_DUAL, (unsigned long long)flops_acc);
 }

@@ -23,30 +23,49 @@ namespace {
 
 struct TCarve {
   int x, kn, z, s, u, d, r, col, KN, Pm, act, isact, fs, gv, fsinv, red, bc, total, psq;
+  CMPC_CANARY_FIELDS
 };
 
 __host__ __device__ inline TCarve make_tcarve(int nmax, int qcap) {
   TCarve c;
   int o = 0;
+  CMPC_GUARD_INIT(c);
   const int m = 5 * (nmax / 3);
   c.psq = (qcap + 1) | 1;
   c.x = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.kn = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.z = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.s = o; o += align16(8 * m);
+  CMPC_GUARD(o, c);
   c.u = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.d = o; o += align16(8 * (qcap + 4));
+  CMPC_GUARD(o, c);
   c.r = o; o += align16(8 * (qcap + 4));
+  CMPC_GUARD(o, c);
   c.col = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.KN = o; o += align16(8 * qcap * nmax);
+  CMPC_GUARD(o, c);
   c.Pm = o; o += align16(8 * (qcap + 1) * c.psq);
+  CMPC_GUARD(o, c);
   c.act = o; o += align16(2 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.isact = o; o += align16(m);
+  CMPC_GUARD(o, c);
   c.fs = o; o += align16(CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.gv = o; o += align16(CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.fsinv = o; o += align16(CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.red = o; o += 8 * 48;
+  CMPC_GUARD(o, c);
   c.bc = o; o += 64;
+  CMPC_GUARD(o, c);
   c.total = o;
   return c;
 }
@@ -82,6 +101,9 @@ __global__ void __launch_bounds__(NT) cmpc_dual_team_kernel(const __grid_constan
   const int count = P.count_ptr ? min(*P.count_ptr, P.count) : P.count;
   const double mu_inv = P.mu_inv;
   double flops_acc = 0.0;
+#ifdef CMPC_CANARY
+  canary_fill(smem, cv.guard, cv.nguard, tid, NT);
+#endif
 
   while (true) {
     __syncthreads();  // the previous instance's arrays (and bc) are free
@@ -514,5 +536,9 @@ __global__ void __launch_bounds__(NT) cmpc_dual_team_kernel(const __grid_constan
       }
     }
   }
+#ifdef CMPC_CANARY
+  __syncthreads();
+  canary_check(smem, cv.guard, cv.nguard, tid, NT, "cmpc_dual_team_kernel");
+#endif
   if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_DUAL, (unsigned long long)flops_acc);
 }

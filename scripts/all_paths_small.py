@@ -21,3 +21,10 @@ for tag, h, gaits, nseg, B, spread in (("trot10", 10, ("trot",), None, 300, 2.0)
             b.solve_commands(c)
     print(tag, "ok, status", np.unique(res["status"]), "iters max", res["iterations"].max(), flush=True)
     b.close()
+    # the capacity tiers behind a small first tier: CTA-per-instance tier, one-warp tiers, hand-over with and without P
+    for opts in ({"qcap1": 8}, {"qcap1": 8, "dual_team": 0}, {"qcap1": 5, "resume_p": 0}, {"qcap1": 6, "resume": 0}, {"path_fused": 1}):
+        b = engine.Batch(B, options=opts); b.setup(inst["dt"], h, inst["mu"], inst["f_max"])
+        r = b.solve_host(inst)
+        assert np.abs(r["forces"] - res["forces"]).max() <= 1e-7, (tag, opts)
+        b.close()
+    print(tag, "tiers ok", flush=True)
