@@ -52,9 +52,6 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // prints the region and traps, so the test run under this build fails.
 // ---------------------------------------------------------------------------
 #ifdef CMPC_CANARY
-#define CMPC_CANARY_FIELDS int guard[24]; int nguard;
-#define CMPC_GUARD_INIT(c) (c).nguard = 0
-#define CMPC_GUARD(o, c) do { (o) = ((o) + 15) & ~15; (c).guard[(c).nguard++] = (o); (o) += 64; } while (0)
 __device__ __forceinline__ void canary_fill(unsigned char* base, const int* guard, int n, int tid, int nt) {
   for (int g = 0; g < n; g++)
     for (int i = tid; i < 16; i += nt) reinterpret_cast<unsigned*>(base + guard[g])[i] = 0xC0FFEE00u + (unsigned)g;
@@ -67,10 +64,6 @@ __device__ __forceinline__ void canary_check(const unsigned char* base, const in
         __trap();
       }
 }
-#else
-#define CMPC_CANARY_FIELDS
-#define CMPC_GUARD_INIT(c)
-#define CMPC_GUARD(o, c)
 #endif
 
 // ---------------------------------------------------------------------------

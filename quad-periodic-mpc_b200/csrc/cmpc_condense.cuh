@@ -35,30 +35,47 @@ using CShape128 = CShape<16, 32, 4, 1>;  // n <= 128: 256 threads, 16x4 tiles
 
 struct CCarve {
   int rec0, rec1, bars, sig, small, evec, agg, fs, fsinv, g, hs, pan, mm, dinv, red, total;
+  CMPC_CANARY_FIELDS
 };
 
 __host__ __device__ inline CCarve make_ccarve(int h, int nmax, int rec_stride, int npad, bool adapt) {
   CCarve c;
   int o = 0;
+  CMPC_GUARD_INIT(c);
   c.rec0 = o; o += align16(rec_stride);
+  CMPC_GUARD(o, c);
   c.rec1 = o; o += align16(rec_stride);
+  CMPC_GUARD(o, c);
   c.bars = o; o += 16;
+  CMPC_GUARD(o, c);
   c.sig = o; o += align16(8 * CMPC_SIG_COUNT * h * h);
+  CMPC_GUARD(o, c);
   c.small = o; o += align16(8 * (36 + 36 + 144 + 144 + 16));  // W, RW, PT, PO, scalars
+  CMPC_GUARD(o, c);
   c.evec = o; o += align16(8 * 12 * h);
+  CMPC_GUARD(o, c);
   c.agg = o; o += align16(8 * 10 * h);
+  CMPC_GUARD(o, c);
   c.fs = o; o += align16(4 * CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.fsinv = o; o += align16(4 * CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.g = o; o += align16(8 * npad);
+  CMPC_GUARD(o, c);
   {
     int hb = 8 * nmax * nmax;  // H staging; the estimator stage borrows it for 3 x 400 doubles
     if (adapt && hb < 8 * CMPC_ADAPT_SCRATCH) hb = 8 * CMPC_ADAPT_SCRATCH;
     c.hs = o; o += align16(hb);
+    CMPC_GUARD(o, c);
   }
   c.pan = o; o += align16(8 * 8 * (npad + 4));
+  CMPC_GUARD(o, c);
   c.mm = o; o += align16(8 * 8 * (npad + 4));
+  CMPC_GUARD(o, c);
   c.dinv = o; o += 8 * 64;
+  CMPC_GUARD(o, c);
   c.red = o; o += 512;
+  CMPC_GUARD(o, c);
   c.total = o;
   return c;
 }
@@ -270,6 +287,10 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
   const int tid = threadIdx.x;
   const int h = P.horizon, hh = h * h;
   const CCarve cv = make_ccarve(h, P.nmax, P.rec_stride, NPAD, ADAPT);
+#ifdef CMPC_CANARY
+  canary_fill(smem, cv.guard, cv.nguard, tid, NT);
+  __syncthreads();
+#endif
   unsigned char* recbuf[2] = {smem + cv.rec0, smem + cv.rec1};
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.bars);
   double* sig = reinterpret_cast<double*>(smem + cv.sig);
@@ -697,5 +718,9 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
     pc.tick(CMPC_PH_STORE);
     cur = redi[2 + (buf ^ 1)];
   }
+#ifdef CMPC_CANARY
+  __syncthreads();
+  canary_check(smem, cv.guard, cv.nguard, tid, NT, "cmpc_condense_kernel");
+#endif
   if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_ASSEMBLE, (unsigned long long)flops_acc);
 }

@@ -38,30 +38,47 @@ __host__ __device__ constexpr int tix(int I, int J) { return I * (I + 1) / 2 + J
 
 struct MCarve {
   int rec0, rec1, bars, sig, ss, small, evec, agg, fs, rowinfo, g, pq, xtab, pan, mm, dv, red, total;
+  CMPC_CANARY_FIELDS
 };
 
 __host__ __device__ inline MCarve make_mcarve(int h, int rec_stride, bool adapt) {
   MCarve c;
   int o = 0;
+  CMPC_GUARD_INIT(c);
   c.rec0 = o; o += align16(rec_stride);
+  CMPC_GUARD(o, c);
   c.rec1 = o; o += align16(rec_stride);
+  CMPC_GUARD(o, c);
   c.bars = o; o += 16;
+  CMPC_GUARD(o, c);
   c.sig = o; o += align16(8 * CMPC_SIG_COUNT * h * h);
+  CMPC_GUARD(o, c);
   c.ss = o; o += 16 * h * h;  // (s22, s11) interleaved
+  CMPC_GUARD(o, c);
   c.small = o; o += align16(8 * (36 + 36 + 144 + 144 + 24));  // W, RW, PT, PO, scalars
+  CMPC_GUARD(o, c);
   c.evec = o; o += align16(8 * 12 * h);
+  CMPC_GUARD(o, c);
   c.agg = o; o += align16(8 * 10 * h);
+  CMPC_GUARD(o, c);
   c.fs = o; o += align16(CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.rowinfo = o; o += 4 * MMA_NPAD;
+  CMPC_GUARD(o, c);
   c.g = o; o += 8 * MMA_NPAD;
+  CMPC_GUARD(o, c);
   c.pq = o; o += 16 * MMA_PQ;
+  CMPC_GUARD(o, c);
   c.xtab = o; o += align16(32 * h * h);  // x_drag couplings: XA[ab], X0[ab], XA[ba], and a table of zeros
+  CMPC_GUARD(o, c);
   // scratch of the estimator stage (adaptive launches only)
   c.pan = o;
   c.mm = o;
   c.dv = o;
   if (adapt) o = c.pan + 8 * CMPC_ADAPT_SCRATCH;
+  if (adapt) CMPC_GUARD(o, c);
   c.red = o; o += 512;
+  CMPC_GUARD(o, c);
   c.total = o;
   return c;
 }
@@ -159,6 +176,10 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
   const int r = lane >> 2, q = lane & 3;
   const int h = P.horizon, hh = h * h;
   const MCarve cv = make_mcarve(h, P.rec_stride, ADAPT);
+#ifdef CMPC_CANARY
+  canary_fill(smem, cv.guard, cv.nguard, threadIdx.x, MMA_NT);
+  __syncthreads();
+#endif
   unsigned char* recbuf[2] = {smem + cv.rec0, smem + cv.rec1};
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.bars);
   double* sig = reinterpret_cast<double*>(smem + cv.sig);
@@ -524,5 +545,9 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
     pc.tick(CMPC_PH_STORE);
     cur = redi[2 + (buf ^ 1)];
   }
+#ifdef CMPC_CANARY
+  __syncthreads();
+  canary_check(smem, cv.guard, cv.nguard, tid, NT, "cmpc_assemble_mma_kernel");
+#endif
   if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_ASSEMBLE, (unsigned long long)flops_acc);
 }

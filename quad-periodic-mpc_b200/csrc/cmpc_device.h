@@ -6,6 +6,17 @@
 #include "../../include/cmpc_b200.h"
 
 #define CMPC_MAX_FS 80 /* 4 * CMPC_MAX_HORIZON rounded up */
+
+/* shared-memory canaries of a -DCMPC_CANARY build (cmpc_common.cuh): guard words behind every region of a carve */
+#ifdef CMPC_CANARY
+#define CMPC_CANARY_FIELDS int guard[32]; int nguard;
+#define CMPC_GUARD_INIT(c) (c).nguard = 0
+#define CMPC_GUARD(o, c) do { (o) = ((o) + 15) & ~15; (c).guard[(c).nguard++] = (o); (o) += 64; } while (0)
+#else
+#define CMPC_CANARY_FIELDS
+#define CMPC_GUARD_INIT(c)
+#define CMPC_GUARD(o, c)
+#endif
 #define CMPC_SM_SLOTS 1024 /* >= the largest %smid + 1 */
 #define CMPC_RESUME_INTS 34 /* q, iterations, up to 64 working-set rows as 16-bit ids */
 #define CMPC_QCAP_MID 56    /* middle capacity tier of the one-warp active-set kernel (reduced problems beyond 64 variables; "dual_team" = 0) */

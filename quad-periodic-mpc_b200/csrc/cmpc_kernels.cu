@@ -50,6 +50,7 @@ using ShapeGmem = Shape<8, 16, 8, 4, false, 1, true>;  // beyond shared memory: 
 struct Carve {
   int rec0, rec1, bars, small, evec, agg, fs, fsinv, rowinfo, cbuf, K, g, x, kn, z, v, s, rc, isact, act, u, d, r,
       col, Pp, red, total;
+  CMPC_CANARY_FIELDS
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
@@ -57,37 +58,64 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline Carve make_carve(int h, int nmax, int qcap, int rec_stride, int npad, bool adapt, bool gmem) {
   Carve c;
   int o = 0;
+  CMPC_GUARD_INIT(c);
   int nc = nmax / 3, m = 5 * nc;
   c.rec0 = o; o += align16(rec_stride);
+  CMPC_GUARD(o, c);
   c.rec1 = o; o += align16(rec_stride);
+  CMPC_GUARD(o, c);
   c.bars = o; o += 16;
+  CMPC_GUARD(o, c);
   c.small = o; o += align16(8 * (36 + 36 + 144 + 144 + 16));  // W, RW, PT, PO, scalars
+  CMPC_GUARD(o, c);
   c.evec = o; o += align16(8 * 12 * h);
+  CMPC_GUARD(o, c);
   c.agg = o; o += align16(8 * 10 * h);
+  CMPC_GUARD(o, c);
   c.fs = o; o += align16(4 * CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.fsinv = o; o += align16(4 * CMPC_MAX_FS);
+  CMPC_GUARD(o, c);
   c.rowinfo = o; o += align16(4 * (npad > nmax ? npad : nmax));
+  CMPC_GUARD(o, c);
   c.cbuf = o; o += align16(8 * (2 * (npad + 2) + 2 * npad));  // pivot rows (x2) + diagonal copies (x2)
+  CMPC_GUARD(o, c);
   {
     int kb = gmem ? 0 : 8 * nmax * nmax;  // the estimator stage borrows this region for 3 x 400 doubles of work space
     if (adapt && kb < 8 * CMPC_ADAPT_SCRATCH) kb = 8 * CMPC_ADAPT_SCRATCH;
     c.K = o; o += align16(kb);
+    CMPC_GUARD(o, c);
   }
   c.g = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.x = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.kn = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.z = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.v = o; o += align16(8 * nmax);
+  CMPC_GUARD(o, c);
   c.s = o; o += align16(8 * m);
+  CMPC_GUARD(o, c);
   c.rc = o; o += align16(8 * m);
+  CMPC_GUARD(o, c);
   c.isact = o; o += align16(m);
+  CMPC_GUARD(o, c);
   c.act = o; o += align16(2 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.u = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.d = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.r = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.col = o; o += align16(8 * (qcap + 1));
+  CMPC_GUARD(o, c);
   c.Pp = o; o += gmem ? 0 : align16(8 * ((qcap + 1) * (qcap + 2) / 2));
+  CMPC_GUARD(o, c);
   c.red = o; o += 512;
+  CMPC_GUARD(o, c);
   c.total = o;
   return c;
 }
@@ -138,6 +166,10 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
   const int h = P.horizon;
   constexpr bool gmem = S::GMEM;  // compile-time, so that K stays a shared-window pointer (LDS, not generic LD) otherwise
   const Carve cv = make_carve(h, P.nmax, P.qcap, P.rec_stride, S::NPAD, ADAPT, gmem);
+#ifdef CMPC_CANARY
+  canary_fill(smem, cv.guard, cv.nguard, tid, NT);
+  __syncthreads();
+#endif
   unsigned char* recbuf[2] = {smem + cv.rec0, smem + cv.rec1};
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cv.bars);
   double* sW = reinterpret_cast<double*>(smem + cv.small);  // W[4][3][3]
@@ -506,6 +538,10 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_solve_kernel(const __grid
     __syncthreads();  // record buffer and work arrays are reused by the next instance
     pc.tick(CMPC_PH_OUT);
   }
+#ifdef CMPC_CANARY
+  __syncthreads();
+  canary_check(smem, cv.guard, cv.nguard, tid, NT, "cmpc_solve_kernel");
+#endif
   if (tid == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_FUSED, (unsigned long long)flops_acc);
 }
 
