@@ -299,6 +299,7 @@ struct cmpc_batch {
   bool sweep_dmma = false;            // CMPC_SWEEP=dmma: tensor-core sweep in the 96 / 128 condensation shapes (measured:
                                       // +5 % on mixed gaits at h = 16, rounding error 50x the DFMA sweep's -> not the default)
   int inv_stagger = 2000;             // start offset (cycles) between the inversion CTAs of an SM (CMPC_INV_STAGGER, 0 = off)
+  int inv_refine = 512;               // inversion kernel: refine the panel of block steps whose pivot-block inverse exceeds this; -1 = never
   bool resume = true;                 // CMPC_RESUME=0: overflowed instances restart from scratch in the full-capacity launch
   std::vector<PipePlan> plans;        // launch plans by (reduced size bound, horizon, adaptive)
   HostBinding bound;                  // cmpc_batch_bind_host
@@ -683,6 +684,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.qws_stride = slot;
     Q.k_tiled = tiled;
     Q.sweep_dmma = (!tiled && cshape != CMPC_CSHAPE_64 && b->sweep_dmma) ? 1 : 0;
+    Q.inv_refine = (double)b->inv_refine;
     Q.qws_goff = cmpc_qws_goff(nmax, tiled);
     Q.worklist = nullptr;
     Q.count_ptr = nullptr;
@@ -1421,7 +1423,7 @@ int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_output
   return resolve_binding(b, in, out, b->bound);
 }
 
-// Diagnostic / test switches.  Keys: nstreams, split, serial, lpt, resume, sweep_dmma, inv_stagger, traj_copy, cshape,
+// Diagnostic / test switches.  Keys: nstreams, split, serial, lpt, resume, sweep_dmma, inv_stagger, inv_refine, traj_copy, cshape,
 // ws_mb, qcap1, dual_generic, wpc, no_mid_tier, path_fused, shape, host_pack, d2h_copy, chunks, submit_copy,
 // host_threads, dual_team, resume_p (and exp_skip_pack in a -DCMPC_EXPERIMENTS build).
 int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
@@ -1437,6 +1439,7 @@ int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
   else if (k == "resume") b->resume = value != 0;
   else if (k == "sweep_dmma") b->sweep_dmma = value != 0;
   else if (k == "inv_stagger") b->inv_stagger = std::max(0, value);
+  else if (k == "inv_refine") b->inv_refine = std::max(-1, value);
   else if (k == "traj_copy") b->traj_copy = value != 0;
   else if (k == "cshape") kn.cshape = value;
   else if (k == "ws_mb") kn.ws_mb = std::max(1, value);

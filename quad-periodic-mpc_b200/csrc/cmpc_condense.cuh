@@ -72,7 +72,7 @@ __host__ __device__ inline CCarve make_ccarve(int h, int nmax, int rec_stride, i
   CMPC_GUARD(o, c);
   c.mm = o; o += align16(8 * 8 * (npad + 4));
   CMPC_GUARD(o, c);
-  c.dinv = o; o += 8 * 64;
+  c.dinv = o; o += 8 * (64 + 64 + 2);  // D^-1, D itself, the refinement flag of the block step
   CMPC_GUARD(o, c);
   c.red = o; o += 512;
   CMPC_GUARD(o, c);
@@ -107,11 +107,13 @@ __device__ __forceinline__ void warp_inv8(double& a0, double& a1, int lane) {
 
 template <class S>
 __device__ __forceinline__ void sweep_blocked(double (&A)[S::TM][S::TN], int n, int tid, double* pan, double* mm,
-                                              double* dinvs) {
+                                              double* dinvs, double refine_above) {
   constexpr int TX = S::TX, TM = S::TM, TN = S::TN, PS = S::PS;
   const int ty = tid / TX, tx = tid - ty * TX;
   const int lane = tid & 31;
   const int nblk = (n + 7) >> 3;
+  double* dsave = dinvs + 64;
+  volatile int* flag = reinterpret_cast<volatile int*>(dinvs + 128);
 #pragma unroll 1
   for (int s = 0; s < nblk; s++) {
     const int k0 = 8 * s;
@@ -123,6 +125,8 @@ __device__ __forceinline__ void sweep_blocked(double (&A)[S::TM][S::TN], int n, 
         for (int bb = 0; bb < TN; bb++) {
           const int j = tx + TX * bb;
           double v = A[aa][bb];
+          // the pivot block itself goes to warp 0 as it is: (d - 1) + 1 would cost the small pivots their low bits
+          if (j >= k0 && j < k0 + 8) dsave[ty * 8 + (j - k0)] = v;
           if (j == k0 + ty) v -= 1.0;
           pan[ty * PS + j] = v;
         }
@@ -132,15 +136,16 @@ __device__ __forceinline__ void sweep_blocked(double (&A)[S::TM][S::TN], int n, 
     // D^-1 by warp 0
     if (tid < 32) {
       const int r = lane & 7, c0 = 2 * (lane >> 3);
-      double a0 = pan[r * PS + k0 + c0], a1 = pan[r * PS + k0 + c0 + 1];
-      if (c0 == r) a0 += 1.0;
-      if (c0 + 1 == r) a1 += 1.0;
+      double a0 = dsave[r * 8 + c0], a1 = dsave[r * 8 + c0 + 1];
       warp_inv8(a0, a1, lane);
       dinvs[r * 8 + c0] = a0;
       dinvs[r * 8 + c0 + 1] = a1;
+      const bool big = refine_above >= 0.0 && __any_sync(0xffffffffu, fmax(fabs(a0), fabs(a1)) > refine_above);
+      if (lane == 0) *flag = big ? 1 : 0;
     }
     __syncthreads();
     // M = D^-1 C  (thread (ty, tx): row ty, columns tx + TX b)
+    double mreg[TN];
     {
       double di[8];
 #pragma unroll
@@ -152,9 +157,50 @@ __device__ __forceinline__ void sweep_blocked(double (&A)[S::TM][S::TN], int n, 
 #pragma unroll
         for (int q = 0; q < 8; q++) acc = fma(di[q], pan[q * PS + j], acc);
         mm[ty * PS + j] = acc;
+        mreg[bb] = acc;
       }
     }
     __syncthreads();
+    // Block Gauss-Jordan with an explicitly inverted pivot block loses ~cond(D) digits more than a scalar sweep.  One
+    // residual correction of the panel, M += D^-1 (C - D M), gives them back; it is applied only to block steps whose
+    // pivot-block inverse is large (none on the A1 defaults).  The flag is uniform over the CTA.
+    if (*flag) {
+      double rr[TN];
+      {
+        double dr[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) dr[q] = dsave[ty * 8 + q];
+#pragma unroll
+        for (int bb = 0; bb < TN; bb++) {
+          const int j = tx + TX * bb;
+          double acc = pan[ty * PS + j];
+#pragma unroll
+          for (int q = 0; q < 8; q++) acc = fma(-dr[q], mm[q * PS + j], acc);
+          rr[bb] = acc;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int bb = 0; bb < TN; bb++) mm[ty * PS + tx + TX * bb] = rr[bb];
+      __syncthreads();
+      {
+        double di[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) di[q] = dinvs[ty * 8 + q];
+#pragma unroll
+        for (int bb = 0; bb < TN; bb++) {
+          const int j = tx + TX * bb;
+          double acc = mreg[bb];
+#pragma unroll
+          for (int q = 0; q < 8; q++) acc = fma(di[q], mm[q * PS + j], acc);
+          mreg[bb] = acc;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int bb = 0; bb < TN; bb++) mm[ty * PS + tx + TX * bb] = mreg[bb];
+      __syncthreads();
+    }
     // rank-8 update of the tile
 #pragma unroll 2
     for (int p = 0; p < 8; p++) {
@@ -220,7 +266,7 @@ __device__ __forceinline__ void cinv8_acc(double& a0, double& a1, int r, int q) 
 template <class S>
 __device__ __forceinline__ void sweep_dmma(double (&t)[DSweep<S>::TPW][2], const int (&tI)[DSweep<S>::TPW],
                                            const int (&tJ)[DSweep<S>::TPW], int n, int tid, double* pan, double* mm,
-                                           double* dv) {
+                                           double* dv, double refine_above) {
   constexpr int PS = S::PS, TPW = DSweep<S>::TPW, NW = DSweep<S>::NW;
   const int lane = tid & 31, w = tid >> 5, r = lane >> 2, q = lane & 3;
   const int fo = q * PS + r;  // fragment offset: element (k = q, row / column = r)
@@ -250,18 +296,43 @@ __device__ __forceinline__ void sweep_dmma(double (&t)[DSweep<S>::TPW][2], const
     if (w == 0) {
       const double2 d = *reinterpret_cast<const double2*>(dv + r * 8 + 2 * q);
       double d0 = d.x, d1 = d.y;
+      *reinterpret_cast<double2*>(dv + 64 + r * 8 + 2 * q) = d;  // D itself stays for the refinement
       cinv8_acc(d0, d1, r, q);
       *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
+      const bool big = refine_above >= 0.0 && __any_sync(0xffffffffu, fmax(fabs(d0), fabs(d1)) > refine_above);
+      if (lane == 0) *reinterpret_cast<volatile int*>(dv + 128) = big ? 1 : 0;
     }
     __syncthreads();
-    // 3. M = -D^-1 C
+    // 3. M = -D^-1 C; where the pivot-block inverse is large, one residual correction M += -D^-1 (C + D M) (see
+    //    sweep_blocked) — a column tile of M belongs to one warp, so the correction needs no block barrier
     {
       const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
+      const bool refine = *reinterpret_cast<volatile int*>(dv + 128) != 0;
+      double da0 = 0.0, da1 = 0.0;
+      if (refine) {
+        da0 = dv[64 + r * 8 + q];
+        da1 = dv[64 + r * 8 + 4 + q];
+      }
       for (int J = w; J < nblk; J += NW) {
         double m0 = 0.0, m1 = 0.0;
         cdmma(m0, m1, a0, pan[fo + 8 * J]);
         cdmma(m0, m1, a1, pan[fo + 4 * PS + 8 * J]);
-        *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(m0, m1);
+        double2* mt = reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q);
+        *mt = make_double2(m0, m1);
+        if (refine) {
+          __syncwarp();
+          const double2 c = *reinterpret_cast<const double2*>(pan + r * PS + 8 * J + 2 * q);
+          double r0 = c.x, r1 = c.y;
+          cdmma(r0, r1, da0, mm[fo + 8 * J]);
+          cdmma(r0, r1, da1, mm[fo + 4 * PS + 8 * J]);
+          __syncwarp();
+          *mt = make_double2(r0, r1);
+          __syncwarp();
+          cdmma(m0, m1, a0, mm[fo + 8 * J]);
+          cdmma(m0, m1, a1, mm[fo + 4 * PS + 8 * J]);
+          __syncwarp();
+          *mt = make_double2(m0, m1);
+        }
       }
     }
     __syncthreads();
@@ -623,7 +694,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
         }
         pc.tick(CMPC_PH_LOAD);
         __syncthreads();  // every tile is in registers before the staging area is reused
-        sweep_dmma<S>(t, tI, tJ, n, tid, pan, mm, dinvs);
+        sweep_dmma<S>(t, tI, tJ, n, tid, pan, mm, dinvs, P.inv_refine);
         pc.tick(CMPC_PH_SWEEP);
         // K_ij = -(A_ij - 2 d_ij) scale, both triangles, into the staging area
 #pragma unroll
@@ -668,7 +739,7 @@ __global__ void __launch_bounds__(S::NT, S::MINB) cmpc_condense_kernel(const __g
           A[a][b] = (i < n && j < n) ? Hs[i * n + j] * scale : (i == j ? 0.5 : 0.0);  // harmless padding beyond n
         }
       pc.tick(CMPC_PH_LOAD);
-      sweep_blocked<S>(A, n, tid, pan, mm, dinvs);
+      sweep_blocked<S>(A, n, tid, pan, mm, dinvs, P.inv_refine);
       pc.tick(CMPC_PH_SWEEP);
       // -swept = (scaled H)^-1 with +2 on the diagonal:  K_ij = -(A_ij - 2 d_ij) scale
       // x0 = -K g: partial column sums over this thread's rows, reduced over ty through shared memory

@@ -72,6 +72,8 @@ struct CmpcParams {
   int max_iter;
   int adapt_mode;   // -1 off, 0 estimate only, 1 estimate and apply, 2 apply the stored estimate
   int inv_stagger;  // inversion kernel: start offset (SM cycles) between the CTAs that share an SM; 0 = none
+  double inv_refine; // inversion kernel: a block step whose pivot-block inverse has an entry above this (the matrix is scaled to a
+                     // diagonal below 1) gets one residual correction of its panel; < 0 = never
   double dt;        // (double)(float)dt
   double mu_inv;    // (double)(1.f/(float)mu)   SolverMPC.cpp:657
   double f_max;     // (double)(float)f_max

@@ -427,6 +427,15 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
       // a last block of at most four real rows: its second k-step (padding rows, the border) contributes zeros
       const bool half_step = (8 * s + 4 >= n);
       const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
+      // Block Gauss-Jordan with an explicitly inverted pivot block loses ~cond(D) digits more than the scalar sweep
+      // (profiles/r2_block_gj_accuracy.txt).  One residual correction of the panel, M += -D^-1 (C + D M), gives them back;
+      // it is applied only to block steps whose pivot-block inverse is large (none on the A1 defaults).
+      const bool refine = P.inv_refine >= 0.0 && __any_sync(0xffffffffu, fmax(fabs(a0), fabs(a1)) > P.inv_refine);
+      double da0 = 0.0, da1 = 0.0;  // D itself as the A operand (the helper is done with the parked tile)
+      if (refine) {
+        da0 = dtile[r * 8 + q];
+        da1 = dtile[r * 8 + 4 + q];
+      }
       // 2a. the next diagonal tile FIRST: its column block of M (two DMMAs), its update (two DMMAs), then it is handed
       //     to the helper, whose pivot chain runs under the rest of M and the 72 update DMMAs of this step
       if (s + 1 < nblk) {
@@ -436,6 +445,20 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
         dmma884(m0, m1, a1, pan[fo + 4 * PS + o]);
         *reinterpret_cast<double2*>(mm + r * PS + o + 2 * q) = make_double2(m0, m1);
         __syncwarp();
+        if (refine) {
+          const double2 c = *reinterpret_cast<const double2*>(pan + r * PS + o + 2 * q);
+          double r0 = c.x, r1 = c.y;
+          dmma884(r0, r1, da0, mm[fo + o]);
+          dmma884(r0, r1, da1, mm[fo + 4 * PS + o]);
+          __syncwarp();
+          *reinterpret_cast<double2*>(mm + r * PS + o + 2 * q) = make_double2(r0, r1);
+          __syncwarp();
+          dmma884(m0, m1, a0, mm[fo + o]);
+          dmma884(m0, m1, a1, mm[fo + 4 * PS + o]);
+          __syncwarp();
+          *reinterpret_cast<double2*>(mm + r * PS + o + 2 * q) = make_double2(m0, m1);
+          __syncwarp();
+        }
         double e0, e1;
         switch (s) {
           case 0: e0 = t[tix(1, 1)][0]; e1 = t[tix(1, 1)][1]; break;
@@ -464,6 +487,38 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
         for (int J = 0; J < 8; J++) {
           dmma884(mt[J][0], mt[J][1], a1, pan[fo + 4 * PS + 8 * J]);
           *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(mt[J][0], mt[J][1]);
+        }
+        if (refine) {  // four tiles at a time (registers): R = C + D M, then M += -D^-1 R, the same operations as in 2a
+          __syncwarp();
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            double rt[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int J = 4 * hf + j;
+              const double2 c = *reinterpret_cast<const double2*>(pan + r * PS + 8 * J + 2 * q);
+              rt[j][0] = c.x;
+              rt[j][1] = c.y;
+              dmma884(rt[j][0], rt[j][1], da0, mm[fo + 8 * J]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(rt[j][0], rt[j][1], da1, mm[fo + 4 * PS + 8 * (4 * hf + j)]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              *reinterpret_cast<double2*>(mm + r * PS + 8 * (4 * hf + j) + 2 * q) = make_double2(rt[j][0], rt[j][1]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(mt[4 * hf + j][0], mt[4 * hf + j][1], a0, mm[fo + 8 * (4 * hf + j)]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(mt[4 * hf + j][0], mt[4 * hf + j][1], a1, mm[fo + 4 * PS + 8 * (4 * hf + j)]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int J = 4 * hf + j;
+              *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(mt[J][0], mt[J][1]);
+            }
+          }
         }
       }
       __syncwarp();
