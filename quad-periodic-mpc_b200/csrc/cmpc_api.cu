@@ -299,7 +299,9 @@ struct cmpc_batch {
   bool sweep_dmma = false;            // CMPC_SWEEP=dmma: tensor-core sweep in the 96 / 128 condensation shapes (measured:
                                       // +5 % on mixed gaits at h = 16, rounding error 50x the DFMA sweep's -> not the default)
   int inv_stagger = 2000;             // start offset (cycles) between the inversion CTAs of an SM (CMPC_INV_STAGGER, 0 = off)
-  int inv_refine = 512;               // inversion kernel: refine the panel of block steps whose pivot-block inverse exceeds this; -1 = never
+  int inv_refine = 1024;              // blocked sweeps: refine the panel of block steps whose pivot-block inverse exceeds this; -1 = never
+                                      // (measured, profiles/r2_illcond_accuracy.txt: 1024 costs nothing on the A1 trot batch and 1 % on
+                                      // the mixed-gait h = 16 batch; 512 costs 8 % there)
   bool resume = true;                 // CMPC_RESUME=0: overflowed instances restart from scratch in the full-capacity launch
   std::vector<PipePlan> plans;        // launch plans by (reduced size bound, horizon, adaptive)
   HostBinding bound;                  // cmpc_batch_bind_host

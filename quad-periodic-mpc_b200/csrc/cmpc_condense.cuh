@@ -163,7 +163,7 @@ __device__ __forceinline__ void sweep_blocked(double (&A)[S::TM][S::TN], int n, 
     __syncthreads();
     // Block Gauss-Jordan with an explicitly inverted pivot block loses ~cond(D) digits more than a scalar sweep.  One
     // residual correction of the panel, M += D^-1 (C - D M), gives them back; it is applied only to block steps whose
-    // pivot-block inverse is large (none on the A1 defaults).  The flag is uniform over the CTA.
+    // pivot-block inverse is large (P.inv_refine; next to none on the A1 defaults).  The flag is uniform over the CTA.
     if (*flag) {
       double rr[TN];
       {

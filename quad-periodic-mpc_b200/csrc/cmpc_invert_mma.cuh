@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
       const double a0 = dv[r * 8 + q], a1 = dv[r * 8 + 4 + q];
       // Block Gauss-Jordan with an explicitly inverted pivot block loses ~cond(D) digits more than the scalar sweep
       // (profiles/r2_block_gj_accuracy.txt).  One residual correction of the panel, M += -D^-1 (C + D M), gives them back;
-      // it is applied only to block steps whose pivot-block inverse is large (none on the A1 defaults).
+      // it is applied only to block steps whose pivot-block inverse is large (P.inv_refine; next to none on the A1 defaults).
       const bool refine = P.inv_refine >= 0.0 && __any_sync(0xffffffffu, fmax(fabs(a0), fabs(a1)) > P.inv_refine);
       double da0 = 0.0, da1 = 0.0;  // D itself as the A operand (the helper is done with the parked tile)
       if (refine) {

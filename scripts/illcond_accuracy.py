@@ -49,8 +49,9 @@ def study(title, gaits, variants):
             print("   alpha %.0e: %3d instances, max |dF| %.2e N, max slack on rows active at the optimum %.2e" % (a, sel.sum(), dF, sl))
 
 
-common = [("default (panel refinement above 512)", {}), ("no panel refinement (inv_refine = -1)", {"inv_refine": -1}),
-          ("always refine (inv_refine = 0)", {"inv_refine": 0}), ("fused kernel (scalar sweep)", {"path_fused": 1})]
+common = [("default (panel refinement above 1024)", {}), ("no panel refinement (inv_refine = -1)", {"inv_refine": -1}),
+          ("always refine (inv_refine = 0)", {"inv_refine": 0}), ("inv_refine = 512", {"inv_refine": 512}),
+          ("inv_refine = 4096", {"inv_refine": 4096}), ("fused kernel (scalar sweep)", {"path_fused": 1})]
 which = os.environ.get("STUDY", "12")
 if "1" in which:
     study("n <= 63 pipeline (tensor-core inversion kernel)", ("trot", "pace"), common)
