@@ -20,7 +20,7 @@ ON_ERROR_ABORT, ON_ERROR_HOLD = 0, 1
 _ENV_OPTIONS = {
     "CMPC_NSTREAMS": ("nstreams", int), "CMPC_SPLIT": ("split", int), "CMPC_SERIAL": ("serial", int),
     "CMPC_LPT": ("lpt", int), "CMPC_RESUME": ("resume", int), "CMPC_INV_STAGGER": ("inv_stagger", int),
-    "CMPC_INV_REFINE": ("inv_refine", int),
+    "CMPC_INV_REFINE": ("inv_refine", int), "CMPC_INV_F32": ("inv_f32", int), "CMPC_INV_CTAS": ("inv_ctas", int),
     "CMPC_TRAJ_COPY": ("traj_copy", int), "CMPC_CSHAPE": ("cshape", int), "CMPC_WS_MB": ("ws_mb", int),
     "CMPC_QCAP1": ("qcap1", int), "CMPC_WPC": ("wpc", int), "CMPC_NO_MID_TIER": ("no_mid_tier", lambda v: 1),
     "CMPC_SHAPE": ("shape", int), "CMPC_HOST_PACK": ("host_pack", int), "CMPC_D2H_COPY": ("d2h_copy", int),

@@ -299,6 +299,8 @@ struct cmpc_batch {
   bool sweep_dmma = false;            // CMPC_SWEEP=dmma: tensor-core sweep in the 96 / 128 condensation shapes (measured:
                                       // +5 % on mixed gaits at h = 16, rounding error 50x the DFMA sweep's -> not the default)
   int inv_stagger = 2000;             // start offset (cycles) between the inversion CTAs of an SM (CMPC_INV_STAGGER, 0 = off)
+  int inv_ctas = 0;                   // cap on the inversion kernel's CTAs per SM (0 = what fits; measurements)
+  int inv_f32 = 1;                    // pivot blocks of the inversion kernel: fp32 chain + FP64 Newton steps on the tensor cores (0: FP64 chain)
   int inv_refine = 1024;              // blocked sweeps: refine the panel of block steps whose pivot-block inverse exceeds this; -1 = never
                                       // (measured, profiles/r2_illcond_accuracy.txt: 1024 costs nothing on the A1 trot batch and 1 % on
                                       // the mixed-gait h = 16 batch; 512 costs 8 % there)
@@ -687,6 +689,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
     Q.k_tiled = tiled;
     Q.sweep_dmma = (!tiled && cshape != CMPC_CSHAPE_64 && b->sweep_dmma) ? 1 : 0;
     Q.inv_refine = (double)b->inv_refine;
+    Q.inv_f32 = b->inv_f32;
     Q.qws_goff = cmpc_qws_goff(nmax, tiled);
     Q.worklist = nullptr;
     Q.count_ptr = nullptr;
@@ -711,7 +714,7 @@ int launch_pipeline(cmpc_batch* b, CmpcParams P, int count, int si) {
       Q.sched = ctl + kCtlSched + 3;
       const int ipc2 = cmpc_invert_instances_per_cta();
       if (int e = prof_begin()) return e;
-      rc = cmpc_launch_invert(Q, std::min((cnt + ipc2 - 1) / ipc2, b->sm_count * per_sm_inv), st);
+      rc = cmpc_launch_invert(Q, std::min((cnt + ipc2 - 1) / ipc2, b->sm_count * (b->inv_ctas > 0 ? std::min(b->inv_ctas, per_sm_inv) : per_sm_inv)), st);
       if (rc != 0) return fail_cuda((cudaError_t)rc, "cmpc_invert_mma_kernel launch");
       b->launches++;
       if (int e = prof_end(CMPC_K_INVERT)) return e;
@@ -1425,7 +1428,7 @@ int cmpc_batch_bind_host(cmpc_batch* b, const cmpc_inputs* in, const cmpc_output
   return resolve_binding(b, in, out, b->bound);
 }
 
-// Diagnostic / test switches.  Keys: nstreams, split, serial, lpt, resume, sweep_dmma, inv_stagger, inv_refine, traj_copy, cshape,
+// Diagnostic / test switches.  Keys: nstreams, split, serial, lpt, resume, sweep_dmma, inv_stagger, inv_refine, inv_f32, inv_ctas, traj_copy, cshape,
 // ws_mb, qcap1, dual_generic, wpc, no_mid_tier, path_fused, shape, host_pack, d2h_copy, chunks, submit_copy,
 // host_threads, dual_team, resume_p (and exp_skip_pack in a -DCMPC_EXPERIMENTS build).
 int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
@@ -1442,6 +1445,8 @@ int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value) {
   else if (k == "sweep_dmma") b->sweep_dmma = value != 0;
   else if (k == "inv_stagger") b->inv_stagger = std::max(0, value);
   else if (k == "inv_refine") b->inv_refine = std::max(-1, value);
+  else if (k == "inv_f32") b->inv_f32 = value != 0;
+  else if (k == "inv_ctas") b->inv_ctas = std::max(0, value);
   else if (k == "traj_copy") b->traj_copy = value != 0;
   else if (k == "cshape") kn.cshape = value;
   else if (k == "ws_mb") kn.ws_mb = std::max(1, value);

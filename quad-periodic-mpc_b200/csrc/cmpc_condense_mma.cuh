@@ -141,6 +141,30 @@ __device__ __forceinline__ void warp_inv8_acc(double& a0, double& a1, int r, int
   }
 }
 
+// the same chain in fp32 (a starting value for Newton steps in FP64, see cmpc_invert_ws_kernel)
+__device__ __forceinline__ void warp_inv8_acc_f32(float& a0, float& a1, int r, int q) {
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const int pq = p >> 1;
+    const float mine = (p & 1) ? a1 : a0;
+    const float arp = __shfl_sync(0xffffffffu, mine, r * 4 + pq);
+    const float dpp = __shfl_sync(0xffffffffu, mine, p * 4 + pq);
+    const float ap0 = __shfl_sync(0xffffffffu, a0, p * 4 + q);
+    const float ap1 = __shfl_sync(0xffffffffu, a1, p * 4 + q);
+    float dinv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(dinv) : "f"(dpp));
+    const float t = arp * dinv;
+    float n0 = fmaf(-t, ap0, a0), n1 = fmaf(-t, ap1, a1);
+    if (r == p) { n0 = ap0 * dinv; n1 = ap1 * dinv; }
+    if (q == pq) {
+      if (p & 1) n1 = (r == p) ? dinv : -t;
+      else n0 = (r == p) ? dinv : -t;
+    }
+    a0 = n0;
+    a1 = n1;
+  }
+}
+
 // free response of state component c at step rr (0-based), weighted tracking error against the reference trajectory
 __device__ __forceinline__ double tracking_error(const float* rec, const double* sScal, int idx, double dt, double gravity) {
   const double xd = rec[CMPC_REC_XDRAG];

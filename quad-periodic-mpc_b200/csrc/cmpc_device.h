@@ -72,6 +72,7 @@ struct CmpcParams {
   int max_iter;
   int adapt_mode;   // -1 off, 0 estimate only, 1 estimate and apply, 2 apply the stored estimate
   int inv_stagger;  // inversion kernel: start offset (SM cycles) between the CTAs that share an SM; 0 = none
+  int inv_f32;       // inversion kernel: pivot blocks by an fp32 Gauss-Jordan chain + FP64 Newton steps on the tensor cores
   double inv_refine; // inversion kernel: a block step whose pivot-block inverse has an entry above this (the matrix is scaled to a
                      // diagonal below 1) gets one residual correction of its panel; < 0 = never
   double dt;        // (double)(float)dt

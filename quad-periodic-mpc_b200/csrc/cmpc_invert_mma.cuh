@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
 namespace {
 constexpr int WS_MAIN = 4;                                   // main warps (= instances in flight) per CTA
 constexpr int WS_TILE_BYTES = 8 * CMPC_KTILE_DOUBLES;                                 // the 36 tiles of one instance
-constexpr int WS_PAIR_CTRL = 8 * (2 * 8 * MMA_PS + 64 + 64);                          // panel, M, -D^-1, parked tile
+constexpr int WS_PAIR_CTRL = 8 * (2 * 8 * MMA_PS + 64 + 64 + 64);                     // panel, M, -D^-1, parked tile, Newton scratch
 constexpr int WS_PAIR_SMEM = WS_PAIR_CTRL + 16 + WS_TILE_BYTES;  // + control word, mbarrier, prefetched tiles of the NEXT instance
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
@@ -258,9 +258,10 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
   double* mm = pan + 8 * PS;
   double* dv = mm + 8 * PS;
   double* dtile = dv + 64;
-  volatile int* ctrl = reinterpret_cast<volatile int*>(dtile + 64);
-  uint64_t* tbar = reinterpret_cast<uint64_t*>(dtile + 65);      // mbarrier of the tile prefetch
-  double* tbuf = dtile + 66;                                     // 36 tiles, filled by one cp.async.bulk
+  double* nsc = dtile + 64;                                      // helper: residual of the Newton steps
+  volatile int* ctrl = reinterpret_cast<volatile int*>(nsc + 64);
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(nsc + 65);        // mbarrier of the tile prefetch
+  double* tbuf = nsc + 66;                                       // 36 tiles, filled by one cp.async.bulk
   const int BAR_TILE = 1 + 2 * pair, BAR_DV = 2 + 2 * pair;
 
   // The CTAs of an SM start together and every instance takes the same time, so the main warps that share a
@@ -288,7 +289,34 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
         if (s > 0) named_bar_sync(BAR_TILE);
         const double2 d = *reinterpret_cast<const double2*>(dtile + r * 8 + 2 * q);
         double d0 = d.x, d1 = d.y;
-        warp_inv8_acc(d0, d1, r, q);
+        bool done = false;
+        if (P.inv_f32) {
+          // An FP64 instruction of this warp queues behind the DMMA streams of the two main warps of its sub-partition
+          // (profiles/r2_ubench_helper_chain.txt), fp32 ones do not: the serial chain of eight pivots runs in fp32, and
+          // X <- X + X (I - D X) on the tensor cores (four DMMAs a step) squares its error until it is below rounding.
+          float f0 = (float)d0, f1 = (float)d1;
+          warp_inv8_acc_f32(f0, f1, r, q);
+          double x0 = (double)f0, x1 = (double)f1;
+          const double nd0 = -dtile[r * 8 + q], nd1 = -dtile[r * 8 + 4 + q];
+          for (int it = 0; it < 6 && !done; it++) {
+            *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(x0, x1);
+            __syncwarp();
+            double t0 = (r == 2 * q) ? 1.0 : 0.0, t1 = (r == 2 * q + 1) ? 1.0 : 0.0;
+            dmma884(t0, t1, nd0, dv[q * 8 + r]);
+            dmma884(t0, t1, nd1, dv[(4 + q) * 8 + r]);
+            *reinterpret_cast<double2*>(nsc + r * 8 + 2 * q) = make_double2(t0, t1);
+            const double tm = fmax(fabs(t0), fabs(t1));
+            const bool small = !__any_sync(0xffffffffu, !(tm < 1e-8));
+            if (it == 0 && __any_sync(0xffffffffu, !(tm < 0.25))) break;  // fp32 was not enough for this block: FP64 chain below
+            __syncwarp();
+            dmma884(x0, x1, dv[r * 8 + q], nsc[q * 8 + r]);
+            dmma884(x0, x1, dv[r * 8 + 4 + q], nsc[(4 + q) * 8 + r]);
+            __syncwarp();
+            done = small;
+          }
+          if (done) { d0 = x0; d1 = x1; }
+        }
+        if (!done) warp_inv8_acc(d0, d1, r, q);
         *reinterpret_cast<double2*>(dv + r * 8 + 2 * q) = make_double2(-d0, -d1);
         named_bar_arrive(BAR_DV);
       }
