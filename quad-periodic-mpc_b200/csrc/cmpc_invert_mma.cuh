@@ -305,9 +305,11 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
             dmma884(t0, t1, nd0, dv[q * 8 + r]);
             dmma884(t0, t1, nd1, dv[(4 + q) * 8 + r]);
             *reinterpret_cast<double2*>(nsc + r * 8 + 2 * q) = make_double2(t0, t1);
-            const double tm = fmax(fabs(t0), fabs(t1));
-            const bool small = !__any_sync(0xffffffffu, !(tm < 1e-8));
-            if (it == 0 && __any_sync(0xffffffffu, !(tm < 0.25))) break;  // fp32 was not enough for this block: FP64 chain below
+            // magnitude tests on the high words (integer pipe: an FP64 compare would queue behind the main warps' DMMAs);
+            // a NaN compares as large
+            const int tm = max(__double2hiint(t0) & 0x7fffffff, __double2hiint(t1) & 0x7fffffff);
+            const bool small = !__any_sync(0xffffffffu, tm >= 0x3e45798e /* 1e-8 */);
+            if (it == 0 && __any_sync(0xffffffffu, tm >= 0x3fd00000 /* 0.25 */)) break;  // fp32 was not enough: FP64 chain below
             __syncwarp();
             dmma884(x0, x1, dv[r * 8 + q], nsc[q * 8 + r]);
             dmma884(x0, x1, dv[r * 8 + 4 + q], nsc[(4 + q) * 8 + r]);
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
   const int count = P.count;
   unsigned flops_acc = 0u;
   const int fo = q * PS + r;  // fragment offset: element (k = q, row/col = r)
+  const int refine_hi = __double2hiint(P.inv_refine);  // the threshold of the panel refinement, compared on high words
   long long tclk = 0;
   if (CLK) tclk = clock64();
 #define WS_TICK(PH)                                                                     \
@@ -458,7 +461,8 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
       // Block Gauss-Jordan with an explicitly inverted pivot block loses ~cond(D) digits more than the scalar sweep
       // (profiles/r2_block_gj_accuracy.txt).  One residual correction of the panel, M += -D^-1 (C + D M), gives them back;
       // it is applied only to block steps whose pivot-block inverse is large (P.inv_refine; next to none on the A1 defaults).
-      const bool refine = P.inv_refine >= 0.0 && __any_sync(0xffffffffu, fmax(fabs(a0), fabs(a1)) > P.inv_refine);
+      const bool refine = P.inv_refine >= 0.0 &&
+                          __any_sync(0xffffffffu, max(__double2hiint(a0) & 0x7fffffff, __double2hiint(a1) & 0x7fffffff) > refine_hi);
       double da0 = 0.0, da1 = 0.0;  // D itself as the A operand (the helper is done with the parked tile)
       if (refine) {
         da0 = dtile[r * 8 + q];
