@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
   // the work counter is drawn TWO instances ahead (lane 0 holds the ticket, nobody waits for the atomic), and the
   // hardest-first filing of an instance is completed one instance later (same reason)
   int ticket = 0;
-  if (lane == 0) ticket = atomicAdd(P.sched, 1);
+  if (lane == 0) ticket = atom_add_later(P.sched, 1);
   int file_inst = -1, file_key = 0, file_pos = 0;
   auto lpt_flush = [&]() {
     if (lane == 0 && file_inst >= 0) P.lpt_key[file_inst] = (file_key << 24) | file_pos;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
     if (!P.lpt_hist) return;
     lpt_flush();
     if (lane == 0) {
-      file_pos = atomicAdd(P.lpt_hist + key, 1);
+      file_pos = atom_add_later(P.lpt_hist + key, 1);
       file_key = key;
       file_inst = i;
     }
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
     __syncwarp();
     WS_TICK(CMPC_PH_X1)
     const int inst_next = __shfl_sync(0xffffffffu, ticket, 0);
-    if (lane == 0) ticket = atomicAdd(P.sched, 1);
+    if (lane == 0) ticket = atom_add_later(P.sched, 1);
     int nc_next = 0, st_next = 0, gv_next = 0;
     double sc_next = 0.0;
     if (inst_next < count) prefetch(inst_next, nc_next, st_next, sc_next, gv_next);
@@ -506,51 +506,59 @@ __global__ void __launch_bounds__(64 * WS_MAIN, 2) cmpc_invert_ws_kernel(const _
         park_tile(e0, e1, s + 1);
         named_bar_arrive(BAR_TILE);
       }
-      // 2b. M = -D^-1 C (the column block of 2a is formed again, bit for bit the same)
-      {
-        double mt[8][2];  // all eight tiles of M in flight: the two k-steps of a tile are eight DMMAs apart
+      // 2b. M = -D^-1 C (the column block of 2a is formed again, bit for bit the same): four tiles at a time, their eight
+      //     B fragments loaded up front, the two k-steps of a tile four DMMAs apart
 #pragma unroll
-        for (int J = 0; J < 8; J++) {
-          mt[J][0] = 0.0;
-          mt[J][1] = 0.0;
-          dmma884(mt[J][0], mt[J][1], a0, pan[fo + 8 * J]);
+      for (int hf = 0; hf < 2; hf++) {
+        double bf[4][2], mt[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          bf[j][0] = lds_f64v(pan + fo + 8 * (4 * hf + j));
+          bf[j][1] = lds_f64v(pan + fo + 4 * PS + 8 * (4 * hf + j));
         }
 #pragma unroll
-        for (int J = 0; J < 8; J++) {
-          dmma884(mt[J][0], mt[J][1], a1, pan[fo + 4 * PS + 8 * J]);
-          *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(mt[J][0], mt[J][1]);
+        for (int j = 0; j < 4; j++) {
+          mt[j][0] = 0.0;
+          mt[j][1] = 0.0;
+          dmma884v(mt[j][0], mt[j][1], a0, bf[j][0]);
         }
-        if (refine) {  // four tiles at a time (registers): R = C + D M, then M += -D^-1 R, the same operations as in 2a
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884v(mt[j][0], mt[j][1], a1, bf[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          *reinterpret_cast<double2*>(mm + r * PS + 8 * (4 * hf + j) + 2 * q) = make_double2(mt[j][0], mt[j][1]);
+      }
+      if (refine) {  // four tiles at a time: R = C + D M, then M += -D^-1 R, the same operations as in 2a
+        __syncwarp();
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+          double rt[4][2], mt[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int J = 4 * hf + j;
+            const double2 c = *reinterpret_cast<const double2*>(pan + r * PS + 8 * J + 2 * q);
+            const double2 m = *reinterpret_cast<const double2*>(mm + r * PS + 8 * J + 2 * q);
+            rt[j][0] = c.x;
+            rt[j][1] = c.y;
+            mt[j][0] = m.x;
+            mt[j][1] = m.y;
+            dmma884(rt[j][0], rt[j][1], da0, mm[fo + 8 * J]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma884(rt[j][0], rt[j][1], da1, mm[fo + 4 * PS + 8 * (4 * hf + j)]);
           __syncwarp();
 #pragma unroll
-          for (int hf = 0; hf < 2; hf++) {
-            double rt[4][2];
+          for (int j = 0; j < 4; j++)
+            *reinterpret_cast<double2*>(mm + r * PS + 8 * (4 * hf + j) + 2 * q) = make_double2(rt[j][0], rt[j][1]);
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const int J = 4 * hf + j;
-              const double2 c = *reinterpret_cast<const double2*>(pan + r * PS + 8 * J + 2 * q);
-              rt[j][0] = c.x;
-              rt[j][1] = c.y;
-              dmma884(rt[j][0], rt[j][1], da0, mm[fo + 8 * J]);
-            }
+          for (int j = 0; j < 4; j++) dmma884(mt[j][0], mt[j][1], a0, mm[fo + 8 * (4 * hf + j)]);
 #pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(rt[j][0], rt[j][1], da1, mm[fo + 4 * PS + 8 * (4 * hf + j)]);
-            __syncwarp();
+          for (int j = 0; j < 4; j++) dmma884(mt[j][0], mt[j][1], a1, mm[fo + 4 * PS + 8 * (4 * hf + j)]);
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-              *reinterpret_cast<double2*>(mm + r * PS + 8 * (4 * hf + j) + 2 * q) = make_double2(rt[j][0], rt[j][1]);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(mt[4 * hf + j][0], mt[4 * hf + j][1], a0, mm[fo + 8 * (4 * hf + j)]);
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(mt[4 * hf + j][0], mt[4 * hf + j][1], a1, mm[fo + 4 * PS + 8 * (4 * hf + j)]);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const int J = 4 * hf + j;
-              *reinterpret_cast<double2*>(mm + r * PS + 8 * J + 2 * q) = make_double2(mt[J][0], mt[J][1]);
-            }
-          }
+          for (int j = 0; j < 4; j++)
+            *reinterpret_cast<double2*>(mm + r * PS + 8 * (4 * hf + j) + 2 * q) = make_double2(mt[j][0], mt[j][1]);
         }
       }
       __syncwarp();
