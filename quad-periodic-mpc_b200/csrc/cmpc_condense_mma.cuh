@@ -99,6 +99,13 @@ __device__ __forceinline__ double lds_f64v(const double* p) {
   return v;
 }
 
+// one of three doubles by a run-time index, without turning the operands into an indexable (local-memory) array
+__device__ __forceinline__ double pick3(double a0, double a1, double a2, int c) {
+  const int m0 = -(int)(c == 0), m1 = -(int)(c == 1), m2 = -(int)(c == 2);
+  return __hiloint2double((__double2hiint(a0) & m0) | (__double2hiint(a1) & m1) | (__double2hiint(a2) & m2),
+                          (__double2loint(a0) & m0) | (__double2loint(a1) & m1) | (__double2loint(a2) & m2));
+}
+
 // atomicAdd whose result is wanted much LATER, by the issuing lane only.  The compiler turns `if (lane == 0) x =
 // atomicAdd(p, 1)` into its warp-aggregated form — ballot, one atomic, a SHUFFLE of the result to every lane — and the
 // shuffle waits for the round trip to L2 on the spot (ncu: 8 % of the inversion kernel's main-warp cycles).  Inline PTX
@@ -393,7 +400,9 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
         // (R' omega)[c], (R' tau_xi)[c]
         const int t = tid - 104, c = t % 3;
         const int o = (t < 3) ? CMPC_REC_W : CMPC_REC_FDIST;
-        sScal[16 + t] = R[c] * (double)rec[o + 0] + R[3 + c] * (double)rec[o + 1] + R[6 + c] * (double)rec[o + 2];
+        // (column c of R picked with integer masks: R[c] with a run-time c would move all of R to local memory)
+        sScal[16 + t] = pick3(R[0], R[1], R[2], c) * (double)rec[o + 0] + pick3(R[3], R[4], R[5], c) * (double)rec[o + 1] +
+                        pick3(R[6], R[7], R[8], c) * (double)rec[o + 2];
       } else if (tid < 116) {
         const int t = tid - 110;
         sScal[1 + t] = (double)rec[CMPC_REC_WEIGHTS + (t < 3 ? 3 + t : 6 + t)];  // position, velocity weights
@@ -506,7 +515,8 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
 
       // ---- D. this warp's tiles of the bordered matrix [H g; g' .] (row 63 = g, never pivoted) ----
       const int nblk = (n + 7) >> 3;
-      double tl[4][2], th[8][2];  // tile rows ILO (J <= ILO) and IHI (J <= IHI)
+      // tile rows ILO (J <= ILO, J < 4) and IHI (J <= IHI); a tile pair leaves for the workspace slot (accumulator
+      // layout, scaled) as soon as it is formed — held back in arrays the 24 doubles went to local memory
       {
         int rah[2], rpo[2], xs0[2], xs2[2];
 #pragma unroll
@@ -526,6 +536,7 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
         for (int J = 0; J < 8; J++) {
           if (J <= IHI) {
             const int2 info2 = *reinterpret_cast<const int2*>(rowinfo + 8 * J + 2 * q);
+            double vv[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // [t][e]
 #pragma unroll
             for (int e = 0; e < 2; e++) {
               const int info = e ? info2.y : info2.x;
@@ -550,27 +561,15 @@ __global__ void __launch_bounds__(MMA_NT, MINB) cmpc_assemble_mma_kernel(const _
                 if (I == J && i == j) v += (i < n) ? alpha2s : 0.5;  // alpha; 1/2 on the padding diagonal
                 if (t == 1 && brow) v = (j < n) ? g[j] : (j == 63 ? 0.5 : 0.0);                // border row
                 if (t == 1 && I == 7 && J == 7 && j == 63 && i < 63) v = (i < n) ? g[i] : 0.0;  // border column in tile (7,7)
-                if (t == 0) tl[J < 4 ? J : 0][e] = v;
-                else th[J][e] = v;
+                vv[t][e] = v;
               }
             }
+            if (J < 4 && J <= ILO) *reinterpret_cast<double2*>(slot + tix(ILO, J) * 64 + lane * 2) = make_double2(vv[0][0], vv[0][1]);
+            *reinterpret_cast<double2*>(slot + tix(IHI, J) * 64 + lane * 2) = make_double2(vv[1][0], vv[1][1]);
           }
         }
       }
-      // ---- tiles (accumulator layout, scaled) and the scale to the workspace slot for the sweep kernel ----
       {
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-          const int I = t ? IHI : ILO;
-#pragma unroll
-          for (int J = 0; J < 8; J++) {
-            if (t == 0 && J >= 4) continue;
-            if (J <= I) {
-              const double a0 = t ? th[J][0] : tl[J < 4 ? J : 0][0], a1 = t ? th[J][1] : tl[J < 4 ? J : 0][1];
-              *reinterpret_cast<double2*>(slot + tix(I, J) * 64 + lane * 2) = make_double2(a0, a1);
-            }
-          }
-        }
         for (int j = tid; j < n; j += NT) slot[P.qws_goff + j] = g[j];
         if (tid == 0) slot[P.qws_goff + 2 * P.nmax] = scale;
       }

@@ -249,10 +249,16 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
             __syncwarp();
           }
           // slack of the candidate row (held by lane p & 31, register p >> 5)
-          double sp = 0.0;
+          // (picked with integer masks: a chain of `if (j == p >> 5) sp = s[j]` is turned into an indexed load by the
+          //  compiler, which moves s[] — read and written by every iteration — from registers to local memory)
+          int sph = 0, spl = 0;
 #pragma unroll
-          for (int j = 0; j < MPL; j++)
-            if (j == (p >> 5)) sp = s[j];
+          for (int j = 0; j < MPL; j++) {
+            const int pick = -(int)(j == (p >> 5));
+            sph |= __double2hiint(s[j]) & pick;
+            spl |= __double2loint(s[j]) & pick;
+          }
+          double sp = __hiloint2double(sph, spl);
           sp = __shfl_sync(0xffffffffu, sp, p & 31);
           const double rho2_inv = dependent ? 0.0 : fast_rcp(rho2);
           const double t2 = dependent ? 1e300 : -sp * rho2_inv;
