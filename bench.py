@@ -50,7 +50,7 @@ METRIC = "cmpc_qp_solves_per_sec_h10_batched"
 L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (bytes), from the committed ncu --set full capture
 # (profiles/r2_ncu_full_summary.txt; cold cache: ncu flushes L2 between kernels)
-NCU_TRAFFIC = {"assemble": 43.1e6, "invert": 100.6e6, "dual": 29.3e6, "fused": None}
+NCU_TRAFFIC = {"assemble": 25.9e6, "invert": 97.5e6, "dual": 29.3e6, "fused": None}
 
 
 WORKLOADS = {
