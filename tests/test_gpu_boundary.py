@@ -225,6 +225,38 @@ def test_options_replace_environment_switches(built_lib):
     b.close()
 
 
+def test_inversion_kernel_switches_agree(built_lib):
+    """The pivot blocks of the n <= 63 inversion kernel by the fp32 chain + FP64 Newton steps (default) and by the FP64
+    chain (inv_f32 = 0), the panel refinement never / always / by the default threshold: the same forces to rounding on a
+    well conditioned batch, and on a badly conditioned one (alpha = 1e-6) every variant WITH the refinement agrees —
+    without it the FP64 chain is 13 N off there (profiles/r2_illcond_accuracy.txt), which is why it exists."""
+    h, B = 10, 512
+    inst = synth.make_batch(B, horizon=h, seed=77, gaits=("trot", "pace"), spread=1.5)
+    hard = dict(inst)
+    hard["alpha"] = np.full(B, 1e-6, np.float32)
+    w = np.array(inst["weights"], copy=True)
+    w[:, [0, 7]] = 0.0                                   # unweighted roll and y velocity: H conditioned ~1e5
+    hard["weights"] = w
+
+    def run(data, **opts):
+        b = engine.Batch(B, options=opts)
+        b.setup(data["dt"], h, data["mu"], data["f_max"])
+        res = b.solve_host(data)
+        b.close()
+        assert (res["status"] == engine.ST_SOLVED).all(), opts
+        return res
+
+    base = run(inst)
+    for opts in ({"inv_f32": 0}, {"inv_refine": -1}, {"inv_refine": 0}, {"inv_f32": 0, "inv_refine": 0}):
+        res = run(inst, **opts)
+        assert np.abs(res["forces"] - base["forces"]).max() < 1e-7, opts
+        assert (res["active"] == base["active"]).all(), opts
+    hbase = run(hard)
+    for opts in ({"inv_f32": 0}, {"inv_refine": 0}, {"inv_f32": 0, "inv_refine": 0}, {"path_fused": 1}):
+        res = run(hard, **opts)
+        assert np.abs(res["forces"] - hbase["forces"]).max() < 2e-6, opts
+
+
 def test_commands_reject_a_changed_robot_count(built_lib):
     h, B = 10, 64
     b = engine.Batch(B)
