@@ -181,4 +181,34 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return r;
 }
 
+
+// DMMA and shared-memory fragment load that stay in program order against each other (volatile): where the issue order
+// is part of the design — the register allocator otherwise recycles ONE register pair for successive B fragments when the
+// warp is short of registers, and every DMMA then waits a shared-memory round trip
+__device__ __forceinline__ void dmma884v(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds_f64v(const double* p) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+
+// one of three doubles by a run-time index, without turning the operands into an indexable (local-memory) array
+__device__ __forceinline__ double pick3(double a0, double a1, double a2, int c) {
+  const int m0 = -(int)(c == 0), m1 = -(int)(c == 1), m2 = -(int)(c == 2);
+  return __hiloint2double((__double2hiint(a0) & m0) | (__double2hiint(a1) & m1) | (__double2hiint(a2) & m2),
+                          (__double2loint(a0) & m0) | (__double2loint(a1) & m1) | (__double2loint(a2) & m2));
+}
+
+// atomicAdd whose result is wanted much LATER, by the issuing lane only.  The compiler turns `if (lane == 0) x =
+// atomicAdd(p, 1)` into its warp-aggregated form — ballot, one atomic, a SHUFFLE of the result to every lane — and the
+// shuffle waits for the round trip to L2 on the spot (ncu: 8 % of the inversion kernel's main-warp cycles).  Inline PTX
+// is left alone.
+__device__ __forceinline__ int atom_add_later(int* p, int v) {
+  int old;
+  asm volatile("atom.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
 }  // namespace

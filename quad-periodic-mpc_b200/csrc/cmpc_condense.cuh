@@ -153,9 +153,14 @@ __device__ __forceinline__ void sweep_blocked(double (&A)[S::TM][S::TN], int n, 
 #pragma unroll
       for (int bb = 0; bb < TN; bb++) {
         const int j = tx + TX * bb;
+        // the eight panel entries up front (volatile loads): with the tile in registers the allocator otherwise recycles
+        // one register pair and every DFMA of the chain waits a shared-memory round trip
+        double pv[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) pv[q] = lds_f64v(pan + q * PS + j);
         double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc = fma(di[q], pan[q * PS + j], acc);
+        for (int q = 0; q < 8; q++) acc = fma(di[q], pv[q], acc);
         mm[ty * PS + j] = acc;
         mreg[bb] = acc;
       }
