@@ -137,7 +137,13 @@ int cmpc_batch_setup(cmpc_batch* b, double dt, int horizon, double mu, double f_
 int cmpc_batch_set_robot(cmpc_batch* b, double mass, const double inertia_diag[3]);
 /* Diagnostic / test switches (which kernel path, capacity tiers, stream count ...; the keys are listed next to
  * cmpc_batch_set_option in csrc/cmpc_api.cu).  The library reads NO environment variable on any solve path: a
- * switch exists only through this call.  Drains the batch and drops its cached launch plans. */
+ * switch exists only through this call.  Drains the batch and drops its cached launch plans.
+ * Two of them concern accuracy rather than speed: "inv_refine" (default 1024; -1 never, 0 always) is the size of a
+ * pivot-block inverse above which the blocked sweeps correct their panel once — what keeps instances with a badly
+ * conditioned Hessian (alpha ~1e-6, unweighted states) within 1e-6 N of qpOASES; "inv_f32" (default 1) lets the
+ * n <= 63 inversion kernel seed its pivot-block inverses in fp32 and finish them with Newton steps in FP64 (0: FP64
+ * chain).  "submit_copy" (default 0) hands the results of cmpc_batch_submit_bound to the copy engine: faster from four
+ * batches in flight on, slower below. */
 int cmpc_batch_set_option(cmpc_batch* b, const char* key, int value);
 /* Pack `count` host instances into pinned records and copy them to the device (async on the batch stream). */
 int cmpc_batch_upload(cmpc_batch* b, int count, const cmpc_inputs* in);
