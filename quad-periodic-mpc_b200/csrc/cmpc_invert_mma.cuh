@@ -1,20 +1,18 @@
 // Inversion kernel of the pipeline for reduced problems of up to 63 variables: K = H^-1 and x0 = -K g by a
-// blocked symmetric sweep on the FP64 tensor cores (DMMA m8n8k4), ONE WARP PER INSTANCE, one warp per CTA.
+// blocked symmetric sweep on the FP64 tensor cores (DMMA m8n8k4), one MAIN WARP PER INSTANCE.
 //
 // The assembly kernel (cmpc_condense_mma.cuh) left the scaled, bordered matrix [H g; g' .] of the instance as
 // its 36 lower-triangular 8 x 8 tiles in DMMA accumulator layout.  A warp loads them into registers
 // (72 doubles per lane), runs up to eight block steps and stores -(A - 2 diag) scale back in place:
-//   1. invert the diagonal tile (s, s) in registers (Gauss-Jordan over warp shuffles, serial chain of 8
-//      pivots) and publish the pivot rows as an 8 x 64 panel C in warp-private shared memory (tiles
-//      (s, J<=s) as they are, tiles (I>s, s) transposed: the matrix is symmetric), D - I in the diagonal
-//      block; tile indices are compile-time constants inside a switch over s;
-//   2. M = -D^-1 C: 16 DMMAs, the two k-steps of a tile eight DMMAs apart;
+//   1. publish the pivot rows as an 8 x 64 panel C in warp-private shared memory (tiles (s, J<=s) as they are,
+//      tiles (I>s, s) transposed: the matrix is symmetric), D - I in the diagonal block; tile indices are
+//      compile-time constants inside a switch over s; the inverse of the diagonal tile (s, s) comes from a helper
+//      warp (cmpc_invert_ws_kernel below);
+//   2. M = -D^-1 C: 16 DMMAs, four tiles at a time, their B fragments loaded up front;
 //   3. every tile (I, J) += C_I' M_J: 72 independent DMMAs, the two k-steps of a tile 36 DMMAs apart.
-// No block barrier anywhere: warps work on different instances and hide each other's pivot chains.  Measured
-// (profiles/): the DMMA pipe is ~47 % busy at ten warps per SM; variants that form the next pivot-block
-// inverse one step ahead between the update DMMAs, or that split an instance over two warps to double the
-// warps per SM, measured the same or slower and were dropped.
+// No block barrier anywhere: warps work on different instances.
 // Row 63 (the border, g) is never pivoted and ends as g' H^-1 (see cmpc_condense_mma.cuh).
+// (The single-warp form of round 1 — the same warp inverts the diagonal tile — is kept under CMPC_EXPERIMENTS.)
 #pragma once
 
 namespace {
@@ -227,16 +225,19 @@ __global__ void __launch_bounds__(32 * INV_WPC) __maxnreg__(MINB) cmpc_invert_mm
 #endif  // CMPC_EXPERIMENTS
 
 // ------------------------------------------------------------------------------------------------------------
-// Warp-specialised variant: the serial part of a block step — the 8-pivot chain that inverts the diagonal tile,
-// 46 % of an instance's cycles in the kernel above — moves to a HELPER warp.  A CTA is two warpgroups: four
-// main warps (one instance each, all 36 tiles in registers; setmaxnreg raises them to 168 registers) and four
+// Warp-specialised kernel: the serial part of a block step — the 8-pivot chain that inverts the diagonal tile,
+// 46 % of an instance's cycles when the same warp does it — belongs to a HELPER warp.  A CTA is two warpgroups: four
+// main warps (one instance each, all 36 tiles in registers; setmaxnreg raises them to 216 registers) and four
 // helper warps (setmaxnreg drops them to 40).  Main warp w and helper warp w + 4 sit on the same SM sub-partition
-// and talk through two named barriers and 1 KB of shared memory:
+// and talk through two named barriers and 1.5 KB of shared memory:
 //   main:    ... bar.sync(DV); column block s+1 of M and the update of tile (s+1, s+1) FIRST (four DMMAs), park the
 //            tile in shared memory, bar.arrive(TILE); M = -D^-1 C; the 72 update DMMAs of step s; publish panel s+1 ...
-//   helper:  bar.sync(TILE); invert the parked tile (Gauss-Jordan over shuffles); write -D^-1; bar.arrive(DV)
+//   helper:  bar.sync(TILE); invert the parked tile; write -D^-1; bar.arrive(DV)
 // so the pivot chain of step s+1 runs while the main warp issues the update DMMAs of step s.  Two CTAs per SM
 // (the register file: 2 x 128 x (216 + 40)), eight instances per SM, two main warps per FP64 tensor pipe.
+// The helper's chain runs in fp32 and is finished by Newton steps X <- X + X (I - D X) in FP64 on the tensor cores
+// (P.inv_f32; an FP64 instruction of the helper queues behind the main warps' DMMAs, fp32 and integer ones do not);
+// block steps whose pivot-block inverse is large get one residual correction of M (P.inv_refine).  DESIGN.md §4.2.
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr int WS_MAIN = 4;                                   // main warps (= instances in flight) per CTA
