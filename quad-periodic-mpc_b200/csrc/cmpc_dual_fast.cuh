@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
 
   const int count = P.count_ptr ? min(*P.count_ptr, P.count) : P.count;
   const double mu_inv = P.mu_inv;
-  double flops_acc = 0.0;
+  unsigned flops_acc = 0u;  // integer: the flop count of an iteration costs no FP64 instruction
 #ifdef CMPC_CANARY
   canary_fill(base, cv.guard, cv.nguard, lane, 32);
 #endif
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
           }
           if (lane < q) u = fma(-t, rr, u);
           up += t;
-          flops_acc += 2.0 * (4.0 * n + 4.0 * q + (double)q * q + (double)n * q + 4.0 * m + n);
+          flops_acc += 2u * (unsigned)(5 * n + 4 * q + q * q + n * q + 4 * m);
           if (full) {
             if (q >= qcap) { status = CMPC_ST_WSOVERFLOW; done = true; break; }
             if (lane == (p & 31)) amask |= 1u << (p >> 5);
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
 #pragma unroll
             for (int e = 0; e < NPL; e++) KN[q * NS + lane + 32 * e] = kn[e];
             q++;
-            flops_acc += 2.0 * (double)q * q;
+            flops_acc += 2u * (unsigned)(q * q);
             __syncwarp();
             if (!more) done = true;
             p = pn;
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
             if (lane == last) { sact = -1; u = 0.0; }
           }
           q--;
-          flops_acc += 2.0 * (double)q * q;
+          flops_acc += 2u * (unsigned)(q * q);
           __syncwarp();
         }
       }
@@ -501,5 +501,5 @@ __global__ void __launch_bounds__(32 * WPC) cmpc_dual_fast_kernel(const __grid_c
   __syncwarp();
   canary_check(base, cv.guard, cv.nguard, lane, 32, "cmpc_dual_fast_kernel");
 #endif
-  if (lane == 0 && P.flops && flops_acc > 0.0) atomicAdd(P.flops + CMPC_K_DUAL, (unsigned long long)flops_acc);
+  if (lane == 0 && P.flops && flops_acc) atomicAdd(P.flops + CMPC_K_DUAL, (unsigned long long)flops_acc);
 }
