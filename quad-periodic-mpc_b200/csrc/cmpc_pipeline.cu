@@ -129,7 +129,7 @@ size_t cmpc_condense_smem_bytes(int horizon, int nmax, int cshape, bool adapt) {
 }
 
 int cmpc_condense_max_ctas_per_sm(int cshape, size_t smem, bool adapt) {
-  if (cshape == CMPC_CSHAPE_MMA64) return adapt ? occ_mma_t<true, 6>(smem) : occ_mma_t<false, 6>(smem);
+  if (cshape == CMPC_CSHAPE_MMA64) return adapt ? occ_mma_t<true, 6>(smem) : occ_mma_t<false, 7>(smem);
   CMPC_CDISPATCH(occ_condense_t, smem)
 }
 
@@ -140,7 +140,7 @@ int cmpc_launch_condense(const CmpcParams& P, int cshape, int grid, void* stream
   const size_t smem = cmpc_condense_smem_bytes(P.horizon, P.nmax, cshape, adapt);
   cudaStream_t st = (cudaStream_t)stream;
   if (cshape == CMPC_CSHAPE_MMA64)
-    return adapt ? launch_mma_t<true, 6>(P, grid, smem, st) : launch_mma_t<false, 6>(P, grid, smem, st);
+    return adapt ? launch_mma_t<true, 6>(P, grid, smem, st) : launch_mma_t<false, 7>(P, grid, smem, st);
   CMPC_CDISPATCH(launch_condense_t, P, grid, smem, st)
 }
 
